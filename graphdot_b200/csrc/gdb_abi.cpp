@@ -1,0 +1,665 @@
+// gdb_abi.cpp -- host side of the C ABI in include/graphdot_b200.h:
+// device context, NVRTC program cache, graph-set upload and solve launches.
+//
+// Replaces the pycuda plumbing of reference
+// graphdot/kernel/marginalized/_backend_cuda.py (context :49-61, JIT :118-155,
+// code generation :157-228, launch :247-367) and graphdot/cuda/*.py.
+// CUDA runtime (static) is used for memory/streams/events on the device's
+// primary context; the driver entry points needed for NVRTC modules are
+// fetched through cudaGetDriverEntryPoint, so the library loads (and its
+// pure-host functions work) on machines without a GPU driver.
+#include <cuda.h>
+#include <cuda_runtime_api.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "gdb_internal.h"
+
+extern const char *const gdb_embedded_prelude;
+extern const char *const gdb_embedded_solver;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string t_last_error;
+
+int gdb_fail(int code, const char *fmt, ...) {
+    char buf[2048];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_last_error = buf;
+    return code;
+}
+
+extern "C" const char *gdb_last_error(void) { return t_last_error.c_str(); }
+extern "C" const char *gdb_version(void) { return "graphdot_b200 0.1.0 (sm_100a, NVRTC)"; }
+extern "C" void gdb_free(void *p) { free(p); }
+
+extern "C" const char *gdb_solver_template(void) {
+    static std::string joined = std::string(gdb_embedded_prelude) + "\n/* <generated splice> */\n" + gdb_embedded_solver;
+    return joined.c_str();
+}
+
+#define RT(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return gdb_fail(GDB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define DRV(ctx, call)                                                                   \
+    do {                                                                                 \
+        CUresult r_ = (call);                                                            \
+        if (r_ != CUDA_SUCCESS) {                                                        \
+            const char *s_ = nullptr;                                                    \
+            if ((ctx)->cuGetErrorString) (ctx)->cuGetErrorString(r_, &s_);               \
+            return gdb_fail(GDB_ERR_CUDA, "%s: %s", #call, s_ ? s_ : "unknown driver error"); \
+        }                                                                                \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t cap = 0;
+};
+
+struct gdb_context_s {
+    int device = 0;
+    cudaDeviceProp prop{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    // driver entry points
+    CUresult (*cuModuleLoadData)(CUmodule *, const void *) = nullptr;
+    CUresult (*cuModuleUnload)(CUmodule) = nullptr;
+    CUresult (*cuModuleGetFunction)(CUfunction *, CUmodule, const char *) = nullptr;
+    CUresult (*cuModuleGetGlobal)(CUdeviceptr *, size_t *, CUmodule, const char *) = nullptr;
+    CUresult (*cuFuncGetAttribute)(int *, CUfunction_attribute, CUfunction) = nullptr;
+    CUresult (*cuFuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+    CUresult (*cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                               CUstream, void **, void **) = nullptr;
+    CUresult (*cuOccupancyMaxActiveBlocksPerMultiprocessor)(int *, CUfunction, int, size_t) = nullptr;
+    CUresult (*cuGetErrorString)(CUresult, const char **) = nullptr;
+    // persistent device buffers, grown on demand
+    DevBuf jobs, starts, gram, grad, scratch, counters;
+    std::mutex mu;
+    std::map<std::string, gdb_program_t> programs;  // source text -> program
+};
+
+static int dev_reserve(DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return GDB_OK;
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    RT(cudaMalloc(&b.ptr, want));
+    b.cap = want;
+    return GDB_OK;
+}
+
+template<class F> static int load_entry(const char *name, F *&fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    RT(cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &st));
+    if (!p || st != cudaDriverEntryPointSuccess) return gdb_fail(GDB_ERR_CUDA, "driver entry point %s unavailable", name);
+    fn = reinterpret_cast<F *>(p);
+    return GDB_OK;
+}
+
+extern "C" int gdb_context_create(int device, gdb_context_t *out) {
+    if (!out) return gdb_fail(GDB_ERR_INVALID, "gdb_context_create: null out");
+    int n = 0;
+    RT(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return gdb_fail(GDB_ERR_CUDA, "CUDA device %d not present (%d visible)", device, n);
+    RT(cudaSetDevice(device));
+    RT(cudaFree(0));  // establishes the primary context
+    gdb_context_s *c = new gdb_context_s;
+    c->device = device;
+    RT(cudaGetDeviceProperties(&c->prop, device));
+    if (c->prop.major < 10)
+        fprintf(stderr, "graphdot_b200: warning: device %s is sm_%d%d; kernels are built for sm_100a\n", c->prop.name,
+                c->prop.major, c->prop.minor);
+    RT(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) RT(cudaEventCreate(&e));
+    int rc;
+    if ((rc = load_entry("cuModuleLoadData", c->cuModuleLoadData))) return rc;
+    if ((rc = load_entry("cuModuleUnload", c->cuModuleUnload))) return rc;
+    if ((rc = load_entry("cuModuleGetFunction", c->cuModuleGetFunction))) return rc;
+    if ((rc = load_entry("cuModuleGetGlobal", c->cuModuleGetGlobal))) return rc;
+    if ((rc = load_entry("cuFuncGetAttribute", c->cuFuncGetAttribute))) return rc;
+    if ((rc = load_entry("cuFuncSetAttribute", c->cuFuncSetAttribute))) return rc;
+    if ((rc = load_entry("cuLaunchKernel", c->cuLaunchKernel))) return rc;
+    if ((rc = load_entry("cuOccupancyMaxActiveBlocksPerMultiprocessor", c->cuOccupancyMaxActiveBlocksPerMultiprocessor)))
+        return rc;
+    if ((rc = load_entry("cuGetErrorString", c->cuGetErrorString))) return rc;
+    RT(cudaMalloc(&c->counters.ptr, 64));
+    c->counters.cap = 64;
+    *out = c;
+    return GDB_OK;
+}
+
+extern "C" int gdb_context_info(gdb_context_t c, gdb_device_info *o) {
+    if (!c || !o) return gdb_fail(GDB_ERR_INVALID, "gdb_context_info: null argument");
+    memset(o, 0, sizeof *o);
+    o->device = c->device;
+    o->sm_count = c->prop.multiProcessorCount;
+    o->cc_major = c->prop.major;
+    o->cc_minor = c->prop.minor;
+    o->max_smem_per_block_optin = (int)c->prop.sharedMemPerBlockOptin;
+    o->max_smem_per_sm = (int)c->prop.sharedMemPerMultiprocessor;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+    o->clock_khz = khz;
+    o->l2_bytes = c->prop.l2CacheSize;
+    o->total_mem = c->prop.totalGlobalMem;
+    snprintf(o->name, sizeof o->name, "%s", c->prop.name);
+    return GDB_OK;
+}
+
+extern "C" int gdb_context_synchronize(gdb_context_t c) {
+    if (!c) return gdb_fail(GDB_ERR_INVALID, "null context");
+    RT(cudaSetDevice(c->device));
+    RT(cudaStreamSynchronize(c->stream));
+    return GDB_OK;
+}
+
+extern "C" int gdb_program_destroy(gdb_program_t p);
+
+extern "C" int gdb_context_destroy(gdb_context_t c) {
+    if (!c) return GDB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &kv : c->programs) {
+        gdb_program_t p = kv.second;
+        kv.second = nullptr;
+        (void)p;  // programs are owned by their handles; the cache only aliases them
+    }
+    for (DevBuf *b : {&c->jobs, &c->starts, &c->gram, &c->grad, &c->scratch, &c->counters})
+        if (b->ptr) cudaFree(b->ptr);
+    for (auto &e : c->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return GDB_OK;
+}
+
+extern "C" int gdb_host_alloc(size_t bytes, void **out) {
+    if (!out) return gdb_fail(GDB_ERR_INVALID, "gdb_host_alloc: null out");
+    *out = nullptr;
+    RT(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return GDB_OK;
+}
+
+extern "C" int gdb_host_free(void *p) {
+    if (p) RT(cudaFreeHost(p));
+    return GDB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// program
+// ---------------------------------------------------------------------------
+struct gdb_program_s {
+    gdb_context_t ctx = nullptr;
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+    unsigned layout[8] = {};
+    std::string source, log;
+    gdb_program_info info{};
+    uint32_t theta_size[3] = {};
+    int eval_gradient = 0, nodal = 0;
+    int refcount = 1;
+};
+
+static void emit_functor(std::ostringstream &o, const char *name, const gdb_functor_src &f, bool binary) {
+    const char *args = binary ? "X const &x1, X const &x2" : "X const &n";
+    o << "struct " << name << "_theta_t { " << (f.theta_decl ? f.theta_decl : "") << " };\n";
+    o << "struct " << name << "_t : " << name << "_theta_t {\n";
+    o << "    static constexpr int jac_dims = " << f.n_jac << ";\n";
+    o << "    template<class X> __device__ __forceinline__ float operator()(" << args << ") const {\n";
+    o << "        return (" << f.expr << ");\n    }\n";
+    o << "    template<class X> __device__ __forceinline__ void jacobian(" << args << ", float *j) const {\n";
+    for (uint32_t k = 0; k < f.n_jac; ++k) o << "        j[" << k << "] = (" << f.jac[k] << ");\n";
+    o << "    }\n};\n";
+}
+
+static int pick_block(const gdb_program_desc *d) {
+    int b = d->block_size;
+    if (b <= 0) b = 64;
+    if (b % 32 || b > 1024) return -1;
+    return b;
+}
+
+static int render(const gdb_program_desc *d, std::string &src) {
+    if (!d || !d->node_decl || !d->edge_decl || !d->node_kernel.expr || !d->edge_kernel.expr || !d->p_start.expr)
+        return gdb_fail(GDB_ERR_INVALID, "gdb_program_desc: missing source strings");
+    const int block = pick_block(d);
+    if (block < 0) return gdb_fail(GDB_ERR_INVALID, "block_size must be a multiple of 32 up to 1024");
+    if (d->nodal < 0 || d->nodal > 2 || d->lmin < 0 || d->lmin > 1) return gdb_fail(GDB_ERR_INVALID, "invalid traits");
+    if (d->eval_gradient && d->nodal != GDB_NODAL_NONE)
+        return gdb_fail(GDB_ERR_INVALID, "nodal gradients are not implemented by this engine yet");
+    std::ostringstream o;
+    o << gdb_embedded_prelude << "\n";
+    o << "// ---- generated splice ----\n";
+    o << "#define GDB_BLOCK " << block << "\n";
+    o << "#define GDB_MIN_BLOCKS " << std::max(1, std::min(32, 2048 / block) / 2) << "\n";
+    o << "#define GDB_WEIGHTED " << (d->weighted ? 1 : 0) << "\n";
+    o << "#define GDB_DIAGONAL " << (d->diagonal ? 1 : 0) << "\n";
+    o << "#define GDB_SYMMETRIC " << (d->symmetric ? 1 : 0) << "\n";
+    o << "#define GDB_NODAL " << d->nodal << "\n";
+    o << "#define GDB_LMIN " << d->lmin << "\n";
+    o << "#define GDB_GRADIENT " << (d->eval_gradient ? 1 : 0) << "\n";
+    o << "#define GDB_NP " << d->p_start.n_jac << "\n";
+    o << "#define GDB_NV " << d->node_kernel.n_jac << "\n";
+    o << "#define GDB_NE " << d->edge_kernel.n_jac << "\n";
+    o << "struct node_t { " << d->node_decl << " };\n";
+    o << "struct edge_label_t { " << d->edge_decl << " };\n";
+    o << "static_assert(sizeof(node_t) == " << d->node_size << ", \"node_t layout differs from the host dtype\");\n";
+    o << "static_assert(sizeof(edge_label_t) == " << d->edge_label_size
+      << ", \"edge label layout differs from the host dtype\");\n";
+    o << "static_assert(alignof(edge_label_t) == " << d->edge_label_align << ", \"edge label alignment\");\n";
+    emit_functor(o, "node_kernel", d->node_kernel, true);
+    emit_functor(o, "edge_kernel", d->edge_kernel, true);
+    emit_functor(o, "p_start", d->p_start, false);
+    const gdb_functor_src *fs[3] = {&d->node_kernel, &d->edge_kernel, &d->p_start};
+    const char *names[3] = {"node_kernel", "edge_kernel", "p_start"};
+    for (int k = 0; k < 3; ++k)
+        if (fs[k]->theta_size)
+            o << "static_assert(sizeof(" << names[k] << "_theta_t) == " << fs[k]->theta_size << ", \"" << names[k]
+              << " hyper-parameter layout differs from the host dtype\");\n";
+    o << "// ---- end of generated splice ----\n";
+    o << gdb_embedded_solver << "\n";
+    src = o.str();
+    return GDB_OK;
+}
+
+extern "C" int gdb_render_source(const gdb_program_desc *d, char **out) {
+    if (!out) return gdb_fail(GDB_ERR_INVALID, "null out");
+    std::string s;
+    int rc = render(d, s);
+    if (rc) return rc;
+    *out = static_cast<char *>(malloc(s.size() + 1));
+    if (!*out) return gdb_fail(GDB_ERR_NOMEM, "out of memory");
+    memcpy(*out, s.c_str(), s.size() + 1);
+    return GDB_OK;
+}
+
+static int compile_cubin(const std::string &src, const char *extra, std::vector<char> &cubin, std::string &log) {
+    nvrtcProgram prog;
+    nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "mlgk_solver.cu", 0, nullptr, nullptr);
+    if (r != NVRTC_SUCCESS) return gdb_fail(GDB_ERR_COMPILE, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
+    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "--use_fast_math", "-lineinfo",
+                                     "-default-device", "--extra-device-vectorization"};
+    if (extra) {
+        std::istringstream is(extra);
+        std::string tok;
+        while (is >> tok) opts.push_back(tok);
+    }
+    std::vector<const char *> copts;
+    for (auto &s : opts) copts.push_back(s.c_str());
+    r = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
+    size_t ls = 0;
+    nvrtcGetProgramLogSize(prog, &ls);
+    log.assign(ls ? ls - 1 : 0, '\0');
+    if (ls > 1) nvrtcGetProgramLog(prog, &log[0]);
+    if (r != NVRTC_SUCCESS) {
+        nvrtcDestroyProgram(&prog);
+        return gdb_fail(GDB_ERR_COMPILE, "NVRTC compilation failed: %s\n%s", nvrtcGetErrorString(r), log.c_str());
+    }
+    size_t cs = 0;
+    nvrtcGetCUBINSize(prog, &cs);
+    cubin.resize(cs);
+    nvrtcGetCUBIN(prog, cubin.data());
+    nvrtcDestroyProgram(&prog);
+    return GDB_OK;
+}
+
+extern "C" int gdb_program_compile_only(const gdb_program_desc *d, uint64_t *cubin_bytes) {
+    std::string src, log;
+    int rc = render(d, src);
+    if (rc) return rc;
+    std::vector<char> cubin;
+    if ((rc = compile_cubin(src, d->extra_options, cubin, log))) return rc;
+    if (cubin_bytes) *cubin_bytes = cubin.size();
+    return GDB_OK;
+}
+
+extern "C" int gdb_program_create(gdb_context_t c, const gdb_program_desc *d, gdb_program_t *out) {
+    if (!c || !out) return gdb_fail(GDB_ERR_INVALID, "gdb_program_create: null argument");
+    std::string src;
+    int rc = render(d, src);
+    if (rc) return rc;
+    std::string key = src + "\n//opts:" + (d->extra_options ? d->extra_options : "");
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        auto it = c->programs.find(key);
+        if (it != c->programs.end() && it->second) {
+            it->second->refcount++;
+            it->second->info.from_cache = 1;
+            *out = it->second;
+            return GDB_OK;
+        }
+    }
+    RT(cudaSetDevice(c->device));
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<char> cubin;
+    std::string log;
+    if ((rc = compile_cubin(src, d->extra_options, cubin, log))) return rc;
+    gdb_program_s *p = new gdb_program_s;
+    p->ctx = c;
+    p->source = src;
+    p->log = log;
+    p->eval_gradient = d->eval_gradient;
+    p->nodal = d->nodal;
+    p->theta_size[0] = d->node_kernel.theta_size;
+    p->theta_size[1] = d->edge_kernel.theta_size;
+    p->theta_size[2] = d->p_start.theta_size;
+    DRV(c, c->cuModuleLoadData(&p->mod, cubin.data()));
+    DRV(c, c->cuModuleGetFunction(&p->fn, p->mod, "mlgk_solve"));
+    CUdeviceptr lay = 0;
+    size_t lay_bytes = 0;
+    DRV(c, c->cuModuleGetGlobal(&lay, &lay_bytes, p->mod, "gdb_param_layout"));
+    if (lay_bytes != sizeof p->layout) return gdb_fail(GDB_ERR_LAYOUT, "gdb_param_layout has %zu bytes", lay_bytes);
+    RT(cudaMemcpy(p->layout, reinterpret_cast<void *>(lay), sizeof p->layout, cudaMemcpyDeviceToHost));
+    if (p->layout[4] != sizeof(gdb_params_fixed_host))
+        return gdb_fail(GDB_ERR_LAYOUT, "device gdb_params_fixed is %u bytes, host mirror %zu", p->layout[4],
+                        sizeof(gdb_params_fixed_host));
+    if (p->layout[5] != d->node_size) return gdb_fail(GDB_ERR_LAYOUT, "node_t is %u bytes on device", p->layout[5]);
+    int v = 0;
+    p->info.block_size = pick_block(d);
+    c->cuFuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_NUM_REGS, p->fn);
+    p->info.num_regs = v;
+    c->cuFuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, p->fn);
+    p->info.static_smem = v;
+    c->cuFuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, p->fn);
+    p->info.local_bytes = v;
+    p->info.max_dynamic_smem = (int)c->prop.sharedMemPerBlockOptin - p->info.static_smem;
+    DRV(c, c->cuFuncSetAttribute(p->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, p->info.max_dynamic_smem));
+    p->info.n_jac = (int)p->layout[7];
+    p->info.from_cache = 0;
+    p->info.compile_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        c->programs[key] = p;
+        p->refcount++;  // the cache keeps programs alive for the context's lifetime
+    }
+    *out = p;
+    return GDB_OK;
+}
+
+extern "C" int gdb_program_info_get(gdb_program_t p, gdb_program_info *o) {
+    if (!p || !o) return gdb_fail(GDB_ERR_INVALID, "null argument");
+    *o = p->info;
+    return GDB_OK;
+}
+extern "C" const char *gdb_program_log(gdb_program_t p) { return p ? p->log.c_str() : ""; }
+extern "C" const char *gdb_program_source(gdb_program_t p) { return p ? p->source.c_str() : ""; }
+
+extern "C" int gdb_program_destroy(gdb_program_t p) {
+    if (!p) return GDB_OK;
+    if (--p->refcount > 0) return GDB_OK;
+    if (p->mod && p->ctx) p->ctx->cuModuleUnload(p->mod);
+    delete p;
+    return GDB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// graph set
+// ---------------------------------------------------------------------------
+struct gdb_graphset_s {
+    gdb_context_t ctx = nullptr;
+    gdb_layout layout{};
+    uint32_t n = 0;
+    uint8_t *host = nullptr;  // pinned image: [table | blobs]
+    uint8_t *dev = nullptr;
+    uint64_t bytes = 0, table_bytes = 0;
+    std::vector<uint32_t> n_node, blob_bytes, nnz;
+    uint32_t max_blob[2] = {0, 0};  // two largest blobs
+    uint32_t max_node[2] = {0, 0};  // two largest node counts
+};
+
+extern "C" int gdb_graphset_create(gdb_context_t c, const gdb_layout *L, uint32_t n, const void *const *blobs,
+                                   const uint64_t *blob_bytes, gdb_graphset_t *out) {
+    if (!c || !L || !n || !blobs || !blob_bytes || !out) return gdb_fail(GDB_ERR_INVALID, "gdb_graphset_create: null argument");
+    RT(cudaSetDevice(c->device));
+    gdb_graphset_s *gs = new gdb_graphset_s;
+    gs->ctx = c;
+    gs->layout = *L;
+    gs->n = n;
+    gs->table_bytes = ((uint64_t)n * sizeof(gdb_graph_ref_host) + 255u) & ~255ull;
+    uint64_t total = gs->table_bytes;
+    for (uint32_t k = 0; k < n; ++k) {
+        if (blob_bytes[k] % 16 || blob_bytes[k] < GDB_HDR_BYTES) {
+            delete gs;
+            return gdb_fail(GDB_ERR_INVALID, "graph %u: malformed blob", k);
+        }
+        total += blob_bytes[k];
+    }
+    gs->bytes = total;
+    RT(cudaHostAlloc((void **)&gs->host, total, cudaHostAllocPortable));
+    RT(cudaMalloc((void **)&gs->dev, total));
+    gdb_graph_ref_host *table = reinterpret_cast<gdb_graph_ref_host *>(gs->host);
+    uint64_t off = gs->table_bytes;
+    for (uint32_t k = 0; k < n; ++k) {
+        uint8_t *dst = gs->host + off;
+        memcpy(dst, blobs[k], blob_bytes[k]);
+        const gdb_graph_hdr_host *h = reinterpret_cast<const gdb_graph_hdr_host *>(dst);
+        if (h->blob_bytes != blob_bytes[k]) {
+            gdb_graphset_destroy(gs);
+            return gdb_fail(GDB_ERR_INVALID, "graph %u: blob size mismatch", k);
+        }
+        const uint64_t dev_base = reinterpret_cast<uint64_t>(gs->dev) + off;
+        // relocate frozen_array data pointers: blob-relative -> device address
+        for (int32_t i = 0; i < h->n_node; ++i)
+            for (uint32_t f = 0; f < L->n_node_ptr; ++f)
+                *reinterpret_cast<uint64_t *>(dst + h->off_node + (size_t)i * L->node_size + L->node_ptr_offset[f]) += dev_base;
+        if (L->n_edge_ptr) {
+            uint32_t label_off = 0, edge_size = L->edge_label_size;
+            if (L->weighted) {
+                const uint32_t a = std::max<uint32_t>(4u, L->edge_label_align);
+                label_off = (4u + L->edge_label_align - 1u) / L->edge_label_align * L->edge_label_align;
+                edge_size = (label_off + L->edge_label_size + a - 1u) / a * a;
+            }
+            for (int32_t e = 0; e < h->nnz; ++e)
+                for (uint32_t f = 0; f < L->n_edge_ptr; ++f)
+                    *reinterpret_cast<uint64_t *>(dst + h->off_edge + (size_t)e * edge_size + label_off + L->edge_ptr_offset[f]) +=
+                        dev_base;
+        }
+        table[k].blob = dev_base;
+        table[k].bytes = (uint32_t)blob_bytes[k];
+        table[k].n_node = (uint32_t)h->n_node;
+        gs->n_node.push_back((uint32_t)h->n_node);
+        gs->blob_bytes.push_back((uint32_t)blob_bytes[k]);
+        gs->nnz.push_back((uint32_t)h->nnz);
+        auto top2 = [](uint32_t *m, uint32_t v) {
+            if (v > m[0]) {
+                m[1] = m[0];
+                m[0] = v;
+            } else if (v > m[1]) {
+                m[1] = v;
+            }
+        };
+        top2(gs->max_blob, (uint32_t)blob_bytes[k]);
+        top2(gs->max_node, (uint32_t)h->n_node);
+        off += blob_bytes[k];
+    }
+    if (n == 1) {
+        gs->max_blob[1] = gs->max_blob[0];
+        gs->max_node[1] = gs->max_node[0];
+    }
+    *out = gs;
+    return gdb_graphset_upload(gs);
+}
+
+extern "C" int gdb_graphset_upload(gdb_graphset_t gs) {
+    if (!gs) return gdb_fail(GDB_ERR_INVALID, "null graph set");
+    RT(cudaSetDevice(gs->ctx->device));
+    RT(cudaMemcpyAsync(gs->dev, gs->host, gs->bytes, cudaMemcpyHostToDevice, gs->ctx->stream));
+    RT(cudaStreamSynchronize(gs->ctx->stream));
+    return GDB_OK;
+}
+
+extern "C" int gdb_graphset_bytes(gdb_graphset_t gs, uint64_t *bytes) {
+    if (!gs || !bytes) return gdb_fail(GDB_ERR_INVALID, "null argument");
+    *bytes = gs->bytes;
+    return GDB_OK;
+}
+
+extern "C" int gdb_graphset_destroy(gdb_graphset_t gs) {
+    if (!gs) return GDB_OK;
+    cudaSetDevice(gs->ctx->device);
+    if (gs->dev) cudaFree(gs->dev);
+    if (gs->host) cudaFreeHost(gs->host);
+    delete gs;
+    return GDB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// solve
+// ---------------------------------------------------------------------------
+extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gdb_solve_args *a) {
+    if (!c || !p || !gs || !a) return gdb_fail(GDB_ERR_INVALID, "gdb_solve: null argument");
+    if (p->ctx != c || gs->ctx != c) return gdb_fail(GDB_ERR_INVALID, "program / graph set belong to another context");
+    if (!a->starts || !a->gramian) return gdb_fail(GDB_ERR_INVALID, "gdb_solve: starts and gramian are required");
+    if (p->eval_gradient && !a->gradient) return gdb_fail(GDB_ERR_INVALID, "program evaluates gradients: gradient buffer required");
+    if (p->eval_gradient && a->nJ != p->layout[7])
+        return gdb_fail(GDB_ERR_INVALID, "nJ = %u but the program has %u hyper-parameters", a->nJ, p->layout[7]);
+    uint64_t n_jobs = 0;
+    if (a->job_mode == GDB_JOBS_LIST) {
+        if (!a->jobs && a->n_jobs) return gdb_fail(GDB_ERR_INVALID, "job list missing");
+        n_jobs = a->n_jobs;
+        for (uint64_t k = 0; k < 2 * n_jobs; ++k)
+            if (a->jobs[k] >= gs->n) return gdb_fail(GDB_ERR_INVALID, "job %llu references graph %u of %u", (unsigned long long)(k / 2), a->jobs[k], gs->n);
+    } else if (a->job_mode == GDB_JOBS_RECT) {
+        if (a->i1 > gs->n || a->j1 > gs->n || a->i0 > a->i1 || a->j0 > a->j1) return gdb_fail(GDB_ERR_INVALID, "job rectangle out of range");
+        n_jobs = (uint64_t)(a->i1 - a->i0) * (a->j1 - a->j0);
+    } else if (a->job_mode == GDB_JOBS_TRIU) {
+        if (a->i1 > gs->n || a->i0 > a->i1) return gdb_fail(GDB_ERR_INVALID, "job triangle out of range");
+        const uint64_t n = a->i1 - a->i0;
+        n_jobs = n * (n + 1) / 2;
+    } else {
+        return gdb_fail(GDB_ERR_INVALID, "unknown job_mode %d", a->job_mode);
+    }
+    if (a->n_starts < gs->n) return gdb_fail(GDB_ERR_INVALID, "starts has %u entries for %u graphs", a->n_starts, gs->n);
+    a->kernel_ms = a->h2d_ms = a->d2h_ms = 0.f;
+    a->cg_iterations = a->matvec_products = 0;
+    a->n_launches = 0;
+    if (n_jobs == 0) return GDB_OK;
+
+    RT(cudaSetDevice(c->device));
+    cudaStream_t st = a->stream ? static_cast<cudaStream_t>(a->stream) : c->stream;
+    const uint64_t plane = (uint64_t)a->nX * a->nY;
+    const uint64_t grad_floats = p->eval_gradient ? plane * a->nJ : 0;
+    int rc;
+    if ((rc = dev_reserve(c->gram, plane * 4))) return rc;
+    if (grad_floats && (rc = dev_reserve(c->grad, grad_floats * 4))) return rc;
+    if ((rc = dev_reserve(c->starts, (size_t)a->n_starts * 4))) return rc;
+    if (a->job_mode == GDB_JOBS_LIST && (rc = dev_reserve(c->jobs, n_jobs * 8))) return rc;
+
+    // ---- launch configuration -------------------------------------------------
+    const int block = p->info.block_size;
+    const int nvec = p->eval_gradient ? 6 : 5;
+    const uint64_t maxN = (uint64_t)gs->max_node[0] * (a->job_mode == GDB_JOBS_LIST || true ? gs->max_node[0] : gs->max_node[1]);
+    const uint64_t maxNpad = (maxN + 3) & ~3ull;
+    const uint64_t graphs_need = (uint64_t)gs->max_blob[0] + gs->max_blob[1];
+    const uint64_t full_need = graphs_need + nvec * maxNpad * 4;
+    uint64_t cap = (uint64_t)p->info.max_dynamic_smem;
+    if (const char *env = getenv("GDB_SMEM_CAP")) {  // testing / tuning hook
+        const uint64_t v = strtoull(env, nullptr, 10);
+        cap = std::min<uint64_t>(cap, v & ~15ull);
+    }
+    uint64_t smem = 0;
+    bool spill = true;
+    if (full_need <= cap) {
+        smem = full_need;
+        spill = false;
+    } else if (graphs_need <= cap / 2) {
+        smem = graphs_need;  // graphs staged, vectors in the global arena
+    } else {
+        smem = 0;
+    }
+    int blocks_per_sm = 0;
+    DRV(c, c->cuOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, p->fn, block, (size_t)smem));
+    if (blocks_per_sm < 1) return gdb_fail(GDB_ERR_CUDA, "kernel does not fit on an SM (block %d, smem %llu)", block, (unsigned long long)smem);
+    uint64_t grid = (uint64_t)c->prop.multiProcessorCount * blocks_per_sm;
+    if (spill) {
+        // bound the arena: at most ~1/4 of device memory
+        const uint64_t per_cta = nvec * maxNpad * 4;
+        const uint64_t budget = c->prop.totalGlobalMem / 4;
+        grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, budget / std::max<uint64_t>(per_cta, 1)));
+        if ((rc = dev_reserve(c->scratch, grid * per_cta))) return rc;
+    }
+    grid = std::min<uint64_t>(grid, n_jobs);
+
+    // ---- inputs -----------------------------------------------------------------
+    RT(cudaEventRecord(c->ev[0], st));
+    if (a->job_mode == GDB_JOBS_LIST) RT(cudaMemcpyAsync(c->jobs.ptr, a->jobs, n_jobs * 8, cudaMemcpyHostToDevice, st));
+    RT(cudaMemcpyAsync(c->starts.ptr, a->starts, (size_t)a->n_starts * 4, cudaMemcpyHostToDevice, st));
+    RT(cudaMemsetAsync(c->counters.ptr, 0, 64, st));
+    RT(cudaMemsetAsync(c->gram.ptr, 0, plane * 4, st));
+    if (grad_floats) RT(cudaMemsetAsync(c->grad.ptr, 0, grad_floats * 4, st));
+
+    std::vector<unsigned char> params(p->layout[0], 0);
+    gdb_params_fixed_host f{};
+    f.graphs = reinterpret_cast<uint64_t>(gs->dev);
+    f.jobs = reinterpret_cast<uint64_t>(c->jobs.ptr);
+    f.starts = reinterpret_cast<uint64_t>(c->starts.ptr);
+    f.gram = reinterpret_cast<uint64_t>(c->gram.ptr);
+    f.grad = reinterpret_cast<uint64_t>(c->grad.ptr);
+    f.scratch = reinterpret_cast<uint64_t>(c->scratch.ptr);
+    f.counters = reinterpret_cast<uint64_t>(c->counters.ptr);
+    f.scratch_stride = spill ? nvec * maxNpad : 0;
+    f.n_jobs = n_jobs;
+    f.job_mode = (uint32_t)a->job_mode;
+    f.i0 = a->i0, f.i1 = a->i1, f.j0 = a->j0, f.j1 = a->j1;
+    f.nX = a->nX, f.nY = a->nY, f.nJ = a->nJ;
+    f.q = a->q, f.eps = a->eps, f.ftol = a->ftol, f.gtol = a->gtol;
+    f.smem_bytes = (uint32_t)smem;
+    memcpy(params.data(), &f, sizeof f);
+    const void *thetas[3] = {a->node_theta, a->edge_theta, a->p_theta};
+    for (int k = 0; k < 3; ++k) {
+        if (!p->theta_size[k]) continue;
+        if (!thetas[k]) return gdb_fail(GDB_ERR_INVALID, "hyper-parameter block %d missing", k);
+        if (p->layout[1 + k] + p->theta_size[k] > p->layout[0]) return gdb_fail(GDB_ERR_LAYOUT, "theta block %d overflows the parameter struct", k);
+        memcpy(params.data() + p->layout[1 + k], thetas[k], p->theta_size[k]);
+    }
+    void *kargs[1] = {params.data()};
+
+    RT(cudaEventRecord(c->ev[1], st));
+    DRV(c, c->cuLaunchKernel(p->fn, (unsigned)grid, 1, 1, (unsigned)block, 1, 1, (unsigned)smem, (CUstream)st, kargs, nullptr));
+    a->n_launches = 1;
+    RT(cudaEventRecord(c->ev[2], st));
+    unsigned long long counters[4] = {0, 0, 0, 0};
+    RT(cudaMemcpyAsync(counters, c->counters.ptr, sizeof counters, cudaMemcpyDeviceToHost, st));
+    if (!a->keep_on_device) {
+        RT(cudaMemcpyAsync(a->gramian, c->gram.ptr, plane * 4, cudaMemcpyDeviceToHost, st));
+        if (grad_floats) RT(cudaMemcpyAsync(a->gradient, c->grad.ptr, grad_floats * 4, cudaMemcpyDeviceToHost, st));
+    }
+    RT(cudaEventRecord(c->ev[3], st));
+    RT(cudaStreamSynchronize(st));
+    RT(cudaGetLastError());
+    cudaEventElapsedTime(&a->h2d_ms, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&a->kernel_ms, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&a->d2h_ms, c->ev[2], c->ev[3]);
+    a->cg_iterations = counters[1];
+    a->matvec_products = counters[2];
+    return GDB_OK;
+}
+
+extern "C" int gdb_last_outputs(gdb_context_t c, void **g, void **d) {
+    if (!c) return gdb_fail(GDB_ERR_INVALID, "null context");
+    if (g) *g = c->gram.ptr;
+    if (d) *d = c->grad.ptr;
+    return GDB_OK;
+}

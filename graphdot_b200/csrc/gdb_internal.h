@@ -1,0 +1,41 @@
+// gdb_internal.h -- definitions shared by the host translation units.
+#pragma once
+#include <cstdint>
+
+#include "../../include/graphdot_b200.h"
+
+#define GDB_HDR_BYTES 64
+
+// Host mirrors of the device structs in mlgk_solver.cuh.
+struct gdb_graph_hdr_host {
+    int32_t n_node, n_octile, nnz, n_tile;
+    uint32_t off_degree, off_node, off_octile, off_tilerow;
+    uint32_t off_edge, off_pool, blob_bytes, flags;
+    uint32_t reserved[4];
+};
+static_assert(sizeof(gdb_graph_hdr_host) == GDB_HDR_BYTES, "header layout");
+
+struct gdb_octile_host {
+    uint64_t mask;
+    uint32_t start;
+    uint16_t trow, tcol;
+};
+static_assert(sizeof(gdb_octile_host) == 16, "octile layout");
+
+struct gdb_graph_ref_host {
+    uint64_t blob;
+    uint32_t bytes, n_node;
+};
+static_assert(sizeof(gdb_graph_ref_host) == 16, "graph ref layout");
+
+struct gdb_params_fixed_host {
+    uint64_t graphs, jobs, starts, gram, grad, scratch, counters;
+    uint64_t scratch_stride, n_jobs;
+    uint32_t job_mode, i0, i1, j0, j1, nX, nY, nJ;
+    float q, eps, ftol, gtol;
+    uint32_t smem_bytes, pad0, pad1, pad2;
+};
+static_assert(sizeof(gdb_params_fixed_host) == 136, "params layout");
+
+// Records `msg` as the calling thread's last error and returns `code`.
+int gdb_fail(int code, const char *fmt, ...);

@@ -1,0 +1,175 @@
+// gdb_pack.cpp -- host-side octile packer (pure C++, no CUDA).
+//
+// Turns one graph (node AoS + undirected edge list) into the
+// position-independent device blob described in include/graphdot_b200.h.
+// Replaces the numpy packer of reference
+// graphdot/kernel/marginalized/_octilegraph.py:100-177 (degrees :113-139,
+// symmetric replication :142-147, tile sort :150-158, bit masks :160-168).
+// Differences by design: octiles are sorted by (tile row, tile column) and
+// carry one row-major mask, elements are stored row-major inside a tile and a
+// per-tile-row index (CSR over tiles) is added, because the B200 matvec
+// gathers along rows instead of scattering with atomics.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "gdb_internal.h"
+
+namespace {
+
+inline uint64_t pad16(uint64_t v) { return (v + 15u) & ~uint64_t(15); }
+
+struct Sizes {
+    uint32_t edge_size, label_off;
+    uint32_t nnz, n_octile, n_tile;
+    uint64_t off_degree, off_node, off_octile, off_tilerow, off_edge, off_pool, total;
+};
+
+struct Nz {
+    uint32_t key;  // (trow, tcol, row, col) packed: trow<<19 | tcol<<6 | row<<3 | col
+    uint32_t i, j, e;
+};
+
+bool collect(const gdb_graph_src *g, std::vector<Nz> &nz) {
+    nz.clear();
+    nz.reserve(2 * (size_t)g->n_edge);
+    for (uint32_t k = 0; k < g->n_edge; ++k) {
+        const uint32_t i = g->edge_i[k], j = g->edge_j[k];
+        if (i >= g->n_node || j >= g->n_node) return false;
+        nz.push_back({0, i, j, k});
+        if (i != j) nz.push_back({0, j, i, k});
+    }
+    for (auto &z : nz) z.key = ((z.i >> 3) << 19) | ((z.j >> 3) << 6) | ((z.i & 7) << 3) | (z.j & 7);
+    std::sort(nz.begin(), nz.end(), [](const Nz &a, const Nz &b) { return a.key < b.key; });
+    // duplicate directed entries (multi-edges): keep the last, like a dense assignment
+    size_t w = 0;
+    for (size_t r = 0; r < nz.size(); ++r) {
+        if (w > 0 && nz[w - 1].key == nz[r].key)
+            nz[w - 1] = nz[r];
+        else
+            nz[w++] = nz[r];
+    }
+    nz.resize(w);
+    return true;
+}
+
+void plan(const gdb_layout *L, const gdb_graph_src *g, const std::vector<Nz> &nz, Sizes &s) {
+    if (L->weighted) {
+        const uint32_t a = std::max<uint32_t>(4u, L->edge_label_align);
+        s.label_off = (4u + L->edge_label_align - 1u) / L->edge_label_align * L->edge_label_align;
+        s.edge_size = (s.label_off + L->edge_label_size + a - 1u) / a * a;
+    } else {
+        s.label_off = 0;
+        s.edge_size = L->edge_label_size;
+    }
+    s.nnz = (uint32_t)nz.size();
+    s.n_tile = (g->n_node + 7u) / 8u;
+    uint32_t n_oct = 0;
+    for (size_t k = 0; k < nz.size(); ++k)
+        if (k == 0 || (nz[k].key >> 6) != (nz[k - 1].key >> 6)) ++n_oct;
+    s.n_octile = n_oct;
+    s.off_degree = GDB_HDR_BYTES;
+    s.off_node = s.off_degree + pad16(4ull * g->n_node);
+    s.off_octile = s.off_node + pad16((uint64_t)L->node_size * g->n_node);
+    s.off_tilerow = s.off_octile + 16ull * s.n_octile;
+    s.off_edge = s.off_tilerow + pad16(4ull * (s.n_tile + 1));
+    s.off_pool = s.off_edge + pad16((uint64_t)s.edge_size * s.nnz);
+    s.total = s.off_pool + pad16(g->pool_bytes);
+}
+
+}  // namespace
+
+extern "C" int gdb_graph_packed_size(const gdb_layout *layout, const gdb_graph_src *g, uint64_t *bytes) {
+    if (!layout || !g || !bytes) return gdb_fail(GDB_ERR_INVALID, "gdb_graph_packed_size: null argument");
+    if (g->n_node == 0 || g->n_node >= (1u << 16)) return gdb_fail(GDB_ERR_INVALID, "graph must have 1..65535 nodes");
+    std::vector<Nz> nz;
+    if (!collect(g, nz)) return gdb_fail(GDB_ERR_INVALID, "edge end point out of range");
+    Sizes s;
+    plan(layout, g, nz, s);
+    if (s.total >= (1ull << 32)) return gdb_fail(GDB_ERR_INVALID, "packed graph exceeds 4 GiB");
+    *bytes = s.total;
+    return GDB_OK;
+}
+
+extern "C" int gdb_graph_pack(const gdb_layout *L, const gdb_graph_src *g, void *blob, uint64_t capacity) {
+    if (!L || !g || !blob) return gdb_fail(GDB_ERR_INVALID, "gdb_graph_pack: null argument");
+    std::vector<Nz> nz;
+    if (!collect(g, nz)) return gdb_fail(GDB_ERR_INVALID, "edge end point out of range");
+    Sizes s;
+    plan(L, g, nz, s);
+    if (s.total > capacity) return gdb_fail(GDB_ERR_INVALID, "gdb_graph_pack: blob too small");
+    uint8_t *base = static_cast<uint8_t *>(blob);
+    std::memset(base, 0, s.total);
+
+    gdb_graph_hdr_host *h = reinterpret_cast<gdb_graph_hdr_host *>(base);
+    h->n_node = (int32_t)g->n_node;
+    h->n_octile = (int32_t)s.n_octile;
+    h->nnz = (int32_t)s.nnz;
+    h->n_tile = (int32_t)s.n_tile;
+    h->off_degree = (uint32_t)s.off_degree;
+    h->off_node = (uint32_t)s.off_node;
+    h->off_octile = (uint32_t)s.off_octile;
+    h->off_tilerow = (uint32_t)s.off_tilerow;
+    h->off_edge = (uint32_t)s.off_edge;
+    h->off_pool = (uint32_t)s.off_pool;
+    h->blob_bytes = (uint32_t)s.total;
+    h->flags = L->weighted ? 1u : 0u;
+
+    // degrees: sum of incident weights, self loops once, 0 -> 1
+    std::vector<double> deg(g->n_node, 0.0);
+    for (uint32_t k = 0; k < g->n_edge; ++k) {
+        const double w = g->edge_w ? (double)g->edge_w[k] : 1.0;
+        deg[g->edge_i[k]] += w;
+        if (g->edge_i[k] != g->edge_j[k]) deg[g->edge_j[k]] += w;
+    }
+    float *degree = reinterpret_cast<float *>(base + s.off_degree);
+    for (uint32_t i = 0; i < g->n_node; ++i) degree[i] = deg[i] == 0.0 ? 1.0f : (float)deg[i];
+
+    // nodes: verbatim AoS; frozen_array slots become blob-relative offsets
+    std::memcpy(base + s.off_node, g->nodes, (size_t)L->node_size * g->n_node);
+    for (uint32_t i = 0; i < g->n_node; ++i)
+        for (uint32_t f = 0; f < L->n_node_ptr; ++f) {
+            uint64_t *slot = reinterpret_cast<uint64_t *>(base + s.off_node + (size_t)i * L->node_size + L->node_ptr_offset[f]);
+            *slot += s.off_pool;
+        }
+
+    // octiles, tile rows, elements
+    gdb_octile_host *oct = reinterpret_cast<gdb_octile_host *>(base + s.off_octile);
+    uint32_t *tilerow = reinterpret_cast<uint32_t *>(base + s.off_tilerow);
+    uint8_t *edges = base + s.off_edge;
+    int32_t o = -1;
+    for (uint32_t k = 0; k < s.nnz; ++k) {
+        const Nz &z = nz[k];
+        if (k == 0 || (z.key >> 6) != (nz[k - 1].key >> 6)) {
+            ++o;
+            oct[o].mask = 0;
+            oct[o].start = k;
+            oct[o].trow = (uint16_t)(z.i >> 3);
+            oct[o].tcol = (uint16_t)(z.j >> 3);
+        }
+        oct[o].mask |= 1ull << (z.key & 63u);
+        uint8_t *e = edges + (size_t)k * s.edge_size;
+        if (L->weighted) {
+            const float w = g->edge_w ? g->edge_w[z.e] : 1.0f;
+            std::memcpy(e, &w, 4);
+        }
+        if (L->edge_label_size)
+            std::memcpy(e + s.label_off, static_cast<const uint8_t *>(g->edge_labels) + (size_t)z.e * L->edge_label_size,
+                        L->edge_label_size);
+        for (uint32_t f = 0; f < L->n_edge_ptr; ++f) {
+            uint64_t *slot = reinterpret_cast<uint64_t *>(e + s.label_off + L->edge_ptr_offset[f]);
+            *slot += s.off_pool;
+        }
+    }
+    // CSR over tile rows
+    {
+        uint32_t oi = 0;
+        for (uint32_t t = 0; t <= s.n_tile; ++t) {
+            while (oi < s.n_octile && oct[oi].trow < t) ++oi;
+            tilerow[t] = oi;
+        }
+    }
+    if (g->pool_bytes) std::memcpy(base + s.off_pool, g->pool, g->pool_bytes);
+    return GDB_OK;
+}

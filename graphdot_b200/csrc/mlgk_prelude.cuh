@@ -1,0 +1,94 @@
+// mlgk_prelude.cuh -- fixed device-side vocabulary available to the spliced
+// microkernel expressions.  Compiled by NVRTC (no system headers) and by nvcc.
+//
+// Provides what the reference's generated expressions may name (SURVEY.md
+// appendix A; reference graphdot/cpp/numpy_type.h, fmath.h, frozen_array.h,
+// basekernel/{normalize,convolution,dotproduct}.h): numpy scalar aliases,
+// graphdot::ipow<N>/ripow<N>, frozen_array<T>, normalize / normalize_jacobian,
+// convolution<mean> / convolution_jacobian<mean>, dotproduct.
+#pragma once
+
+typedef bool bool_;
+typedef signed char int8;
+typedef short int16;
+typedef int int32;
+typedef long long int64;
+typedef unsigned char uint8;
+typedef unsigned short uint16;
+typedef unsigned int uint32;
+typedef unsigned long long uint64;
+typedef float float32;
+typedef double float64;
+typedef long long intp;
+typedef unsigned long long uintp;
+struct empty_t {};
+
+namespace graphdot {
+
+// x^E for a compile-time non-negative integer E by repeated squaring.
+template<int E, class F> __host__ __device__ __forceinline__ constexpr F ipow(F base) {
+    if constexpr (E == 0) {
+        return F(1);
+    } else if constexpr (E == 1) {
+        return base;
+    } else {
+        F h = ipow<E / 2>(base);
+        return (E & 1) ? h * h * base : h * h;
+    }
+}
+
+// x^-E
+template<int E, class F> __host__ __device__ __forceinline__ constexpr F ripow(F base) {
+    return ipow<E>(F(1) / base);
+}
+
+}  // namespace graphdot
+
+// Read-only view of a variable-length feature; `_data` holds an absolute
+// device address after upload (pool-relative offset inside a packed blob).
+template<class T> struct frozen_array {
+    const T *_data;
+    int32 size;
+    __device__ __forceinline__ const T *begin() const { return _data; }
+    __device__ __forceinline__ const T *end() const { return _data + size; }
+    __device__ __forceinline__ const T &operator[](int i) const { return _data[i]; }
+};
+
+// k(x,y) / sqrt(k(x,x) k(y,y)); 0 when a self-similarity is not positive.
+template<class F, class X, class Y>
+__device__ __forceinline__ float normalize(F const f, X const &x, Y const &y) {
+    float const kxx = f(x, x), kyy = f(y, y);
+    float const s = kxx * kyy;
+    return s > 0.f ? f(x, y) * rsqrtf(s) : 0.f;
+}
+
+template<class F, class J, class X, class Y>
+__device__ __forceinline__ float normalize_jacobian(F const f, J const j, X const &x, Y const &y) {
+    float const kxx = f(x, x), kxy = f(x, y), kyy = f(y, y);
+    float const jxx = j(x, x), jxy = j(x, y), jyy = j(y, y);
+    float const s = kxx * kyy;
+    if (!(s > 0.f)) return 0.f;
+    float const rs = rsqrtf(s);
+    return jxy * rs - 0.5f * kxy * rs * rs * rs * (jxx * kyy + kxx * jyy);
+}
+
+// sum (or mean) of f over all element pairs of two sequences
+template<bool mean, class F, class X, class Y>
+__device__ __forceinline__ float convolution(F const f, X const &x, Y const &y) {
+    float k = 0.f;
+    for (auto const &_1 : x)
+        for (auto const &_2 : y) k += f(_1, _2);
+    return mean ? k / (float)(x.size * y.size) : k;
+}
+
+template<bool mean, class J, class X, class Y>
+__device__ __forceinline__ float convolution_jacobian(J const j, X const &x, Y const &y) {
+    return convolution<mean>(j, x, y);
+}
+
+template<class T>
+__device__ __forceinline__ float dotproduct(frozen_array<T> const &x, frozen_array<T> const &y) {
+    float s = 0.f;
+    for (int i = 0; i < x.size; ++i) s += (float)x._data[i] * (float)y._data[i];
+    return s;
+}

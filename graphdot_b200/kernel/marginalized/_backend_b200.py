@@ -1,0 +1,491 @@
+"""B200 back end of the marginalized graph kernel.
+
+Implements the reference's back-end contract (reference
+graphdot/kernel/marginalized/_backend_cuda.py:23-368: static allocators
+:37-47, per-graph device format cached in ``graph.cookie`` :111-116, code
+generation :157-228 and :282-293, theta upload :318-340, launch :346-367)
+on top of libgraphdot_b200.so: NVRTC splices the microkernels' ``gen_expr``
+strings into the fixed sm_100a solver (csrc/mlgk_solver.cuh).
+
+Only duck-typed protocols are used on the inputs, so the objects may come from
+this package or from the reference:
+graphs offer ``.nodes/.edges`` column stores and ``.cookie``; microkernels
+offer ``gen_expr('x1', 'x2')``, ``.dtype`` (aligned numpy struct of the
+hyper-parameters) and ``.state`` (matching nested tuple); starting
+probabilities offer ``gen_expr()``, ``.dtype`` and ``.state``.
+"""
+import ctypes as C
+import uuid
+
+import numpy as np
+
+from ... import native
+from ._backend import Backend
+
+_FROZEN = np.dtype([('_data', np.uint64), ('size', np.int32)], align=True)
+
+
+# --------------------------------------------------------------------------
+# attribute struct layout (what reference codegen/cpptool.py `decltype` and
+# minipandas `rowtype` produce: fields ordered by decreasing size, aligned)
+# --------------------------------------------------------------------------
+def _cxx_scalar(dt):
+    dt = np.dtype(dt)
+    if dt.kind not in 'biuf' or dt.names is not None:
+        raise TypeError(f'Unsupported attribute type {dt}')
+    return 'bool_' if dt.kind == 'b' else dt.name
+
+
+class AttributeLayout:
+    """Device struct of one attribute table (nodes or edge labels)."""
+
+    def __init__(self, df, drop):
+        fields = []
+        for key in df.columns:
+            if key in drop:
+                continue
+            if not key.isidentifier():
+                raise TypeError(f'Attribute name {key!r} is not a valid '
+                                'identifier')
+            col = df[key]
+            ct = getattr(col, 'concrete_type', None)
+            if isinstance(ct, np.dtype) and ct.kind != 'O':
+                fields.append((key, np.dtype(ct).newbyteorder('='), None))
+            elif ct in (list, tuple, np.ndarray) or ct is None:
+                inner = {np.asarray(v).dtype for v in col}
+                if len(inner) != 1:
+                    raise TypeError(
+                        f'Sequence attribute {key!r} has mixed element types '
+                        f'{inner}; use Graph.unify_datatype.')
+                inner = inner.pop()
+                _cxx_scalar(inner)
+                fields.append((key, _FROZEN, inner))
+            else:
+                raise TypeError(f'Unsupported non-scalar attribute {key!r} '
+                                f'of type {ct}')
+        if not fields:   # phantom member, like the reference's `labeled`
+            fields.append(('labeled', np.dtype(np.bool_), None))
+        order = np.argsort([-f[1].itemsize for f in fields], kind='stable')
+        self.fields = [fields[i] for i in order]
+        self.dtype = np.dtype([(k, dt) for k, dt, _ in self.fields],
+                              align=True)
+        self.decl = ' '.join(
+            (f'frozen_array<{_cxx_scalar(inner)}> {k};' if inner is not None
+             else f'{_cxx_scalar(dt)} {k};') for k, dt, inner in self.fields)
+        self.ptr_offsets = [self.dtype.fields[k][1]
+                            for k, _, inner in self.fields if inner is not None]
+        if len(self.ptr_offsets) > 8:
+            raise TypeError('At most 8 variable-length attributes supported')
+
+    @property
+    def key(self):
+        return (self.decl, self.dtype.itemsize, self.dtype.alignment)
+
+    def fill(self, df, order, pool, pool_base):
+        """AoS rows (in ``order``) + appends variable-length data to
+        ``pool`` (list of byte strings); returns (rows, new pool size)."""
+        rows = np.zeros(len(order), dtype=self.dtype)
+        for k, dt, inner in self.fields:
+            if k not in df:
+                continue    # phantom
+            col = df[k]
+            if inner is None:
+                rows[k] = np.asarray(col)[order]
+                continue
+            seqs = [np.ascontiguousarray(col[i], dtype=inner) for i in order]
+            sizes = np.array([len(s) for s in seqs], dtype=np.int64)
+            pad = (-pool_base) % 16
+            if pad:
+                pool.append(b'\0' * pad)
+                pool_base += pad
+            offs = pool_base + (np.cumsum(sizes) - sizes) * inner.itemsize
+            rows[k]['_data'] = offs
+            rows[k]['size'] = sizes
+            data = (np.concatenate(seqs) if seqs else np.zeros(0, inner))
+            pool.append(data.tobytes())
+            pool_base += data.nbytes
+        return rows, pool_base
+
+
+def struct_decl(dtype):
+    """C++ member declarations of a (nested) hyper-parameter struct dtype;
+    zero-size members (kernels without hyper-parameters) are skipped."""
+    dtype = np.dtype(dtype)
+    out = []
+    for name in dtype.names or ():
+        sub = dtype.fields[name][0]
+        if sub.itemsize == 0:
+            continue
+        if sub.names is not None:
+            out.append(f'struct{{{struct_decl(sub)}}}{name};')
+        elif sub.subdtype is not None:
+            base, shape = sub.subdtype
+            dims = ''.join(f'[{d}]' for d in shape)
+            out.append(f'{_cxx_scalar(base)} {name}{dims};')
+        else:
+            out.append(f'{_cxx_scalar(sub)} {name};')
+    return ''.join(out)
+
+
+def state_bytes(obj):
+    """Raw bytes of an object's hyper-parameter struct (``state`` packed
+    with ``dtype``), or None when it has no hyper-parameters."""
+    dt = np.dtype(obj.dtype)
+    if dt.itemsize == 0:
+        return None
+    return np.array([obj.state], dtype=dt).tobytes()
+
+
+class _Functor:
+    """Keeps the ctypes strings of one gdb_functor_src alive."""
+
+    def __init__(self, obj, args):
+        expr, jac = obj.gen_expr(*args)
+        dt = np.dtype(obj.dtype)
+        self.expr, self.jac = expr, list(jac)
+        self.theta_decl = struct_decl(dt)
+        self.theta_size = dt.itemsize
+        self._jac_arr = (C.c_char_p * max(1, len(self.jac)))(
+            *[j.encode() for j in self.jac])
+        self.c = native.FunctorSrc(
+            self.theta_decl.encode(), self.theta_size, self.expr.encode(),
+            len(self.jac), C.cast(self._jac_arr, C.POINTER(C.c_char_p)))
+
+    @property
+    def key(self):
+        return (self.theta_decl, self.expr, tuple(self.jac))
+
+
+class PackedGraph:
+    __slots__ = ('blob', 'n_node', 'key')
+
+    def __init__(self, blob, n_node, key):
+        self.blob, self.n_node, self.key = blob, n_node, key
+
+
+class GraphSet:
+    """Device-resident set of packed graphs."""
+
+    def __init__(self, backend, layout_c, packed):
+        lib = native.load()
+        self.backend = backend
+        self.packed = packed
+        n = len(packed)
+        ptrs = (C.c_void_p * n)(*[p.blob.ctypes.data for p in packed])
+        sizes = (C.c_uint64 * n)(*[p.blob.nbytes for p in packed])
+        self.handle = C.c_void_p()
+        native.check(lib.gdb_graphset_create(
+            backend.context, C.byref(layout_c), n, ptrs, sizes,
+            C.byref(self.handle)))
+        self.n = n
+        self.sizes = np.array([p.n_node for p in packed])
+
+    @property
+    def nbytes(self):
+        b = C.c_uint64()
+        native.check(native.load().gdb_graphset_bytes(self.handle,
+                                                      C.byref(b)))
+        return b.value
+
+    def upload(self):
+        native.check(native.load().gdb_graphset_upload(self.handle))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                native.load().gdb_graphset_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class B200Backend(Backend):
+    """The sm_100a engine behind the reference's back-end interface.
+
+    Parameters
+    ----------
+    device: int
+        CUDA device ordinal (one back end per GPU).
+    block_size: int or None
+        Threads cooperating on one graph pair (multiple of 32); None picks it
+        from the size of the largest pair.
+    nvrtc_extra: list of str
+        Extra NVRTC options (the reference's ``nvcc_extra``).
+    """
+
+    @staticmethod
+    def array(ndarray):
+        out = native.pinned_empty(ndarray.size, ndarray.dtype)
+        out[:] = ndarray.ravel()
+        return out
+
+    @staticmethod
+    def zeros(size, dtype=np.float32):
+        out = native.pinned_empty(size, dtype)
+        out[:] = 0
+        return out
+
+    @staticmethod
+    def empty(size, dtype=np.float32):
+        return native.pinned_empty(size, dtype)
+
+    def __init__(self, device=0, block_size=None, nvrtc_extra=(),
+                 graphset_cache=4):
+        self.uuid = uuid.uuid4()
+        self.device = device
+        self.block_size = block_size
+        self.nvrtc_extra = list(nvrtc_extra)
+        self._context = None
+        self._programs = {}
+        self._graphsets = []     # small LRU of (key, GraphSet)
+        self._graphset_cache = graphset_cache
+        self.last = {}           # diagnostics of the most recent solve
+        native.load()            # fail loudly if the library is missing
+
+    def __deepcopy__(self, memo):
+        return self              # kernels cloned by theta share the engine
+
+    # -- context -----------------------------------------------------------
+    @property
+    def context(self):
+        if self._context is None:
+            ctx = C.c_void_p()
+            native.check(native.load().gdb_context_create(self.device,
+                                                          C.byref(ctx)))
+            self._context = ctx
+        return self._context
+
+    def device_info(self):
+        info = native.DeviceInfo()
+        native.check(native.load().gdb_context_info(self.context,
+                                                    C.byref(info)))
+        return info
+
+    # -- graphs ------------------------------------------------------------
+    @staticmethod
+    def _layouts(graph):
+        weighted = '!w' in graph.edges
+        nl = AttributeLayout(graph.nodes, drop=('!i',))
+        el = AttributeLayout(graph.edges, drop=('!i', '!j', '!w'))
+        return nl, el, weighted
+
+    @staticmethod
+    def _layout_c(nl, el, weighted):
+        L = native.Layout()
+        L.node_size = nl.dtype.itemsize
+        L.edge_label_size = el.dtype.itemsize
+        L.edge_label_align = el.dtype.alignment
+        L.weighted = int(weighted)
+        L.n_node_ptr = len(nl.ptr_offsets)
+        for k, o in enumerate(nl.ptr_offsets):
+            L.node_ptr_offset[k] = o
+        L.n_edge_ptr = len(el.ptr_offsets)
+        for k, o in enumerate(el.ptr_offsets):
+            L.edge_ptr_offset[k] = o
+        return L
+
+    def pack_graph(self, graph):
+        """Octile-pack one graph (cached in ``graph.cookie``)."""
+        cached = graph.cookie.get(self.uuid)
+        if cached is not None:
+            return cached
+        lib = native.load()
+        nl, el, weighted = self._layouts(graph)
+        L = self._layout_c(nl, el, weighted)
+        n = len(graph.nodes)
+        order = np.argsort(np.asarray(graph.nodes['!i']), kind='stable')
+        pool = []
+        nodes, pb = nl.fill(graph.nodes, order, pool, 0)
+        ne = len(graph.edges)
+        labels, pb = el.fill(graph.edges, np.arange(ne), pool, pb)
+        pool_bytes = b''.join(pool)
+        ei = np.ascontiguousarray(graph.edges['!i'], dtype=np.uint32)
+        ej = np.ascontiguousarray(graph.edges['!j'], dtype=np.uint32)
+        ew = (np.ascontiguousarray(graph.edges['!w'], dtype=np.float32)
+              if weighted else None)
+        pool_arr = np.frombuffer(pool_bytes, dtype=np.uint8)
+        src = native.GraphSrc(
+            n, ne, nodes.ctypes.data, ei.ctypes.data, ej.ctypes.data,
+            ew.ctypes.data if weighted else None, labels.ctypes.data,
+            pool_arr.ctypes.data if len(pool_arr) else None, len(pool_arr))
+        size = C.c_uint64()
+        native.check(lib.gdb_graph_packed_size(C.byref(L), C.byref(src),
+                                               C.byref(size)))
+        blob = np.empty(size.value, dtype=np.uint8)
+        native.check(lib.gdb_graph_pack(C.byref(L), C.byref(src),
+                                        blob.ctypes.data, blob.nbytes))
+        packed = PackedGraph(blob, n, (nl.key, el.key, weighted))
+        graph.cookie[self.uuid] = packed
+        return packed
+
+    def graphset(self, graphs):
+        """Device graph set for a list of graphs (LRU-cached)."""
+        packed = [self.pack_graph(g) for g in graphs]
+        first = packed[0]
+        for g, p in zip(graphs, packed):
+            if p.key != first.key:
+                raise TypeError(
+                    'All nodes/edges must be of the same type and graphs '
+                    'must be all weighted or all unweighted. If the '
+                    'attributes match in name but differ in type, try '
+                    '`Graph.unify_datatype`.')
+        key = tuple(id(p) for p in packed)
+        for k, (kk, gs) in enumerate(self._graphsets):
+            if kk == key:
+                self._graphsets.insert(0, self._graphsets.pop(k))
+                return gs
+        nl, el, weighted = self._layouts(graphs[0])
+        gs = GraphSet(self, self._layout_c(nl, el, weighted), packed)
+        gs.layouts = (nl, el, weighted)
+        self._graphsets.insert(0, (key, gs))
+        del self._graphsets[self._graphset_cache:]
+        return gs
+
+    # -- programs ----------------------------------------------------------
+    def _pick_block(self, sizes):
+        if self.block_size:
+            return int(self.block_size)
+        n = int(np.max(sizes))
+        N = n * n
+        if N <= 1024:
+            return 32
+        if N <= 4096:
+            return 64
+        if N <= 16384:
+            return 128
+        return 256
+
+    @staticmethod
+    def _desc(nl, el, weighted, node_kernel, edge_kernel, p, traits, block,
+              extra):
+        fn = _Functor(node_kernel, ('x1', 'x2'))
+        fe = _Functor(edge_kernel, ('x1', 'x2'))
+        fp = _Functor(p, ())
+        d = native.ProgramDesc()
+        d.node_decl = nl.decl.encode()
+        d.node_size = nl.dtype.itemsize
+        d.edge_decl = el.decl.encode()
+        d.edge_label_size = el.dtype.itemsize
+        d.edge_label_align = el.dtype.alignment
+        d.weighted = int(weighted)
+        d.node_kernel, d.edge_kernel, d.p_start = fn.c, fe.c, fp.c
+        d.diagonal = int(bool(traits.diagonal))
+        d.symmetric = int(bool(traits.symmetric))
+        d.nodal = native.NODAL_CODES[traits.nodal]
+        d.lmin = int(traits.lmin)
+        d.eval_gradient = int(traits.eval_gradient is True)
+        d.block_size = int(block)
+        d.extra_options = ' '.join(extra).encode() if extra else None
+        keep = (fn, fe, fp)
+        key = (nl.key, el.key, weighted, fn.key, fe.key, fp.key,
+               tuple(traits), block, tuple(extra))
+        return d, keep, key
+
+    def program(self, gs, node_kernel, edge_kernel, p, traits):
+        if traits.lmin not in (0, 1):
+            raise ValueError(f'lmin must be 0 or 1, got {traits.lmin}')
+        if traits.eval_gradient is True and traits.nodal is not False:
+            raise NotImplementedError(
+                'nodal gradients are not implemented by the B200 engine yet')
+        nl, el, weighted = gs.layouts
+        block = self._pick_block(gs.sizes)
+        d, keep, key = self._desc(nl, el, weighted, node_kernel, edge_kernel,
+                                  p, traits, block, self.nvrtc_extra)
+        prog = self._programs.get(key)
+        if prog is None:
+            prog = C.c_void_p()
+            native.check(native.load().gdb_program_create(
+                self.context, C.byref(d), C.byref(prog)))
+            self._programs[key] = prog
+        return prog
+
+    def program_info(self, prog):
+        info = native.ProgramInfo()
+        native.check(native.load().gdb_program_info_get(prog, C.byref(info)))
+        return info
+
+    # -- the back-end call ---------------------------------------------------
+    def __call__(self, graphs, node_kernel, edge_kernel, p, q, eps, ftol,
+                 gtol, jobs, starts, gramian, gradient, nX, nY, nJ, traits,
+                 timer, stream=None, keep_on_device=False):
+        lib = native.load()
+        timer.tic('transferring graphs to GPU')
+        gs = self.graphset(list(graphs))
+        timer.toc('transferring graphs to GPU')
+
+        timer.tic('code generation + JIT')
+        prog = self.program(gs, node_kernel, edge_kernel, p, traits)
+        timer.toc('code generation + JIT')
+
+        timer.tic('GPU kernel execution')
+        a = native.SolveArgs()
+        jobs = np.ascontiguousarray(jobs)
+        a.job_mode = native.JOBS_LIST
+        a.jobs = jobs.ctypes.data
+        a.n_jobs = len(jobs)
+        starts = np.ascontiguousarray(starts, dtype=np.uint32)
+        a.starts = starts.ctypes.data
+        a.n_starts = len(starts)
+        a.q, a.eps, a.ftol, a.gtol = float(q), float(eps), float(ftol), \
+            float(gtol)
+        blobs = [state_bytes(node_kernel), state_bytes(edge_kernel),
+                 state_bytes(p)]
+        bufs = [C.create_string_buffer(b, len(b)) if b else None
+                for b in blobs]
+        a.node_theta, a.edge_theta, a.p_theta = [
+            C.cast(b, C.c_void_p) if b is not None else None for b in bufs]
+        a.gramian = gramian.ctypes.data
+        a.gradient = gradient.ctypes.data if gradient is not None else None
+        a.nX, a.nY, a.nJ = int(nX), int(nY), int(nJ)
+        a.stream = stream
+        a.keep_on_device = int(keep_on_device)
+        native.check(lib.gdb_solve(self.context, prog, gs.handle, C.byref(a)))
+        timer.toc('GPU kernel execution')
+        self.last = dict(kernel_ms=a.kernel_ms, h2d_ms=a.h2d_ms,
+                         d2h_ms=a.d2h_ms, cg_iterations=a.cg_iterations,
+                         matvec_products=a.matvec_products,
+                         n_jobs=len(jobs), n_launches=a.n_launches,
+                         graph_bytes=gs.nbytes)
+        return a
+
+
+# --------------------------------------------------------------------------
+# build check support: the translation units of the BASELINE configurations
+# --------------------------------------------------------------------------
+def preset_sources():
+    """Rendered solver sources for the BASELINE.json configurations (no GPU
+    needed): used by csrc/build.py to compile them with nvcc for sm_100a."""
+    from ...microkernel import (Constant, Convolution, KroneckerDelta,
+                                SquareExponential, TensorProduct)
+    from ...synthetic import make_config_graphs
+    from ._kernel import MarginalizedGraphKernel
+    from .starting_probability import Uniform
+    lib = native.load()
+    T = MarginalizedGraphKernel.traits
+    mol = (TensorProduct(element=KroneckerDelta(0.5),
+                         x=SquareExponential(1.0)),
+           TensorProduct(length=SquareExponential(0.1)))
+    conv = (TensorProduct(feat=Convolution(SquareExponential(1.0))),
+            TensorProduct(length=SquareExponential(0.2)))
+    presets = {
+        'c1_unlabeled': ('C1', (Constant(1.0), Constant(1.0)),
+                         T(symmetric=True), 32),
+        'c2_molecular': ('C2', mol, T(symmetric=True), 32),
+        'c2_molecular_diag': ('C2', mol, T(diagonal=True), 32),
+        'c3_molecular_grad': ('C2', mol, T(symmetric=True,
+                                           eval_gradient=True), 32),
+        'c4_convolution': ('C4', conv, T(symmetric=True), 256),
+        'c5_offdiag': ('C2', mol, T(), 32),
+        'c2_nodal': ('C2', mol, T(symmetric=True, nodal=True), 32),
+    }
+    out = {}
+    for name, (cfg, (kn, ke), traits, block) in presets.items():
+        g = make_config_graphs(cfg, n_graphs=1)[0]
+        nl, el, weighted = B200Backend._layouts(g)
+        d, keep, _ = B200Backend._desc(nl, el, weighted, kn, ke, Uniform(1.0),
+                                       traits, block, ())
+        ptr = C.c_void_p()
+        native.check(lib.gdb_render_source(C.byref(d), C.byref(ptr)))
+        out[name] = C.string_at(ptr).decode()
+        lib.gdb_free(ptr)
+    return out

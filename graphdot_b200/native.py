@@ -1,0 +1,183 @@
+"""ctypes binding of libgraphdot_b200.so (C ABI: include/graphdot_b200.h).
+
+The shared library is built in-tree by ``graphdot_b200/csrc/build.py`` (called
+from ``__graft_entry__.build()``).  There is no fallback: if the library is
+missing, ``load()`` raises, and every product path goes through it.  ctypes
+releases the GIL for the duration of each foreign call, so one Python thread
+per GPU can drive its own context.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libgraphdot_b200.so')
+
+GDB_OK = 0
+JOBS_LIST, JOBS_RECT, JOBS_TRIU = 0, 1, 2
+NODAL_CODES = {False: 0, True: 1, 'block': 2}
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f'libgraphdot_b200 error {code}: {message}')
+        self.code = code
+
+
+class DeviceInfo(C.Structure):
+    _fields_ = [('device', C.c_int32), ('sm_count', C.c_int32),
+                ('cc_major', C.c_int32), ('cc_minor', C.c_int32),
+                ('max_smem_per_block_optin', C.c_int32),
+                ('max_smem_per_sm', C.c_int32), ('clock_khz', C.c_int32),
+                ('l2_bytes', C.c_int32), ('total_mem', C.c_uint64),
+                ('name', C.c_char * 64)]
+
+
+class FunctorSrc(C.Structure):
+    _fields_ = [('theta_decl', C.c_char_p), ('theta_size', C.c_uint32),
+                ('expr', C.c_char_p), ('n_jac', C.c_uint32),
+                ('jac', C.POINTER(C.c_char_p))]
+
+
+class ProgramDesc(C.Structure):
+    _fields_ = [('node_decl', C.c_char_p), ('node_size', C.c_uint32),
+                ('edge_decl', C.c_char_p), ('edge_label_size', C.c_uint32),
+                ('edge_label_align', C.c_uint32), ('weighted', C.c_int32),
+                ('node_kernel', FunctorSrc), ('edge_kernel', FunctorSrc),
+                ('p_start', FunctorSrc),
+                ('diagonal', C.c_int32), ('symmetric', C.c_int32),
+                ('nodal', C.c_int32), ('lmin', C.c_int32),
+                ('eval_gradient', C.c_int32), ('block_size', C.c_int32),
+                ('extra_options', C.c_char_p)]
+
+
+class ProgramInfo(C.Structure):
+    _fields_ = [('block_size', C.c_int32), ('num_regs', C.c_int32),
+                ('static_smem', C.c_int32), ('local_bytes', C.c_int32),
+                ('max_dynamic_smem', C.c_int32), ('n_jac', C.c_int32),
+                ('from_cache', C.c_int32), ('compile_ms', C.c_float)]
+
+
+class GraphSrc(C.Structure):
+    _fields_ = [('n_node', C.c_uint32), ('n_edge', C.c_uint32),
+                ('nodes', C.c_void_p), ('edge_i', C.c_void_p),
+                ('edge_j', C.c_void_p), ('edge_w', C.c_void_p),
+                ('edge_labels', C.c_void_p), ('pool', C.c_void_p),
+                ('pool_bytes', C.c_uint32)]
+
+
+class Layout(C.Structure):
+    _fields_ = [('node_size', C.c_uint32), ('edge_label_size', C.c_uint32),
+                ('edge_label_align', C.c_uint32), ('weighted', C.c_int32),
+                ('n_node_ptr', C.c_uint32), ('node_ptr_offset', C.c_uint32 * 8),
+                ('n_edge_ptr', C.c_uint32),
+                ('edge_ptr_offset', C.c_uint32 * 8)]
+
+
+class SolveArgs(C.Structure):
+    _fields_ = [('job_mode', C.c_int32), ('jobs', C.c_void_p),
+                ('n_jobs', C.c_uint64),
+                ('i0', C.c_uint32), ('i1', C.c_uint32),
+                ('j0', C.c_uint32), ('j1', C.c_uint32),
+                ('starts', C.c_void_p), ('n_starts', C.c_uint32),
+                ('q', C.c_float), ('eps', C.c_float),
+                ('ftol', C.c_float), ('gtol', C.c_float),
+                ('node_theta', C.c_void_p), ('edge_theta', C.c_void_p),
+                ('p_theta', C.c_void_p),
+                ('gramian', C.c_void_p), ('gradient', C.c_void_p),
+                ('nX', C.c_uint32), ('nY', C.c_uint32), ('nJ', C.c_uint32),
+                ('stream', C.c_void_p), ('keep_on_device', C.c_int32),
+                ('kernel_ms', C.c_float), ('h2d_ms', C.c_float),
+                ('d2h_ms', C.c_float), ('cg_iterations', C.c_uint64),
+                ('matvec_products', C.c_uint64), ('n_launches', C.c_uint32)]
+
+
+# every symbol declared in include/graphdot_b200.h: (name, restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = [
+    ('gdb_version', C.c_char_p, []),
+    ('gdb_last_error', C.c_char_p, []),
+    ('gdb_solver_template', C.c_char_p, []),
+    ('gdb_context_create', C.c_int, [C.c_int, C.POINTER(_P)]),
+    ('gdb_context_destroy', C.c_int, [_P]),
+    ('gdb_context_info', C.c_int, [_P, C.POINTER(DeviceInfo)]),
+    ('gdb_context_synchronize', C.c_int, [_P]),
+    ('gdb_host_alloc', C.c_int, [C.c_size_t, C.POINTER(_P)]),
+    ('gdb_host_free', C.c_int, [_P]),
+    ('gdb_program_create', C.c_int, [_P, C.POINTER(ProgramDesc),
+                                     C.POINTER(_P)]),
+    ('gdb_program_info_get', C.c_int, [_P, C.POINTER(ProgramInfo)]),
+    ('gdb_program_log', C.c_char_p, [_P]),
+    ('gdb_program_source', C.c_char_p, [_P]),
+    ('gdb_program_destroy', C.c_int, [_P]),
+    ('gdb_render_source', C.c_int, [C.POINTER(ProgramDesc), C.POINTER(_P)]),
+    ('gdb_program_compile_only', C.c_int, [C.POINTER(ProgramDesc),
+                                           C.POINTER(C.c_uint64)]),
+    ('gdb_free', None, [_P]),
+    ('gdb_graph_packed_size', C.c_int, [C.POINTER(Layout), C.POINTER(GraphSrc),
+                                        C.POINTER(C.c_uint64)]),
+    ('gdb_graph_pack', C.c_int, [C.POINTER(Layout), C.POINTER(GraphSrc), _P,
+                                 C.c_uint64]),
+    ('gdb_graphset_create', C.c_int, [_P, C.POINTER(Layout), C.c_uint32,
+                                      C.POINTER(_P), C.POINTER(C.c_uint64),
+                                      C.POINTER(_P)]),
+    ('gdb_graphset_upload', C.c_int, [_P]),
+    ('gdb_graphset_bytes', C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    ('gdb_graphset_destroy', C.c_int, [_P]),
+    ('gdb_solve', C.c_int, [_P, _P, _P, C.POINTER(SolveArgs)]),
+    ('gdb_last_outputs', C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
+]
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare all prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f'{LIB_PATH} is missing: build it with '
+            '`python -c "import __graft_entry__ as g; g.build()"` or '
+            '`python graphdot_b200/csrc/build.py`. There is no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != GDB_OK:
+        raise NativeError(status, load().gdb_last_error().decode())
+
+
+def pinned_empty(count, dtype):
+    """numpy array over page-locked host memory (freed with the array)."""
+    lib = load()
+    dtype = np.dtype(dtype)
+    nbytes = max(1, int(count) * dtype.itemsize)
+    ptr = C.c_void_p()
+    check(lib.gdb_host_alloc(nbytes, C.byref(ptr)))
+    raw = (C.c_ubyte * nbytes).from_address(ptr.value)
+    # the ctypes buffer is the ultimate .base of every view numpy derives from
+    # this array, so tying the holder to it keeps the allocation alive exactly
+    # as long as any view exists
+    raw._gdb_holder = _PinnedHolder(ptr.value)
+    return np.frombuffer(raw, dtype=dtype, count=int(count))
+
+
+class _PinnedHolder:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            if self.ptr and _lib is not None:
+                _lib.gdb_host_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass

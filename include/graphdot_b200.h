@@ -1,0 +1,215 @@
+/* graphdot_b200.h -- C ABI of the B200-native marginalized graph kernel engine.
+ *
+ * This is the drop-in boundary for the reference's CUDA back end
+ * (reference graphdot/kernel/marginalized/_backend_cuda.py).  Plain pointers
+ * and sizes only; no torch / pycuda types.  Every entry point names the
+ * reference interface it replaces.  All functions return GDB_OK (0) or a
+ * negative status; gdb_last_error() then holds a message for the calling
+ * thread.  The Python wrapper (graphdot_b200/kernel/marginalized/
+ * _backend_b200.py) turns statuses into exceptions and releases the GIL
+ * around every call, so one host thread per GPU can drive a job queue.
+ */
+#ifndef GRAPHDOT_B200_H_
+#define GRAPHDOT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDB_OK 0
+#define GDB_ERR_INVALID (-1) /* bad argument                                */
+#define GDB_ERR_CUDA (-2)    /* CUDA driver/runtime failure, no device      */
+#define GDB_ERR_COMPILE (-3) /* NVRTC rejected the program (see log)        */
+#define GDB_ERR_NOMEM (-4)
+#define GDB_ERR_LAYOUT (-5)  /* host/device struct layout disagreement      */
+
+typedef struct gdb_context_s *gdb_context_t;
+typedef struct gdb_program_s *gdb_program_t;
+typedef struct gdb_graphset_s *gdb_graphset_t;
+
+/* ---- library ---------------------------------------------------------- */
+const char *gdb_version(void);
+const char *gdb_last_error(void);
+/* The fixed hand-written solver template the microkernel expressions are
+ * spliced into (replaces reference kernel/marginalized/template.cu +
+ * graphdot/cpp/ *.h as nvcc input). */
+const char *gdb_solver_template(void);
+
+/* ---- device context ----------------------------------------------------
+ * Replaces pycuda.autoinit / graphdot.cuda.defctx (reference
+ * graphdot/cuda/__init__.py:3-7, _backend_cuda.py:49-52).  Uses the device's
+ * primary context, so it shares memory and streams with the CUDA runtime
+ * (PyTorch). */
+typedef struct gdb_device_info {
+    int32_t device;
+    int32_t sm_count;
+    int32_t cc_major, cc_minor;
+    int32_t max_smem_per_block_optin;
+    int32_t max_smem_per_sm;
+    int32_t clock_khz;
+    int32_t l2_bytes;
+    uint64_t total_mem;
+    char name[64];
+} gdb_device_info;
+
+int gdb_context_create(int device, gdb_context_t *out);
+int gdb_context_destroy(gdb_context_t ctx);
+int gdb_context_info(gdb_context_t ctx, gdb_device_info *out);
+int gdb_context_synchronize(gdb_context_t ctx);
+
+/* Page-locked host buffers for jobs / starts / outputs.  Replaces the
+ * managed-memory allocators Backend.array/zeros/empty (reference
+ * graphdot/cuda/array.py:14-31, _backend_cuda.py:37-47).  Usable without a
+ * context; falls back to nothing: fails if no CUDA device is present. */
+int gdb_host_alloc(size_t bytes, void **out);
+int gdb_host_free(void *ptr);
+
+/* ---- program: NVRTC-compiled solver ------------------------------------
+ * Replaces CUDABackend.gencode_kernel / gencode_probability / template
+ * rendering / pycuda SourceModule (reference _backend_cuda.py:118-134,
+ * :157-228, :282-293).  Inputs are exactly the microkernels' gen_expr()
+ * strings and the C++ member declarations of the attribute structs. */
+typedef struct gdb_functor_src {
+    const char *theta_decl;  /* members of the hyper-parameter struct, e.g.
+                                "struct{float32 h;}element;"               */
+    uint32_t theta_size;     /* sizeof(np.dtype(kernel.dtype)); may be 0   */
+    const char *expr;        /* value expression over x1,x2 (or n)         */
+    uint32_t n_jac;
+    const char *const *jac;  /* one Jacobian expression per hyper-param    */
+} gdb_functor_src;
+
+#define GDB_NODAL_NONE 0
+#define GDB_NODAL_FULL 1
+#define GDB_NODAL_BLOCK 2
+
+typedef struct gdb_program_desc {
+    const char *node_decl;   /* members of node_t                          */
+    uint32_t node_size;
+    const char *edge_decl;   /* members of the edge label struct           */
+    uint32_t edge_label_size, edge_label_align;
+    int32_t weighted;        /* edge_t = {float32 weight; label}           */
+    gdb_functor_src node_kernel, edge_kernel, p_start;
+    /* traits (reference _kernel.py:48-58) -- compile-time specialisation  */
+    int32_t diagonal, symmetric, nodal, lmin, eval_gradient;
+    int32_t block_size;      /* threads cooperating on one pair; 0 = auto  */
+    const char *extra_options; /* extra NVRTC options, space separated     */
+} gdb_program_desc;
+
+typedef struct gdb_program_info {
+    int32_t block_size;
+    int32_t num_regs;
+    int32_t static_smem;
+    int32_t local_bytes;     /* spill / stack per thread                   */
+    int32_t max_dynamic_smem;
+    int32_t n_jac;           /* n_p + 1 + n_node + n_edge                  */
+    int32_t from_cache;
+    float compile_ms;
+} gdb_program_info;
+
+int gdb_program_create(gdb_context_t ctx, const gdb_program_desc *desc,
+                       gdb_program_t *out);
+int gdb_program_info_get(gdb_program_t prog, gdb_program_info *out);
+const char *gdb_program_log(gdb_program_t prog);
+const char *gdb_program_source(gdb_program_t prog);
+int gdb_program_destroy(gdb_program_t prog);
+/* Render the full translation unit without a device (build checks). */
+int gdb_render_source(const gdb_program_desc *desc, char **out_malloced);
+/* NVRTC-compile for sm_100a without a device or context: reports the cubin
+ * size; the compiler log is kept in gdb_last_error() on failure. */
+int gdb_program_compile_only(const gdb_program_desc *desc,
+                             uint64_t *cubin_bytes);
+void gdb_free(void *p);
+
+/* ---- graphs: octile packing and upload ---------------------------------
+ * Replaces OctileGraph (reference _octilegraph.py:11-189) and graph_t
+ * (reference graphdot/cpp/graph.h:8-33).  A packed graph is ONE
+ * position-independent, 16-byte aligned blob
+ *   [header | degree f32[n] | node_t[n] | octile[n_oct] | tile_row u32[T+1]
+ *    | edge_t[nnz] | variable-length feature pool]
+ * with 8x8 octiles sorted by (tile row, tile column), a row-major 64-bit
+ * non-zero mask per octile and compact row-major elements.  Degrees are the
+ * sums of incident weights (self loops once), 0 replaced by 1 (reference
+ * _octilegraph.py:113-139). */
+typedef struct gdb_graph_src {
+    uint32_t n_node;
+    uint32_t n_edge;          /* undirected edges                          */
+    const void *nodes;        /* node_t[n_node] in node-index order        */
+    const uint32_t *edge_i, *edge_j;
+    const float *edge_w;      /* NULL when unweighted                      */
+    const void *edge_labels;  /* label struct per undirected edge          */
+    const void *pool;         /* variable-length feature data              */
+    uint32_t pool_bytes;
+} gdb_graph_src;
+
+typedef struct gdb_layout {
+    uint32_t node_size;
+    uint32_t edge_label_size, edge_label_align;
+    int32_t weighted;
+    /* byte offsets (inside node_t / edge label) of the 8-byte data-pointer
+     * slots of frozen_array members; the host passes pool-relative offsets
+     * there and the packer/uploader relocates them. */
+    uint32_t n_node_ptr, node_ptr_offset[8];
+    uint32_t n_edge_ptr, edge_ptr_offset[8];
+} gdb_layout;
+
+/* Size of / write the packed blob of one graph (pure host code). */
+int gdb_graph_packed_size(const gdb_layout *layout, const gdb_graph_src *g,
+                          uint64_t *bytes);
+int gdb_graph_pack(const gdb_layout *layout, const gdb_graph_src *g,
+                   void *blob, uint64_t capacity);
+
+/* Assemble packed blobs into one device-resident graph set. */
+int gdb_graphset_create(gdb_context_t ctx, const gdb_layout *layout,
+                        uint32_t n_graphs, const void *const *blobs,
+                        const uint64_t *blob_bytes, gdb_graphset_t *out);
+/* Re-send the staged (pinned) host image to the device: the host->device
+ * leg of an end-to-end call. */
+int gdb_graphset_upload(gdb_graphset_t gs);
+int gdb_graphset_bytes(gdb_graphset_t gs, uint64_t *bytes);
+int gdb_graphset_destroy(gdb_graphset_t gs);
+
+/* ---- solve --------------------------------------------------------------
+ * Replaces the launch of graph_kernel_solver (reference
+ * _backend_cuda.py:303-367, template.cu:29-475): for every job (i, j) solve
+ * the product-graph system of graphs i and j and write the Gram entry (and
+ * Jacobian) at starts[i], starts[j] of the Fortran-ordered outputs. */
+#define GDB_JOBS_LIST 0 /* explicit (i, j) pairs                          */
+#define GDB_JOBS_RECT 1 /* all (i, j) with i in [i0,i1), j in [j0,j1)     */
+#define GDB_JOBS_TRIU 2 /* all i <= j in [i0,i1)                          */
+
+typedef struct gdb_solve_args {
+    int32_t job_mode;
+    const uint32_t *jobs;     /* host, 2*n_jobs (GDB_JOBS_LIST)            */
+    uint64_t n_jobs;
+    uint32_t i0, i1, j0, j1;  /* GDB_JOBS_RECT / TRIU                      */
+    const uint32_t *starts;   /* host, one per graph (+1)                  */
+    uint32_t n_starts;
+    float q, eps, ftol, gtol;
+    const void *node_theta, *edge_theta, *p_theta; /* raw struct bytes     */
+    float *gramian;           /* host; nX*nY floats, Fortran order         */
+    float *gradient;          /* host or NULL; nX*nY*nJ floats             */
+    uint32_t nX, nY, nJ;
+    void *stream;             /* CUstream to run on; NULL = context stream */
+    int32_t keep_on_device;   /* 1: skip the device->host copy; outputs
+                                 stay in the context's device buffers      */
+    /* diagnostics (out) */
+    float kernel_ms;          /* device time of the solver kernel          */
+    float h2d_ms, d2h_ms;
+    uint64_t cg_iterations;   /* total PCG iterations over all jobs        */
+    uint64_t matvec_products; /* total nnz1*nnz2 products evaluated        */
+    uint32_t n_launches;
+} gdb_solve_args;
+
+int gdb_solve(gdb_context_t ctx, gdb_program_t prog, gdb_graphset_t gs,
+              gdb_solve_args *args);
+/* Device pointers of the most recent outputs (keep_on_device). */
+int gdb_last_outputs(gdb_context_t ctx, void **gramian_dev,
+                     void **gradient_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHDOT_B200_H_ */

@@ -64,12 +64,13 @@ def graph_arrays(g):
     return deg, adj, np.array(src), np.array(dst), np.array(eid)
 
 
-def pair_system(g1, g2, knode, kedge, q, jac=False):
+def pair_system(g1, g2, knode, kedge, q, jac=False, sparse=False):
     """Dense pieces of the product-graph system of a graph pair.
 
     Returns a dict with ``D`` (N), ``V`` (N), ``W`` (N, N) such that
     ``A = diag(D/V) - W`` and ``b = D``; with ``jac`` also ``dV`` (n_v, N) and
-    ``dW`` (n_e, N, N)."""
+    ``dW`` (list of n_e (N, N) matrices).  ``sparse`` assembles W as scipy
+    CSR (for pairs whose dense N x N system would not fit)."""
     n1, n2 = len(g1.nodes), len(g2.nodes)
     N = n1 * n2
     d1, a1, s1, t1, k1 = graph_arrays(g1)
@@ -105,21 +106,27 @@ def pair_system(g1, g2, knode, kedge, q, jac=False):
                 f = kedge(e1, e2)
             E[a, b] = f
 
-    W = np.zeros((N, N))
     rows = (s1[:, None] * n2 + s2[None, :]).ravel()
     cols = (t1[:, None] * n2 + t2[None, :]).ravel()
     ww = (a1[s1, t1][:, None] * a2[s2, t2][None, :]).ravel()
-    W[rows, cols] = ww * E[k1[:, None], k2[None, :]].ravel()
+
+    def assemble(vals):
+        if sparse:
+            import scipy.sparse as sp
+            return sp.csr_matrix((vals, (rows, cols)), shape=(N, N))
+        M = np.zeros((N, N))
+        M[rows, cols] = vals
+        return M
+
+    W = assemble(ww * E[k1[:, None], k2[None, :]].ravel())
     out = {'n1': n1, 'n2': n2, 'V': V, 'W': W,
            'dox': np.outer(d1, d2).ravel(),
            'D': np.outer(d1, d2).ravel() / (1.0 - q) ** 2}
     if jac:
         out['dV'] = dV if dV is not None else np.zeros((0, N))
         nE = 0 if dE is None else dE.shape[0]
-        dW = np.zeros((nE, N, N))
-        for m in range(nE):
-            dW[m][rows, cols] = ww * dE[m][k1[:, None], k2[None, :]].ravel()
-        out['dW'] = dW
+        out['dW'] = [assemble(ww * dE[m][k1[:, None], k2[None, :]].ravel())
+                     for m in range(nE)]
     return out
 
 
@@ -133,16 +140,27 @@ def _start_prob(p, g):
 
 
 def solve_pair(g1, g2, knode, kedge, q, p=None, lmin=0,
-               eval_gradient=False):
+               eval_gradient=False, sparse=None):
     """Nodal solution matrix R (n1, n2) with starting probabilities applied,
     graph-level K = R.sum(), and with ``eval_gradient`` the Jacobian of K in
     the order [p..., q, node..., edge...]."""
     from graphdot_b200.kernel.marginalized.starting_probability import Uniform
     p = Uniform(1.0) if p is None else p
-    s = pair_system(g1, g2, knode, kedge, q, jac=eval_gradient)
+    if sparse is None:
+        sparse = len(g1.nodes) * len(g2.nodes) > 3000
+    s = pair_system(g1, g2, knode, kedge, q, jac=eval_gradient, sparse=sparse)
     n1, n2, D, V, W = s['n1'], s['n2'], s['D'], s['V'], s['W']
-    A = np.diag(D / V) - W
-    x = np.linalg.solve(A, D)
+    if sparse:
+        import scipy.sparse as sp
+        import scipy.sparse.linalg as spla
+        lu = spla.splu((sp.diags(D / V) - W).tocsc())
+        solve = lu.solve
+    else:
+        A = np.diag(D / V) - W
+
+        def solve(rhs):
+            return np.linalg.solve(A, rhs)
+    x = solve(D)
     p1, dp1 = _start_prob(p, g1)
     p2, dp2 = _start_prob(p, g2)
     px = np.outer(p1, p2).ravel()
@@ -151,7 +169,7 @@ def solve_pair(g1, g2, knode, kedge, q, p=None, lmin=0,
     if not eval_gradient:
         return R, R.sum()
 
-    y = np.linalg.solve(A, px)            # A is symmetric
+    y = solve(px)                         # A is symmetric
     Q = 1.0 / (1.0 - q)
     grad = []
     for m in range(dp1.shape[0]):
@@ -163,8 +181,8 @@ def solve_pair(g1, g2, knode, kedge, q, p=None, lmin=0,
         if lmin == 1:
             g -= px @ s['dV'][m]
         grad.append(g)
-    for m in range(s['dW'].shape[0]):
-        grad.append(y @ (s['dW'][m] @ x))
+    for dWm in s['dW']:
+        grad.append(y @ (dWm @ x))
     return R, R.sum(), np.array(grad)
 
 

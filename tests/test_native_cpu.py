@@ -1,0 +1,207 @@
+"""CPU-side checks of the native library: it loads without a GPU driver,
+exports every symbol declared in include/graphdot_b200.h, the octile packer
+reproduces the graph, and NVRTC compiles the spliced solver for sm_100a for
+every fixture kernel (no compute calls without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_graphs, golden_kernels
+from graphdot_b200 import native
+from graphdot_b200.kernel.marginalized import MarginalizedGraphKernel
+from graphdot_b200.kernel.marginalized._backend_b200 import (
+    AttributeLayout, B200Backend, state_bytes, struct_decl)
+from graphdot_b200.kernel.marginalized.starting_probability import (Adhoc,
+                                                                    Uniform)
+from graphdot_b200.synthetic import make_config_graphs, make_config_kernel
+
+
+def test_library_exports_every_declared_symbol():
+    lib = native.load()
+    header = open(os.path.join(ROOT, 'include', 'graphdot_b200.h')).read()
+    declared = set(re.findall(r'\b(gdb_[a-z_0-9]+)\s*\(', header))
+    assert len(declared) >= 20
+    bound = {name for name, _, _ in native.SYMBOLS}
+    assert declared == bound
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b'graphdot_b200' in lib.gdb_version()
+    tpl = lib.gdb_solver_template().decode()
+    assert 'mlgk_solve' in tpl and 'gdb_pcg' in tpl
+
+
+def test_no_device_is_reported_not_hidden():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('needs a machine without a GPU')
+    ctx = C.c_void_p()
+    rc = native.load().gdb_context_create(0, C.byref(ctx))
+    assert rc == -2 and native.load().gdb_last_error()
+    with pytest.raises(native.NativeError):
+        native.pinned_empty(4, np.float32)
+
+
+def _unpack(blob, edge_size, label_off):
+    """Decode a packed blob back into (degree, dense weight/label index)."""
+    hdr = np.frombuffer(blob[:64], dtype=np.uint32)
+    n, n_oct, nnz, n_tile = hdr[:4].astype(int)
+    off_deg, off_node, off_oct, off_trow, off_edge, off_pool, total = \
+        hdr[4:11].astype(int)
+    assert total == len(blob) and total % 16 == 0
+    degree = np.frombuffer(blob[off_deg:off_deg + 4 * n], dtype=np.float32)
+    oct_dt = np.dtype([('mask', '<u8'), ('start', '<u4'), ('trow', '<u2'),
+                       ('tcol', '<u2')])
+    octs = np.frombuffer(blob[off_oct:off_oct + 16 * n_oct], dtype=oct_dt)
+    trow = np.frombuffer(blob[off_trow:off_trow + 4 * (n_tile + 1)],
+                         dtype=np.uint32)
+    entries = {}
+    k = 0
+    for o, t in enumerate(octs):
+        assert t['start'] == k
+        assert trow[t['trow']] <= o < trow[t['trow'] + 1]
+        for bit in range(64):
+            if int(t['mask']) >> bit & 1:
+                i, j = 8 * int(t['trow']) + bit // 8, 8 * int(t['tcol']) + bit % 8
+                entries[(i, j)] = blob[off_edge + k * edge_size:
+                                       off_edge + (k + 1) * edge_size]
+                k += 1
+    assert k == nnz
+    keys = [(int(t['trow']), int(t['tcol'])) for t in octs]
+    assert keys == sorted(keys) and len(set(keys)) == len(keys)
+    return n, degree, entries
+
+
+def test_octile_packer_roundtrip():
+    be = B200Backend()
+    rng = np.random.default_rng(5)
+    graphs = make_config_graphs('C2', 6) + make_config_graphs('C1', 3)
+    for g in graphs:
+        p = be.pack_graph(g)
+        assert be.pack_graph(g) is p            # cookie cache
+        weighted = '!w' in g.edges
+        el = AttributeLayout(g.edges, drop=('!i', '!j', '!w'))
+        label_off = 4 if weighted else 0
+        edge_size = label_off + el.dtype.itemsize
+        n, degree, entries = _unpack(p.blob.tobytes(), edge_size, label_off)
+        assert n == len(g.nodes)
+        ei, ej = np.asarray(g.edges['!i']), np.asarray(g.edges['!j'])
+        w = np.asarray(g.edges['!w']) if weighted else np.ones(len(ei))
+        want_deg = np.zeros(n)
+        np.add.at(want_deg, ei, w)
+        np.add.at(want_deg, ej, w)
+        assert np.allclose(degree, want_deg, rtol=1e-6)
+        assert len(entries) == 2 * len(ei)
+        labels = np.zeros(len(ei), dtype=el.dtype)
+        for k, _, _ in el.fields:
+            if k in g.edges:
+                labels[k] = np.asarray(g.edges[k])
+        for k, (i, j) in enumerate(zip(ei, ej)):
+            for key in ((i, j), (j, i)):
+                raw = entries[key]
+                if weighted:
+                    assert np.frombuffer(raw[:4], np.float32)[0] == w[k]
+                assert raw[label_off:] == labels[k].tobytes()
+    # invalidation: unify_datatype / permute(inplace) clear the cookie
+    g = graphs[0]
+    g.permute(rng.permutation(len(g.nodes)), inplace=True)
+    assert be.uuid not in g.cookie
+
+
+def test_isolated_node_gets_unit_degree():
+    from graphdot_b200 import Graph
+    g = Graph({'!i': np.arange(3, dtype=np.uint32)},
+              {'!i': np.array([0], np.uint32), '!j': np.array([1], np.uint32)})
+    be = B200Backend()
+    n, degree, entries = _unpack(be.pack_graph(g).blob.tobytes(), 1, 0)
+    assert list(degree) == [1.0, 1.0, 1.0] and len(entries) == 2
+
+
+def test_variable_length_features_are_pooled(mlgk_golden):
+    G = golden_graphs(mlgk_golden['cases']['vario-features'])
+    be = B200Backend()
+    nl, el, weighted = be._layouts(G[0])
+    assert nl.decl == 'frozen_array<int16> rings;'
+    assert el.decl == 'frozen_array<int16> spectrum;'
+    assert nl.dtype.itemsize == 16 and nl.ptr_offsets == [0] and weighted
+    blob = be.pack_graph(G[0]).blob.tobytes()
+    hdr = np.frombuffer(blob[:64], dtype=np.uint32)
+    off_node, off_pool = int(hdr[5]), int(hdr[9])
+    rows = np.frombuffer(blob[off_node:off_node + 3 * 16], dtype=nl.dtype)
+    want = [[5, 6], [3], [2, 3, 4]]
+    for r, w in zip(rows['rings'], want):
+        start = int(r['_data'])        # blob-relative after packing
+        assert start >= off_pool and int(r['size']) == len(w)
+        got = np.frombuffer(blob[start:start + 2 * len(w)], dtype=np.int16)
+        assert list(got) == w
+
+
+def test_struct_decl_and_state_bytes():
+    knode, kedge = golden_kernels('labeled')
+    decl = struct_decl(knode.dtype)
+    assert decl == ('struct{struct{float32 h;}hybridization;struct{struct{'
+                    'float32 length_scale;}k1;struct{float32 c;}k2;}charge;}'
+                    'kernel;')
+    raw = state_bytes(knode)
+    assert np.allclose(np.frombuffer(raw, np.float32), [0.3, 1.0, 0.01])
+    from graphdot_b200.microkernel import Product, TensorProduct
+    assert state_bytes(Product()) is None
+    k = TensorProduct(weight=Product(), label=kedge)
+    assert struct_decl(k.dtype).startswith('struct{struct{')
+    assert state_bytes(Adhoc(lambda n: 1, 'n.x')) == b'\0'
+    assert np.frombuffer(state_bytes(Uniform(2.5)), np.float32)[0] == 2.5
+
+
+CASES = ['unlabeled', 'labeled', 'weighted', 'vario-features', 'molecular']
+
+
+@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('traits', [
+    dict(symmetric=True), dict(symmetric=True, eval_gradient=True),
+    dict(diagonal=True, nodal=True), dict(nodal=True, lmin=1),
+    dict(diagonal=True, nodal='block'), dict(diagonal=True, eval_gradient=True,
+                                             lmin=1)])
+def test_nvrtc_compiles_fixture_kernels_for_sm100a(mlgk_golden, name, traits):
+    lib = native.load()
+    G = golden_graphs(mlgk_golden['cases'][name])
+    knode, kedge = golden_kernels(name)
+    nl, el, weighted = B200Backend._layouts(G[0])
+    for block in (32, 128):
+        d, keep, _ = B200Backend._desc(
+            nl, el, weighted, knode, kedge, Uniform(1.0),
+            MarginalizedGraphKernel.traits(**traits), block, ())
+        size = C.c_uint64()
+        rc = lib.gdb_program_compile_only(C.byref(d), C.byref(size))
+        assert rc == 0, lib.gdb_last_error().decode()
+        assert size.value > 1000
+
+
+def test_compile_errors_are_reported():
+    lib = native.load()
+    g = make_config_graphs('C2', 1)[0]
+    k = make_config_kernel('C2', backend=B200Backend())
+    nl, el, weighted = B200Backend._layouts(g)
+    T = MarginalizedGraphKernel.traits
+    bad_p = Adhoc(lambda nodes: np.ones(len(nodes)), 'n.no_such_attribute')
+    d, keep, _ = B200Backend._desc(nl, el, weighted, k.node_kernel,
+                                   k.edge_kernel, bad_p, T(), 32, ())
+    assert lib.gdb_program_compile_only(C.byref(d), None) == -3
+    assert b'no_such_attribute' in lib.gdb_last_error()
+    d, keep, _ = B200Backend._desc(nl, el, weighted, k.node_kernel,
+                                   k.edge_kernel, Uniform(1.0), T(), 48, ())
+    assert lib.gdb_program_compile_only(C.byref(d), None) == -1
+    d, keep, _ = B200Backend._desc(
+        nl, el, weighted, k.node_kernel, k.edge_kernel, Uniform(1.0),
+        T(nodal=True, eval_gradient=True), 32, ())
+    assert lib.gdb_program_compile_only(C.byref(d), None) == -1
+
+
+def test_heterogeneous_graphs_raise_type_error():
+    be = B200Backend()
+    kernel = make_config_kernel('C2', backend=be)
+    a = make_config_graphs('C2', 1)[0]
+    b = make_config_graphs('C1', 1)[0]
+    with pytest.raises(TypeError):
+        kernel([a, b])
