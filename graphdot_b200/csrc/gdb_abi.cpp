@@ -545,15 +545,16 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
         if (a->i1 > gs->n || a->j1 > gs->n || a->i0 > a->i1 || a->j0 > a->j1) return gdb_fail(GDB_ERR_INVALID, "job rectangle out of range");
         n_jobs = (uint64_t)(a->i1 - a->i0) * (a->j1 - a->j0);
     } else if (a->job_mode == GDB_JOBS_TRIU) {
-        if (a->i1 > gs->n || a->i0 > a->i1) return gdb_fail(GDB_ERR_INVALID, "job triangle out of range");
-        const uint64_t n = a->i1 - a->i0;
-        n_jobs = n * (n + 1) / 2;
+        if (a->i1 > gs->n || a->j1 > gs->n || a->i0 > a->i1 || a->i1 > a->j1) return gdb_fail(GDB_ERR_INVALID, "job triangle out of range");
+        const uint64_t rows = a->i1 - a->i0, m = a->j1 - a->i0;
+        n_jobs = rows * m - rows * (rows - 1) / 2;
     } else {
         return gdb_fail(GDB_ERR_INVALID, "unknown job_mode %d", a->job_mode);
     }
     if (a->n_starts < gs->n) return gdb_fail(GDB_ERR_INVALID, "starts has %u entries for %u graphs", a->n_starts, gs->n);
     a->kernel_ms = a->h2d_ms = a->d2h_ms = 0.f;
-    a->cg_iterations = a->matvec_products = 0;
+    a->cg_iterations = a->matvec_products = a->vector_elements = 0;
+    a->h2d_bytes = a->d2h_bytes = 0;
     a->n_launches = 0;
     if (n_jobs == 0) return GDB_OK;
 
@@ -604,8 +605,16 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
 
     // ---- inputs -----------------------------------------------------------------
     RT(cudaEventRecord(c->ev[0], st));
-    if (a->job_mode == GDB_JOBS_LIST) RT(cudaMemcpyAsync(c->jobs.ptr, a->jobs, n_jobs * 8, cudaMemcpyHostToDevice, st));
+    if (a->upload_graphs) {
+        RT(cudaMemcpyAsync(gs->dev, gs->host, gs->bytes, cudaMemcpyHostToDevice, st));
+        a->h2d_bytes += gs->bytes;
+    }
+    if (a->job_mode == GDB_JOBS_LIST) {
+        RT(cudaMemcpyAsync(c->jobs.ptr, a->jobs, n_jobs * 8, cudaMemcpyHostToDevice, st));
+        a->h2d_bytes += n_jobs * 8;
+    }
     RT(cudaMemcpyAsync(c->starts.ptr, a->starts, (size_t)a->n_starts * 4, cudaMemcpyHostToDevice, st));
+    a->h2d_bytes += (uint64_t)a->n_starts * 4;
     RT(cudaMemsetAsync(c->counters.ptr, 0, 64, st));
     RT(cudaMemsetAsync(c->gram.ptr, 0, plane * 4, st));
     if (grad_floats) RT(cudaMemsetAsync(c->grad.ptr, 0, grad_floats * 4, st));
@@ -626,6 +635,7 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     f.nX = a->nX, f.nY = a->nY, f.nJ = a->nJ;
     f.q = a->q, f.eps = a->eps, f.ftol = a->ftol, f.gtol = a->gtol;
     f.smem_bytes = (uint32_t)smem;
+    f.row0 = a->row0, f.col0 = a->col0;
     memcpy(params.data(), &f, sizeof f);
     const void *thetas[3] = {a->node_theta, a->edge_theta, a->p_theta};
     for (int k = 0; k < 3; ++k) {
@@ -645,6 +655,7 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     if (!a->keep_on_device) {
         RT(cudaMemcpyAsync(a->gramian, c->gram.ptr, plane * 4, cudaMemcpyDeviceToHost, st));
         if (grad_floats) RT(cudaMemcpyAsync(a->gradient, c->grad.ptr, grad_floats * 4, cudaMemcpyDeviceToHost, st));
+        a->d2h_bytes = (plane + grad_floats) * 4;
     }
     RT(cudaEventRecord(c->ev[3], st));
     RT(cudaStreamSynchronize(st));
@@ -654,6 +665,7 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     cudaEventElapsedTime(&a->d2h_ms, c->ev[2], c->ev[3]);
     a->cg_iterations = counters[1];
     a->matvec_products = counters[2];
+    a->vector_elements = counters[3];
     return GDB_OK;
 }
 

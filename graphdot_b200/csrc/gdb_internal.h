@@ -33,7 +33,7 @@ struct gdb_params_fixed_host {
     uint64_t scratch_stride, n_jobs;
     uint32_t job_mode, i0, i1, j0, j1, nX, nY, nJ;
     float q, eps, ftol, gtol;
-    uint32_t smem_bytes, pad0, pad1, pad2;
+    uint32_t smem_bytes, row0, col0, pad2;
 };
 static_assert(sizeof(gdb_params_fixed_host) == 136, "params layout");
 

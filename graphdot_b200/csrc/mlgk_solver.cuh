@@ -76,12 +76,12 @@ struct gdb_params_fixed {
     float *gram;
     float *grad;
     float *scratch;
-    unsigned long long *counters;  // [0] next job, [1] CG iterations, [2] products
+    unsigned long long *counters;  // [0] next job, [1] CG iterations, [2] products, [3] vector elements
     unsigned long long scratch_stride;
     unsigned long long n_jobs;
     unsigned job_mode, i0, i1, j0, j1, nX, nY, nJ;
     float q, eps, ftol, gtol;
-    unsigned smem_bytes, pad0, pad1, pad2;
+    unsigned smem_bytes, row0, col0, pad2;
 };
 
 struct gdb_params {
@@ -264,16 +264,16 @@ __device__ __forceinline__ void gdb_decode_job(const gdb_params_fixed &f, unsign
         a = f.i0 + (unsigned)(idx / nj);
         b = f.j0 + (unsigned)(idx % nj);
     } else {
-        // upper triangle of [i0, i1): row r holds n - r entries
-        const double n = (double)(f.i1 - f.i0);
-        double rr = floor(((2.0 * n + 1.0) - sqrt((2.0 * n + 1.0) * (2.0 * n + 1.0) - 8.0 * (double)idx)) * 0.5);
-        long long row = (long long)rr;
-        const long long nn = (long long)(f.i1 - f.i0);
-        while (row > 0 && (unsigned long long)(row * nn - row * (row - 1) / 2) > idx) --row;
-        while ((unsigned long long)((row + 1) * nn - (row + 1) * row / 2) <= idx) ++row;
-        const unsigned long long first = (unsigned long long)(row * nn - row * (row - 1) / 2);
+        // rows i in [i0, i1), columns j in [i, j1): local row r holds m - r entries
+        const long long m = (long long)f.j1 - (long long)f.i0;
+        const double md = (double)m;
+        long long row = (long long)floor(((2.0 * md + 1.0) - sqrt((2.0 * md + 1.0) * (2.0 * md + 1.0) - 8.0 * (double)idx)) * 0.5);
+        if (row < 0) row = 0;
+        while (row > 0 && (unsigned long long)(row * m - row * (row - 1) / 2) > idx) --row;
+        while ((unsigned long long)((row + 1) * m - (row + 1) * row / 2) <= idx) ++row;
+        const unsigned long long first = (unsigned long long)(row * m - row * (row - 1) / 2);
         a = f.i0 + (unsigned)row;
-        b = f.i0 + (unsigned)row + (unsigned)(idx - first);
+        b = a + (unsigned)(idx - first);
     }
 }
 
@@ -363,16 +363,18 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
         if (threadIdx.x == 0) {
             atomicAdd(F.counters + 1, (unsigned long long)iters);
             atomicAdd(F.counters + 2, (unsigned long long)iters * (unsigned long long)g1.nnz * (unsigned long long)g2.nnz);
+            atomicAdd(F.counters + 3, (unsigned long long)iters * (unsigned long long)N);
         }
 
-        const unsigned I1 = F.starts[ja], I2 = F.starts[jb];
+        const unsigned I1 = F.starts[ja] - F.row0, I2 = F.starts[jb] - F.col0;
         const unsigned long long plane = (unsigned long long)F.nX * F.nY;
 
         // ---- epilogue: apply starting probabilities, write the Gram entry ----
 #if GDB_NODAL == 2
         for (int i = threadIdx.x; i < (int)N; i += GDB_BLOCK) {
             const int i1 = i / n2, i2 = i - i1 * n2;
-            float xi = x[i];
+            // a self pair is symmetric in exact arithmetic; make it bit-exact
+            float xi = 0.5f * (x[i] + x[i2 * n2 + i1]);
 #if GDB_LMIN == 1
             xi -= P.node_kernel(g1.node[i1], g2.node[i2]);
 #endif
@@ -391,6 +393,9 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
         for (int i = threadIdx.x; i < (int)N; i += GDB_BLOCK) {
             const int i1 = i / n2, i2 = i - i1 * n2;
             float xi = x[i];
+#if GDB_SYMMETRIC
+            if (ja == jb) xi = 0.5f * (xi + x[i2 * n2 + i1]);  // bit-exact symmetry of self pairs
+#endif
 #if GDB_LMIN == 1
             xi -= P.node_kernel(g1.node[i1], g2.node[i2]);
 #endif

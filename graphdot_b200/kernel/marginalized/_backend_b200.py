@@ -156,6 +156,48 @@ class _Functor:
         return (self.theta_decl, self.expr, tuple(self.jac))
 
 
+class PairJobs:
+    """Implicit pair-job set -- a rectangle ``i in [i0,i1), j in [j0,j1)``
+    or the triangle ``i in [i0,i1), j in [i,j1)`` of graph indices -- decoded
+    on the device from a linear index, so that no 8-byte-per-pair job list is
+    materialised (the reference's list is 800 MB for a 10k x 10k block,
+    reference _kernel.py:172-182).  ``np.asarray`` yields the explicit list
+    for back ends that need one."""
+
+    def __init__(self, mode, i0, i1, j0, j1):
+        self.mode, self.i0, self.i1, self.j0, self.j1 = mode, i0, i1, j0, j1
+
+    @classmethod
+    def rect(cls, i0, i1, j0, j1):
+        return cls(native.JOBS_RECT, i0, i1, j0, j1)
+
+    @classmethod
+    def triu(cls, i0, i1, j1=None):
+        return cls(native.JOBS_TRIU, i0, i1, i0, i1 if j1 is None else j1)
+
+    def __len__(self):
+        if self.mode == native.JOBS_RECT:
+            return (self.i1 - self.i0) * (self.j1 - self.j0)
+        rows, m = self.i1 - self.i0, self.j1 - self.i0
+        return rows * m - rows * (rows - 1) // 2
+
+    def __array__(self, dtype=None, copy=None):
+        if self.mode == native.JOBS_RECT:
+            i, j = np.divmod(np.arange(len(self)), self.j1 - self.j0)
+            i, j = i + self.i0, j + self.j0
+        else:
+            i = np.repeat(np.arange(self.i0, self.i1),
+                          self.j1 - np.arange(self.i0, self.i1))
+            first = np.cumsum(self.j1 - np.arange(self.i0, self.i1))
+            first = np.concatenate([[0], first[:-1]])
+            j = np.arange(len(self)) - np.repeat(
+                first, self.j1 - np.arange(self.i0, self.i1)) + i
+        out = np.empty(len(self), dtype=np.dtype([('i', np.uint32),
+                                                  ('j', np.uint32)]))
+        out['i'], out['j'] = i, j
+        return out
+
+
 class PackedGraph:
     __slots__ = ('blob', 'n_node', 'key')
 
@@ -213,8 +255,12 @@ class B200Backend(Backend):
         Extra NVRTC options (the reference's ``nvcc_extra``).
     """
 
+    pair_jobs = PairJobs     # front ends may hand over implicit job grids
+
     @staticmethod
     def array(ndarray):
+        if isinstance(ndarray, PairJobs):
+            return ndarray
         out = native.pinned_empty(ndarray.size, ndarray.dtype)
         out[:] = ndarray.ravel()
         return out
@@ -418,11 +464,30 @@ class B200Backend(Backend):
         timer.toc('code generation + JIT')
 
         timer.tic('GPU kernel execution')
+        a = self.launch(gs, prog, node_kernel, edge_kernel, p, q, eps, ftol,
+                        gtol, jobs, starts, gramian, gradient, nX, nY, nJ,
+                        stream=stream, keep_on_device=keep_on_device)
+        timer.toc('GPU kernel execution')
+        return a
+
+    def launch(self, gs, prog, node_kernel, edge_kernel, p, q, eps, ftol,
+               gtol, jobs, starts, gramian, gradient, nX, nY, nJ, row0=0,
+               col0=0, stream=None, keep_on_device=False, upload=False):
+        """One ``gdb_solve`` call.  ``jobs`` is an explicit (i, j) array or a
+        ``PairJobs`` grid descriptor (no per-pair host data)."""
+        lib = native.load()
         a = native.SolveArgs()
-        jobs = np.ascontiguousarray(jobs)
-        a.job_mode = native.JOBS_LIST
-        a.jobs = jobs.ctypes.data
-        a.n_jobs = len(jobs)
+        if isinstance(jobs, PairJobs):
+            a.job_mode = jobs.mode
+            a.i0, a.i1, a.j0, a.j1 = jobs.i0, jobs.i1, jobs.j0, jobs.j1
+            n_jobs = len(jobs)
+        else:
+            jobs = np.ascontiguousarray(jobs)
+            a.job_mode = native.JOBS_LIST
+            a.jobs = jobs.ctypes.data
+            a.n_jobs = n_jobs = len(jobs)
+        a.row0, a.col0 = int(row0), int(col0)
+        a.upload_graphs = int(upload)
         starts = np.ascontiguousarray(starts, dtype=np.uint32)
         a.starts = starts.ctypes.data
         a.n_starts = len(starts)
@@ -440,12 +505,12 @@ class B200Backend(Backend):
         a.stream = stream
         a.keep_on_device = int(keep_on_device)
         native.check(lib.gdb_solve(self.context, prog, gs.handle, C.byref(a)))
-        timer.toc('GPU kernel execution')
         self.last = dict(kernel_ms=a.kernel_ms, h2d_ms=a.h2d_ms,
                          d2h_ms=a.d2h_ms, cg_iterations=a.cg_iterations,
                          matvec_products=a.matvec_products,
-                         n_jobs=len(jobs), n_launches=a.n_launches,
-                         graph_bytes=gs.nbytes)
+                         vector_elements=a.vector_elements,
+                         h2d_bytes=a.h2d_bytes, d2h_bytes=a.d2h_bytes,
+                         n_jobs=n_jobs, n_launches=a.n_launches)
         return a
 
 

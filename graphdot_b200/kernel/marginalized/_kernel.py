@@ -138,13 +138,19 @@ class MarginalizedGraphKernel:
         nx, ny = len(X), (len(X) if Y is None else len(Y))
 
         timer.tic('generating jobs')
-        if traits.symmetric:
-            i, j = np.triu_indices(nx)
+        grid = getattr(backend, 'pair_jobs', None)
+        if grid is not None:
+            # implicit job grid, decoded on the device
+            pairs = (grid.triu(0, nx) if traits.symmetric
+                     else grid.rect(0, nx, nx, nx + ny))
         else:
-            i, j = np.divmod(np.arange(nx * ny), ny)
-            j = j + nx
-        pairs = np.empty(len(i), dtype=JOB_DTYPE)
-        pairs['i'], pairs['j'] = i, j
+            if traits.symmetric:
+                i, j = np.triu_indices(nx)
+            else:
+                i, j = np.divmod(np.arange(nx * ny), ny)
+                j = j + nx
+            pairs = np.empty(len(i), dtype=JOB_DTYPE)
+            pairs['i'], pairs['j'] = i, j
         jobs = backend.array(pairs)
         timer.toc('generating jobs')
 

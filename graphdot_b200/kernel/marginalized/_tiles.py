@@ -1,0 +1,180 @@
+"""Tiled evaluation of large (normalized) Gram matrices: the pair-job set of a
+symmetric Gram is cut into row-block tiles ``rows [i0,i1) x columns [i,n)``
+that are independent of each other, so any number of workers -- one per GPU,
+threads in one process or one process per GPU -- can pull them from a shared
+dynamic queue with no collective on the data path.
+
+The reference has no counterpart (it is single-GPU, reference
+_backend_cuda.py:49-52); the per-tile call is the same back-end solve that
+``MarginalizedGraphKernel.__call__`` issues, restricted to a tile and with a
+tile-sized output (``row0``), followed by the reference's normalization
+formulas (reference graphdot/kernel/fix.py:46-73) applied per tile.
+"""
+import threading
+
+import numpy as np
+
+from ._backend_b200 import B200Backend, PairJobs
+from ._kernel import MarginalizedGraphKernel
+
+
+def row_tiles(n, rows):
+    """Row blocks of the upper triangle, largest (top) first."""
+    return [(i0, min(i0 + rows, n)) for i0 in range(0, n, rows)]
+
+
+def tile_pairs(i0, i1, n):
+    rows, m = i1 - i0, n - i0
+    return rows * m - rows * (rows - 1) // 2
+
+
+class GramTileWorker:
+    """Evaluates tiles of the symmetric Gram matrix of ``graphs`` on one
+    device.  All graphs are resident on the device; outputs are tile-sized
+    page-locked host arrays that are reused from tile to tile."""
+
+    def __init__(self, kernel, graphs, backend=None, eval_gradient=False,
+                 max_rows=64, stream=None):
+        self.kernel = kernel
+        self.backend = backend or kernel.backend
+        self.graphs = list(graphs)
+        self.n = len(self.graphs)
+        self.eval_gradient = eval_gradient
+        self.stream = stream
+        be = self.backend
+        self.gs = be.graphset(self.graphs)
+        T = MarginalizedGraphKernel.traits
+        k = kernel
+        self.prog = be.program(gs=self.gs, node_kernel=k.node_kernel,
+                               edge_kernel=k.edge_kernel, p=k.p,
+                               traits=T(eval_gradient=eval_gradient))
+        self.prog_diag = be.program(gs=self.gs, node_kernel=k.node_kernel,
+                                    edge_kernel=k.edge_kernel, p=k.p,
+                                    traits=T(diagonal=True,
+                                             eval_gradient=eval_gradient))
+        self.nJ = k.n_dims
+        self.starts = np.arange(self.n + 1, dtype=np.uint32)
+        self.max_rows = max_rows
+        self.out = be.empty(max_rows * self.n, np.float32)
+        self.dout = (be.empty(max_rows * self.n * self.nJ, np.float32)
+                     if eval_gradient else None)
+        self.stats = dict(kernel_ms=0.0, cg_iterations=0, matvec_products=0,
+                          vector_elements=0, h2d_bytes=0, d2h_bytes=0,
+                          launches=0, pairs=0)
+
+    def _launch(self, prog, jobs, out, dout, nX, nY, row0=0, **kw):
+        k = self.kernel
+        a = self.backend.launch(self.gs, prog, k.node_kernel, k.edge_kernel,
+                                k.p, k.q, k.eps, k.ftol, k.gtol, jobs,
+                                self.starts, out, dout, nX, nY, self.nJ,
+                                row0=row0, stream=self.stream, **kw)
+        s = self.stats
+        s['kernel_ms'] += a.kernel_ms
+        s['cg_iterations'] += a.cg_iterations
+        s['matvec_products'] += a.matvec_products
+        s['vector_elements'] += a.vector_elements
+        s['h2d_bytes'] += a.h2d_bytes
+        s['d2h_bytes'] += a.d2h_bytes
+        s['launches'] += a.n_launches
+        s['pairs'] += len(jobs)
+        return a
+
+    def diag(self, upload=False):
+        """Self-similarities (and their Jacobians) of all graphs."""
+        n = self.n
+        jobs = np.empty(n, dtype=[('i', np.uint32), ('j', np.uint32)])
+        jobs['i'] = jobs['j'] = np.arange(n)
+        d = self.backend.empty(n, np.float32)
+        dd = (self.backend.empty(n * self.nJ, np.float32)
+              if self.eval_gradient else None)
+        self._launch(self.prog_diag, jobs, d, dd, n, 1, upload=upload)
+        d = np.array(d, dtype=float)
+        if dd is not None:
+            dd = np.array(dd, dtype=float).reshape(n, self.nJ, order='F')
+        return d, dd
+
+    def run_tile(self, i0, i1, keep_on_device=False):
+        """Raw tile: ``K[i - i0, j]`` for i in [i0,i1), j in [i,n) (zeros
+        left of the diagonal); views into reused pinned buffers."""
+        rows = i1 - i0
+        assert rows <= self.max_rows
+        out = self.out[:rows * self.n]
+        dout = (self.dout[:rows * self.n * self.nJ]
+                if self.dout is not None else None)
+        self._launch(self.prog, PairJobs.triu(i0, i1, self.n), out, dout,
+                     rows, self.n, row0=i0, keep_on_device=keep_on_device)
+        if keep_on_device:
+            return None, None
+        K = out.reshape(rows, self.n, order='F')
+        dK = (dout.reshape(rows, self.n, self.nJ, order='F')
+              if dout is not None else None)
+        return K, dK
+
+    @staticmethod
+    def normalize_tile(K, dK, i0, d, dd):
+        """K_ij / sqrt(K_ii K_jj) and its gradient for one raw tile
+        (reference kernel/fix.py:46-73)."""
+        rows = K.shape[0]
+        sl = d[i0:i0 + rows] ** -0.5
+        sr = d ** -0.5
+        Kn = sl[:, None] * K * sr[None, :]
+        if dK is None:
+            return Kn, None
+        rl = dd[i0:i0 + rows] / d[i0:i0 + rows, None]
+        rr = dd / d[:, None]
+        dKn = (sl[:, None, None] * dK * sr[None, :, None]
+               - 0.5 * Kn[:, :, None] * (rl[:, None, :] + rr[None, :, :]))
+        return Kn, dKn
+
+
+def gram_tiled(kernel, graphs, devices=(0,), eval_gradient=False,
+               normalize=True, tile_rows=64):
+    """(Normalized) symmetric Gram matrix -- and Jacobian over ALL
+    hyper-parameters -- of ``graphs`` using one worker thread per device that
+    pull row-block tiles from a shared queue."""
+    n = len(graphs)
+    tiles = row_tiles(n, tile_rows)
+    lock = threading.Lock()
+    cursor = [0]
+    K = np.zeros((n, n), dtype=np.float32)
+    dK = (np.zeros((n, n, kernel.n_dims), dtype=np.float32)
+          if eval_gradient else None)
+    errors = []
+
+    def work(dev):
+        try:
+            be = B200Backend(device=dev, block_size=getattr(
+                kernel.backend, 'block_size', None))
+            w = GramTileWorker(kernel, graphs, be, eval_gradient, tile_rows)
+            d = dd = None
+            if normalize:
+                d, dd = w.diag()
+            while True:
+                with lock:
+                    t = cursor[0]
+                    cursor[0] += 1
+                if t >= len(tiles):
+                    break
+                i0, i1 = tiles[t]
+                Kt, dKt = w.run_tile(i0, i1)
+                if normalize:
+                    Kt, dKt = w.normalize_tile(Kt, dKt, i0, d, dd)
+                K[i0:i1] = Kt
+                if dK is not None:
+                    dK[i0:i1] = dKt
+        except Exception as e:      # surfaced in the caller's thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(d,)) for d in devices]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    iu = np.triu_indices(n, 1)
+    K[(iu[1], iu[0])] = K[iu]
+    if dK is not None:
+        dK[(iu[1], iu[0])] = dK[iu]
+        return K, dK
+    return K

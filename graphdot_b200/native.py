@@ -87,10 +87,14 @@ class SolveArgs(C.Structure):
                 ('p_theta', C.c_void_p),
                 ('gramian', C.c_void_p), ('gradient', C.c_void_p),
                 ('nX', C.c_uint32), ('nY', C.c_uint32), ('nJ', C.c_uint32),
+                ('row0', C.c_uint32), ('col0', C.c_uint32),
+                ('upload_graphs', C.c_int32),
                 ('stream', C.c_void_p), ('keep_on_device', C.c_int32),
                 ('kernel_ms', C.c_float), ('h2d_ms', C.c_float),
                 ('d2h_ms', C.c_float), ('cg_iterations', C.c_uint64),
-                ('matvec_products', C.c_uint64), ('n_launches', C.c_uint32)]
+                ('matvec_products', C.c_uint64),
+                ('vector_elements', C.c_uint64), ('h2d_bytes', C.c_uint64),
+                ('d2h_bytes', C.c_uint64), ('n_launches', C.c_uint32)]
 
 
 # every symbol declared in include/graphdot_b200.h: (name, restype, argtypes)

@@ -178,7 +178,7 @@ int gdb_graphset_destroy(gdb_graphset_t gs);
  * Jacobian) at starts[i], starts[j] of the Fortran-ordered outputs. */
 #define GDB_JOBS_LIST 0 /* explicit (i, j) pairs                          */
 #define GDB_JOBS_RECT 1 /* all (i, j) with i in [i0,i1), j in [j0,j1)     */
-#define GDB_JOBS_TRIU 2 /* all i <= j in [i0,i1)                          */
+#define GDB_JOBS_TRIU 2 /* all (i, j) with i in [i0,i1), j in [i,j1)      */
 
 typedef struct gdb_solve_args {
     int32_t job_mode;
@@ -192,6 +192,12 @@ typedef struct gdb_solve_args {
     float *gramian;           /* host; nX*nY floats, Fortran order         */
     float *gradient;          /* host or NULL; nX*nY*nJ floats             */
     uint32_t nX, nY, nJ;
+    uint32_t row0, col0;      /* subtracted from starts[i] / starts[j]: lets
+                                 a tile of a larger Gram use a tile-sized
+                                 output                                    */
+    int32_t upload_graphs;    /* 1: re-send the graph set's pinned host image
+                                 first (host->device leg of an end-to-end
+                                 call)                                     */
     void *stream;             /* CUstream to run on; NULL = context stream */
     int32_t keep_on_device;   /* 1: skip the device->host copy; outputs
                                  stay in the context's device buffers      */
@@ -200,6 +206,8 @@ typedef struct gdb_solve_args {
     float h2d_ms, d2h_ms;
     uint64_t cg_iterations;   /* total PCG iterations over all jobs        */
     uint64_t matvec_products; /* total nnz1*nnz2 products evaluated        */
+    uint64_t vector_elements; /* total N = n1*n2 summed over CG iterations */
+    uint64_t h2d_bytes, d2h_bytes;
     uint32_t n_launches;
 } gdb_solve_args;
 

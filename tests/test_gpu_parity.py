@@ -341,6 +341,41 @@ def test_c4_large_pair_uses_global_arena(backend):
     assert rel_err(Kn, R) < GRAM_RTOL
 
 
+def test_implicit_job_grids_match_explicit_lists(backend):
+    """Device-side decoding of rectangular / triangular job grids (incl. a
+    row-block tile written into a tile-sized output) against explicit (i, j)
+    lists, bit for bit."""
+    from graphdot_b200.kernel.marginalized._backend_b200 import PairJobs
+    from graphdot_b200.util import Timer
+    G = make_config_graphs('C2', 9)
+    kernel = make_config_kernel('C2', backend=backend)
+    K = kernel(G)
+    T = MarginalizedGraphKernel.traits
+    gs = backend.graphset(G)
+
+    def run(jobs, traits, nX, nY, row0=0, col0=0):
+        prog = backend.program(gs, kernel.node_kernel, kernel.edge_kernel,
+                               kernel.p, traits)
+        out = backend.zeros(nX * nY, np.float32)
+        starts = np.arange(len(G) + 1, dtype=np.uint32)
+        backend.launch(gs, prog, kernel.node_kernel, kernel.edge_kernel,
+                       kernel.p, kernel.q, kernel.eps, kernel.ftol,
+                       kernel.gtol, jobs, starts, out, None, nX, nY, 5,
+                       row0=row0, col0=col0)
+        return out.reshape(nX, nY, order='F').astype(float)
+
+    sym = T(symmetric=True)
+    a = run(PairJobs.triu(0, 9), sym, 9, 9)
+    b = run(np.asarray(PairJobs.triu(0, 9)), sym, 9, 9)
+    assert np.array_equal(a, b) and np.array_equal(a, K)
+    tile = run(PairJobs.triu(3, 6, 9), T(), 3, 9, row0=3)
+    for i in range(3, 6):
+        assert np.array_equal(tile[i - 3, i:], K[i, i:])
+        assert np.all(tile[i - 3, :i] == 0)
+    rect = run(PairJobs.rect(2, 4, 5, 9), T(), 2, 4, row0=2, col0=5)
+    assert np.array_equal(rect, K[2:4, 5:9])
+
+
 def test_block_sizes_agree(backend):
     G = make_config_graphs('C2', 6)
     ref = None

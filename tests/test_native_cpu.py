@@ -198,6 +198,22 @@ def test_compile_errors_are_reported():
     assert lib.gdb_program_compile_only(C.byref(d), None) == -1
 
 
+def test_pair_jobs_descriptor_matches_explicit_lists():
+    from graphdot_b200.kernel.marginalized._backend_b200 import PairJobs
+    t = np.asarray(PairJobs.triu(0, 7))
+    i, j = np.triu_indices(7)
+    assert len(PairJobs.triu(0, 7)) == 28
+    assert np.array_equal(t['i'], i) and np.array_equal(t['j'], j)
+    t = np.asarray(PairJobs.triu(2, 5, 9))      # rows 2..4, columns i..8
+    want = [(a, b) for a in range(2, 5) for b in range(a, 9)]
+    assert len(PairJobs.triu(2, 5, 9)) == len(want)
+    assert [tuple(x) for x in t.tolist()] == want
+    r = np.asarray(PairJobs.rect(1, 3, 4, 7))
+    assert [tuple(x) for x in r.tolist()] == \
+        [(a, b) for a in range(1, 3) for b in range(4, 7)]
+    assert B200Backend.array(PairJobs.rect(0, 1, 0, 1)).mode == 1
+
+
 def test_heterogeneous_graphs_raise_type_error():
     be = B200Backend()
     kernel = make_config_kernel('C2', backend=be)
