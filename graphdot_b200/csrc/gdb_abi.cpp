@@ -28,6 +28,7 @@
 
 extern const char *const gdb_embedded_prelude;
 extern const char *const gdb_embedded_solver;
+extern const char *const gdb_embedded_small;
 
 // ---------------------------------------------------------------------------
 // errors
@@ -49,7 +50,8 @@ extern "C" const char *gdb_version(void) { return "graphdot_b200 0.1.0 (sm_100a,
 extern "C" void gdb_free(void *p) { free(p); }
 
 extern "C" const char *gdb_solver_template(void) {
-    static std::string joined = std::string(gdb_embedded_prelude) + "\n/* <generated splice> */\n" + gdb_embedded_solver;
+    static std::string joined = std::string(gdb_embedded_prelude) + "\n/* <generated splice> */\n" + gdb_embedded_solver +
+                                "\n" + gdb_embedded_small;
     return joined.c_str();
 }
 
@@ -213,7 +215,9 @@ extern "C" int gdb_host_free(void *p) {
 struct gdb_program_s {
     gdb_context_t ctx = nullptr;
     CUmodule mod = nullptr;
-    CUfunction fn = nullptr;
+    CUfunction fn = nullptr;        // mlgk_solve: any pair size
+    CUfunction fn_small = nullptr;  // mlgk_solve_small: pair resident in shared memory
+    int small_regs = 0, small_static_smem = 0;
     unsigned layout[8] = {};
     std::string source, log;
     gdb_program_info info{};
@@ -279,7 +283,7 @@ static int render(const gdb_program_desc *d, std::string &src) {
             o << "static_assert(sizeof(" << names[k] << "_theta_t) == " << fs[k]->theta_size << ", \"" << names[k]
               << " hyper-parameter layout differs from the host dtype\");\n";
     o << "// ---- end of generated splice ----\n";
-    o << gdb_embedded_solver << "\n";
+    o << gdb_embedded_solver << "\n" << gdb_embedded_small << "\n";
     src = o.str();
     return GDB_OK;
 }
@@ -386,6 +390,12 @@ extern "C" int gdb_program_create(gdb_context_t c, const gdb_program_desc *d, gd
     p->info.local_bytes = v;
     p->info.max_dynamic_smem = (int)c->prop.sharedMemPerBlockOptin - p->info.static_smem;
     DRV(c, c->cuFuncSetAttribute(p->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, p->info.max_dynamic_smem));
+    DRV(c, c->cuModuleGetFunction(&p->fn_small, p->mod, "mlgk_solve_small"));
+    c->cuFuncGetAttribute(&p->small_regs, CU_FUNC_ATTRIBUTE_NUM_REGS, p->fn_small);
+    c->cuFuncGetAttribute(&p->small_static_smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, p->fn_small);
+    DRV(c, c->cuFuncSetAttribute(p->fn_small, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                 (int)c->prop.sharedMemPerBlockOptin - p->small_static_smem));
+    p->info.num_regs_small = p->small_regs;
     p->info.n_jac = (int)p->layout[7];
     p->info.from_cache = 0;
     p->info.compile_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -427,6 +437,8 @@ struct gdb_graphset_s {
     std::vector<uint32_t> n_node, blob_bytes, nnz;
     uint32_t max_blob[2] = {0, 0};  // two largest blobs
     uint32_t max_node[2] = {0, 0};  // two largest node counts
+    uint32_t max_nnz[2] = {0, 0};   // two largest element counts
+    bool index16 = true;            // every graph carries a valid 16-bit row index
 };
 
 extern "C" int gdb_graphset_create(gdb_context_t c, const gdb_layout *L, uint32_t n, const void *const *blobs,
@@ -492,11 +504,14 @@ extern "C" int gdb_graphset_create(gdb_context_t c, const gdb_layout *L, uint32_
         };
         top2(gs->max_blob, (uint32_t)blob_bytes[k]);
         top2(gs->max_node, (uint32_t)h->n_node);
+        top2(gs->max_nnz, (uint32_t)h->nnz);
+        if (!(h->flags & 2u)) gs->index16 = false;
         off += blob_bytes[k];
     }
     if (n == 1) {
         gs->max_blob[1] = gs->max_blob[0];
         gs->max_node[1] = gs->max_node[0];
+        gs->max_nnz[1] = gs->max_nnz[0];
     }
     *out = gs;
     return gdb_graphset_upload(gs);
@@ -590,9 +605,23 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     } else {
         smem = 0;
     }
+    // small-pair kernel: blobs + cached edge products + diag + 4 vectors (x2 with
+    // gradients) of the largest possible pair must fit in shared memory
+    CUfunction fn = p->fn;
+    {
+        const uint64_t nrhs = p->eval_gradient ? 2 : 1;
+        const uint64_t wmax = ((uint64_t)gs->max_nnz[0] * gs->max_nnz[0] + 3) & ~3ull;
+        const uint64_t small_need = graphs_need + wmax * 4 + maxNpad * 4 + 4 * nrhs * maxNpad * 4;
+        const uint64_t small_cap = std::min<uint64_t>(cap, (uint64_t)c->prop.sharedMemPerBlockOptin - p->small_static_smem);
+        if (gs->index16 && small_need <= small_cap && !getenv("GDB_FORCE_GENERAL")) {
+            fn = p->fn_small;
+            smem = small_need;
+            spill = false;
+        }
+    }
+    a->used_small_kernel = (fn == p->fn_small);
     int blocks_per_sm = 0;
-    DRV(c, c->cuOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, p->fn, block, (size_t)smem));
-    if (blocks_per_sm < 1) return gdb_fail(GDB_ERR_CUDA, "kernel does not fit on an SM (block %d, smem %llu)", block, (unsigned long long)smem);
+    DRV(c, c->cuOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, block, (size_t)smem));
     uint64_t grid = (uint64_t)c->prop.multiProcessorCount * blocks_per_sm;
     if (spill) {
         // bound the arena: at most ~1/4 of device memory
@@ -647,8 +676,10 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     void *kargs[1] = {params.data()};
 
     RT(cudaEventRecord(c->ev[1], st));
-    DRV(c, c->cuLaunchKernel(p->fn, (unsigned)grid, 1, 1, (unsigned)block, 1, 1, (unsigned)smem, (CUstream)st, kargs, nullptr));
+    DRV(c, c->cuLaunchKernel(fn, (unsigned)grid, 1, 1, (unsigned)block, 1, 1, (unsigned)smem, (CUstream)st, kargs, nullptr));
     a->n_launches = 1;
+    a->grid = (uint32_t)grid;
+    a->smem_bytes = (uint32_t)smem;
     RT(cudaEventRecord(c->ev[2], st));
     unsigned long long counters[4] = {0, 0, 0, 0};
     RT(cudaMemcpyAsync(counters, c->counters.ptr, sizeof counters, cudaMemcpyDeviceToHost, st));

@@ -11,7 +11,7 @@ struct gdb_graph_hdr_host {
     int32_t n_node, n_octile, nnz, n_tile;
     uint32_t off_degree, off_node, off_octile, off_tilerow;
     uint32_t off_edge, off_pool, blob_bytes, flags;
-    uint32_t reserved[4];
+    uint32_t off_emeta, off_rowptr, off_rowadj, off_tileelem;
 };
 static_assert(sizeof(gdb_graph_hdr_host) == GDB_HDR_BYTES, "header layout");
 

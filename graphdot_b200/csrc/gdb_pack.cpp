@@ -24,6 +24,7 @@ struct Sizes {
     uint32_t edge_size, label_off;
     uint32_t nnz, n_octile, n_tile;
     uint64_t off_degree, off_node, off_octile, off_tilerow, off_edge, off_pool, total;
+    uint64_t off_emeta, off_rowptr, off_rowadj, off_tileelem;
 };
 
 struct Nz {
@@ -74,7 +75,15 @@ void plan(const gdb_layout *L, const gdb_graph_src *g, const std::vector<Nz> &nz
     s.off_octile = s.off_node + pad16((uint64_t)L->node_size * g->n_node);
     s.off_tilerow = s.off_octile + 16ull * s.n_octile;
     s.off_edge = s.off_tilerow + pad16(4ull * (s.n_tile + 1));
-    s.off_pool = s.off_edge + pad16((uint64_t)s.edge_size * s.nnz);
+    // row index derived from the octiles (pair-independent, so built once
+    // here instead of per pair on the device): per element (row | col << 16)
+    // in octile order, CSR over rows with (col | element << 16), and the
+    // first element of every tile row
+    s.off_emeta = s.off_edge + pad16((uint64_t)s.edge_size * s.nnz);
+    s.off_rowptr = s.off_emeta + pad16(4ull * s.nnz);
+    s.off_rowadj = s.off_rowptr + pad16(4ull * (g->n_node + 1));
+    s.off_tileelem = s.off_rowadj + pad16(4ull * s.nnz);
+    s.off_pool = s.off_tileelem + pad16(4ull * (s.n_tile + 1));
     s.total = s.off_pool + pad16(g->pool_bytes);
 }
 
@@ -114,7 +123,11 @@ extern "C" int gdb_graph_pack(const gdb_layout *L, const gdb_graph_src *g, void 
     h->off_edge = (uint32_t)s.off_edge;
     h->off_pool = (uint32_t)s.off_pool;
     h->blob_bytes = (uint32_t)s.total;
-    h->flags = L->weighted ? 1u : 0u;
+    h->flags = (L->weighted ? 1u : 0u) | (s.nnz < 65536u ? 2u : 0u);  // bit 1: 16-bit row index valid
+    h->off_emeta = (uint32_t)s.off_emeta;
+    h->off_rowptr = (uint32_t)s.off_rowptr;
+    h->off_rowadj = (uint32_t)s.off_rowadj;
+    h->off_tileelem = (uint32_t)s.off_tileelem;
 
     // degrees: sum of incident weights, self loops once, 0 -> 1
     std::vector<double> deg(g->n_node, 0.0);
@@ -160,6 +173,28 @@ extern "C" int gdb_graph_pack(const gdb_layout *L, const gdb_graph_src *g, void 
         for (uint32_t f = 0; f < L->n_edge_ptr; ++f) {
             uint64_t *slot = reinterpret_cast<uint64_t *>(e + s.label_off + L->edge_ptr_offset[f]);
             *slot += s.off_pool;
+        }
+    }
+    // row index
+    {
+        uint32_t *emeta = reinterpret_cast<uint32_t *>(base + s.off_emeta);
+        uint32_t *rowptr = reinterpret_cast<uint32_t *>(base + s.off_rowptr);
+        uint32_t *rowadj = reinterpret_cast<uint32_t *>(base + s.off_rowadj);
+        uint32_t *tileelem = reinterpret_cast<uint32_t *>(base + s.off_tileelem);
+        std::vector<uint32_t> fill(g->n_node + 1, 0);
+        for (uint32_t k = 0; k < s.nnz; ++k) {
+            emeta[k] = (nz[k].i & 0xffffu) | (nz[k].j << 16);
+            fill[nz[k].i + 1]++;
+        }
+        for (uint32_t i = 0; i < g->n_node; ++i) fill[i + 1] += fill[i];
+        for (uint32_t i = 0; i <= g->n_node; ++i) rowptr[i] = fill[i];
+        // nz is sorted by (tile row, tile col, row, col): filling in this order
+        // leaves every row's neighbours sorted by column
+        for (uint32_t k = 0; k < s.nnz; ++k) rowadj[fill[nz[k].i]++] = (nz[k].j & 0xffffu) | (k << 16);
+        uint32_t k = 0;
+        for (uint32_t t = 0; t <= s.n_tile; ++t) {
+            while (k < s.nnz && (nz[k].i >> 3) < t) ++k;
+            tileelem[t] = k;
         }
     }
     // CSR over tile rows

@@ -55,7 +55,7 @@ struct gdb_graph_hdr {
     int n_node, n_octile, nnz, n_tile;
     unsigned off_degree, off_node, off_octile, off_tilerow;
     unsigned off_edge, off_pool, blob_bytes, flags;
-    unsigned reserved[4];
+    unsigned off_emeta, off_rowptr, off_rowadj, off_tileelem;
 };
 
 struct gdb_octile {

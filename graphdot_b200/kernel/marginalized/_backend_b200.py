@@ -510,7 +510,9 @@ class B200Backend(Backend):
                          matvec_products=a.matvec_products,
                          vector_elements=a.vector_elements,
                          h2d_bytes=a.h2d_bytes, d2h_bytes=a.d2h_bytes,
-                         n_jobs=n_jobs, n_launches=a.n_launches)
+                         n_jobs=n_jobs, n_launches=a.n_launches,
+                         small_kernel=bool(a.used_small_kernel), grid=a.grid,
+                         smem_bytes=a.smem_bytes)
         return a
 
 

@@ -54,6 +54,7 @@ class ProgramDesc(C.Structure):
 
 class ProgramInfo(C.Structure):
     _fields_ = [('block_size', C.c_int32), ('num_regs', C.c_int32),
+                ('num_regs_small', C.c_int32),
                 ('static_smem', C.c_int32), ('local_bytes', C.c_int32),
                 ('max_dynamic_smem', C.c_int32), ('n_jac', C.c_int32),
                 ('from_cache', C.c_int32), ('compile_ms', C.c_float)]
@@ -94,7 +95,9 @@ class SolveArgs(C.Structure):
                 ('d2h_ms', C.c_float), ('cg_iterations', C.c_uint64),
                 ('matvec_products', C.c_uint64),
                 ('vector_elements', C.c_uint64), ('h2d_bytes', C.c_uint64),
-                ('d2h_bytes', C.c_uint64), ('n_launches', C.c_uint32)]
+                ('d2h_bytes', C.c_uint64), ('n_launches', C.c_uint32),
+                ('used_small_kernel', C.c_int32), ('grid', C.c_uint32),
+                ('smem_bytes', C.c_uint32)]
 
 
 # every symbol declared in include/graphdot_b200.h: (name, restype, argtypes)

@@ -100,7 +100,8 @@ typedef struct gdb_program_desc {
 
 typedef struct gdb_program_info {
     int32_t block_size;
-    int32_t num_regs;
+    int32_t num_regs;        /* general kernel (mlgk_solve)                */
+    int32_t num_regs_small;  /* shared-memory kernel (mlgk_solve_small)    */
     int32_t static_smem;
     int32_t local_bytes;     /* spill / stack per thread                   */
     int32_t max_dynamic_smem;
@@ -209,6 +210,8 @@ typedef struct gdb_solve_args {
     uint64_t vector_elements; /* total N = n1*n2 summed over CG iterations */
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t n_launches;
+    int32_t used_small_kernel; /* 1: mlgk_solve_small ran, 0: mlgk_solve    */
+    uint32_t grid, smem_bytes; /* launch configuration used                 */
 } gdb_solve_args;
 
 int gdb_solve(gdb_context_t ctx, gdb_program_t prog, gdb_graphset_t gs,
