@@ -222,7 +222,7 @@ struct gdb_program_s {
     std::string source, log;
     gdb_program_info info{};
     uint32_t theta_size[3] = {};
-    int eval_gradient = 0, nodal = 0;
+    int eval_gradient = 0, nodal = 0, wpt = 1;
     int refcount = 1;
 };
 
@@ -245,19 +245,24 @@ static int pick_block(const gdb_program_desc *d) {
     return b;
 }
 
+static int pick_wpt(const gdb_program_desc *d) { return d->workers_per_thread <= 0 ? 1 : d->workers_per_thread; }
+
 static int render(const gdb_program_desc *d, std::string &src) {
     if (!d || !d->node_decl || !d->edge_decl || !d->node_kernel.expr || !d->edge_kernel.expr || !d->p_start.expr)
         return gdb_fail(GDB_ERR_INVALID, "gdb_program_desc: missing source strings");
     const int block = pick_block(d);
     if (block < 0) return gdb_fail(GDB_ERR_INVALID, "block_size must be a multiple of 32 up to 1024");
     if (d->nodal < 0 || d->nodal > 2 || d->lmin < 0 || d->lmin > 1) return gdb_fail(GDB_ERR_INVALID, "invalid traits");
+    if (pick_wpt(d) > 4) return gdb_fail(GDB_ERR_INVALID, "workers_per_thread must be 1..4");
     if (d->eval_gradient && d->nodal != GDB_NODAL_NONE)
         return gdb_fail(GDB_ERR_INVALID, "nodal gradients are not implemented by this engine yet");
     std::ostringstream o;
     o << gdb_embedded_prelude << "\n";
     o << "// ---- generated splice ----\n";
     o << "#define GDB_BLOCK " << block << "\n";
-    o << "#define GDB_MIN_BLOCKS " << std::max(1, std::min(32, 2048 / block) / 2) << "\n";
+    o << "#define GDB_MIN_BLOCKS " << std::max(1, std::min(16, 640 / block)) << "\n";
+    o << "#define GDB_MIN_BLOCKS_SMALL " << std::max(1, 512 / block) << "\n";
+    o << "#define GDB_WPT " << pick_wpt(d) << "\n";
     o << "#define GDB_WEIGHTED " << (d->weighted ? 1 : 0) << "\n";
     o << "#define GDB_DIAGONAL " << (d->diagonal ? 1 : 0) << "\n";
     o << "#define GDB_SYMMETRIC " << (d->symmetric ? 1 : 0) << "\n";
@@ -366,6 +371,7 @@ extern "C" int gdb_program_create(gdb_context_t c, const gdb_program_desc *d, gd
     p->log = log;
     p->eval_gradient = d->eval_gradient;
     p->nodal = d->nodal;
+    p->wpt = pick_wpt(d);
     p->theta_size[0] = d->node_kernel.theta_size;
     p->theta_size[1] = d->edge_kernel.theta_size;
     p->theta_size[2] = d->p_start.theta_size;
@@ -610,10 +616,12 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     CUfunction fn = p->fn;
     {
         const uint64_t nrhs = p->eval_gradient ? 2 : 1;
-        const uint64_t wmax = ((uint64_t)gs->max_nnz[0] * gs->max_nnz[0] + 3) & ~3ull;
-        const uint64_t small_need = graphs_need + wmax * 4 + maxNpad * 4 + 4 * nrhs * maxNpad * 4;
+        const uint64_t wmax = ((uint64_t)gs->max_nnz[0] * (gs->max_nnz[0] + 1) + 3) & ~3ull;
+        const uint64_t small_need = graphs_need + wmax * 4 + nrhs * maxNpad * 4;
+        const uint64_t max_workers = (uint64_t)((gs->max_node[0] + 7) / 8) * gs->max_node[0];
         const uint64_t small_cap = std::min<uint64_t>(cap, (uint64_t)c->prop.sharedMemPerBlockOptin - p->small_static_smem);
-        if (gs->index16 && small_need <= small_cap && !getenv("GDB_FORCE_GENERAL")) {
+        if (gs->index16 && small_need <= small_cap && max_workers <= (uint64_t)block * p->wpt &&
+            !getenv("GDB_FORCE_GENERAL")) {
             fn = p->fn_small;
             smem = small_need;
             spill = false;

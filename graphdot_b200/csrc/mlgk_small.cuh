@@ -1,30 +1,43 @@
-// mlgk_small.cuh -- shared-memory-resident solver for small graph pairs
-// (everything of a pair fits in one CTA's shared memory: both graph blobs, the
-// cached edge-kernel products, and the CG vectors).  This is the kernel behind
-// the BASELINE configurations C1, C2, C3 and C5 (molecular graphs of ~20
-// nodes).  Same algorithm and same results contract as mlgk_solve
+// mlgk_small.cuh -- shared-memory / register-resident solver for small graph
+// pairs: both graph blobs, the cached edge-kernel products W and one vector fit
+// in a CTA's shared memory and the CG state fits in registers.  This is the
+// kernel behind the BASELINE configurations C1, C2, C3 and C5 (molecular
+// graphs of ~20 nodes).  Same algorithm and results contract as mlgk_solve
 // (mlgk_solver.cuh); it replaces reference
 // graphdot/cpp/marginalized_kernel.h:189-490 (compute), :492-804
 // (compute_duo) and :806-997 (derivative) for pairs in this regime.
 //
-// What is different from the general kernel, and why:
+// Design:
 //  * W = w1 w2 kE(e1, e2) is evaluated ONCE per pair for all nnz1 x nnz2
-//    element pairs (perfectly balanced, no divergence) and kept in shared
-//    memory; every CG iteration of both solves then costs one shared load per
-//    product instead of re-evaluating the edge microkernel (the reference
-//    re-evaluates it for every product in every iteration,
-//    marginalized_kernel.h:299-300, :346).
-//  * the matvec is organised by "workers" = (tile row T1 of G1) x (column i2
-//    of G2).  A worker walks the compact elements of the octiles in tile row
-//    T1 (one contiguous range, uniform across the lanes that share T1) and,
-//    per element, the neighbours of i2 from the row index of G2; it owns the
-//    outputs (rows of T1, column i2), so there are no atomics and no races.
-//  * with gradients, the value system (rhs Dx) and the adjoint system (rhs
-//    p1 (x) p2) are solved TOGETHER on float2 vectors: one W load and one
-//    64-bit vector load feed two FMAs.  Each system keeps its own CG scalars
-//    and convergence flag (the reference shares alpha/beta between the two
-//    stacked systems, marginalized_kernel.h:721-772).
+//    element pairs (balanced, divergence-free) into shared memory, with one
+//    extra zero column so that padded adjacency slots need no predicate.  The
+//    reference re-evaluates the edge microkernel for every product in every CG
+//    iteration (marginalized_kernel.h:299-300, :346).
+//  * workers = (tile row T1 of G1: 8 rows) x (column i2 of G2), one or a few
+//    per thread.  A worker owns the 8 product-graph elements (rows of T1,
+//    column i2): their x, r, A p and diagonal live in REGISTERS for the whole
+//    solve; only the search direction p, which neighbours gather, is in shared
+//    memory.  The first GDB_ADJ neighbours of column i2 are held in registers
+//    as byte offsets, so one matvec product is
+//        LDS W[row + off_k], LDS p[row' + off'_k], FMA (x2 with gradients).
+//    No atomics, fixed summation order => bit-reproducible.
+//  * with gradients the value system (rhs Dx) and the adjoint system (rhs
+//    p1 (x) p2) are solved together on float2 data: one W load and one 64-bit
+//    load feed two FMAs.  Each system has its own CG scalars and convergence
+//    flag (the reference shares alpha/beta between the stacked systems,
+//    marginalized_kernel.h:721-772).
+//  * three barriers per CG iteration (two reductions + publish p); the dot
+//    products are warp-shuffle trees joined through a double-buffered
+//    shared-memory slot.
+//
+// Extra macro from the generated header: GDB_WPT (workers per thread, so that
+// GDB_BLOCK * GDB_WPT >= max tile rows * max nodes of the graph set).
 #pragma once
+
+#ifndef GDB_WPT
+#define GDB_WPT 1
+#endif
+#define GDB_ADJ 4  // neighbours of a column kept in registers
 
 #if GDB_GRADIENT
 typedef float2 gv_t;
@@ -32,7 +45,6 @@ typedef float2 gv_t;
 __device__ __forceinline__ gv_t gv_make(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ gv_t gv_fma(float a, gv_t b, gv_t c) { return make_float2(fmaf(a, b.x, c.x), fmaf(a, b.y, c.y)); }
 __device__ __forceinline__ gv_t gv_fma2(gv_t a, gv_t b, gv_t c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
-__device__ __forceinline__ gv_t gv_sub(gv_t a, gv_t b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ gv_t gv_scale(float a, gv_t b) { return make_float2(a * b.x, a * b.y); }
 __device__ __forceinline__ gv_t gv_neg(gv_t a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ float gv_get(gv_t a, int k) { return k ? a.y : a.x; }
@@ -42,13 +54,12 @@ typedef float gv_t;
 __device__ __forceinline__ gv_t gv_make(float a, float) { return a; }
 __device__ __forceinline__ gv_t gv_fma(float a, gv_t b, gv_t c) { return fmaf(a, b, c); }
 __device__ __forceinline__ gv_t gv_fma2(gv_t a, gv_t b, gv_t c) { return fmaf(a, b, c); }
-__device__ __forceinline__ gv_t gv_sub(gv_t a, gv_t b) { return a - b; }
 __device__ __forceinline__ gv_t gv_scale(float a, gv_t b) { return a * b; }
 __device__ __forceinline__ gv_t gv_neg(gv_t a) { return -a; }
 __device__ __forceinline__ float gv_get(gv_t a, int) { return a; }
 #endif
 
-// Group sum of K values at once (one barrier); fixed summation order.
+// Group sum of K <= 4 values at once (one barrier); fixed summation order.
 template<int K> __device__ __forceinline__ void gdb_group_sum_n(float (&v)[K], float *red, int &flip) {
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = gdb_warp_sum(v[k]);
@@ -68,15 +79,28 @@ template<int K> __device__ __forceinline__ void gdb_group_sum_n(float (&v)[K], f
         v[k] = t;
     }
 #else
-    __syncwarp();  // orders the lanes' shared-memory writes like the barrier above
+    __syncwarp();  // orders the lanes' shared-memory accesses like the barrier above
 #endif
+}
+
+// q = a / d, r = a % d for a < 2^24 through one float multiply (+ fix-up)
+__device__ __forceinline__ void gdb_divmod(unsigned a, unsigned d, float inv_d, unsigned &q, unsigned &r) {
+    q = (unsigned)(__uint2float_rz(a) * inv_d);
+    r = a - q * d;
+    if ((int)r < 0) {
+        --q;
+        r += d;
+    } else if (r >= d) {
+        ++q;
+        r -= d;
+    }
 }
 
 struct gdb_small_graph {
     const float *degree;
     const node_t *node;
     const edge_t *edge;
-    const unsigned *emeta, *rowptr, *rowadj, *tileelem;
+    const unsigned *emeta, *rowptr, *rowadj;
     int n, nnz, n_tile;
 };
 
@@ -89,29 +113,32 @@ __device__ __forceinline__ gdb_small_graph gdb_small_view(const unsigned char *b
     v.emeta = reinterpret_cast<const unsigned *>(base + h->off_emeta);
     v.rowptr = reinterpret_cast<const unsigned *>(base + h->off_rowptr);
     v.rowadj = reinterpret_cast<const unsigned *>(base + h->off_rowadj);
-    v.tileelem = reinterpret_cast<const unsigned *>(base + h->off_tileelem);
     v.n = h->n_node;
     v.nnz = h->nnz;
     v.n_tile = h->n_tile;
     return v;
 }
 
-extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
+extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
     mlgk_solve_small(const __grid_constant__ gdb_params P) {
     extern __shared__ __align__(16) unsigned char gdb_smem[];
-    __shared__ unsigned long long s_job;
+    __shared__ unsigned s_job[2];
     __shared__ float s_red[2 * 4 * (GDB_WARPS > 0 ? GDB_WARPS : 1)];
     int flip = 0;
     const gdb_params_fixed &F = P.f;
 
     while (true) {
         gdb_group_sync();  // previous job's shared memory is dead
-        if (threadIdx.x == 0) s_job = atomicAdd(F.counters, 1ull);
+        if (threadIdx.x == 0) {
+            const unsigned long long job = atomicAdd(F.counters, 1ull);
+            unsigned a = 0xffffffffu, b = 0;
+            if (job < F.n_jobs) gdb_decode_job(F, job, a, b);
+            s_job[0] = a;
+            s_job[1] = b;
+        }
         gdb_group_sync();
-        const unsigned long long job = s_job;
-        if (job >= F.n_jobs) break;
-        unsigned ja, jb;
-        gdb_decode_job(F, job, ja, jb);
+        const unsigned ja = s_job[0], jb = s_job[1];
+        if (ja == 0xffffffffu) break;
         const gdb_graph_ref ref1 = F.graphs[ja], ref2 = F.graphs[jb];
         const bool same = (ja == jb);
 
@@ -127,44 +154,84 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
         gdb_group_sync();
         const gdb_small_graph g1 = gdb_small_view(gdb_smem), g2 = gdb_small_view(base2);
         const int n1 = g1.n, n2 = g2.n, N = n1 * n2, nnz1 = g1.nnz, nnz2 = g2.nnz;
-        const int Npad = (N + 3) & ~3;
+        const int wstride = nnz2 + 1;  // + one zero column for padded adjacency slots
         float *W = reinterpret_cast<float *>(gdb_smem + used);
-        float *diag = W + ((nnz1 * nnz2 + 3) & ~3);
-        gv_t *x = reinterpret_cast<gv_t *>(diag + Npad);
-        gv_t *r = x + Npad, *p = r + Npad, *Ap = p + Npad;
+        gv_t *pbuf = reinterpret_cast<gv_t *>(W + ((nnz1 * wstride + 3) & ~3));
 
         // ---- W = w1 w2 kE(e1, e2), once per pair ---------------------------------
-        for (int idx = threadIdx.x; idx < nnz1 * nnz2; idx += GDB_BLOCK) {
-            const int e1 = idx / nnz2, e2 = idx - e1 * nnz2;
-            W[idx] = gdb_edge_value(P, g1.edge[e1], g2.edge[e2]);
+        {
+            const float inv = __frcp_rn((float)nnz2);
+            for (unsigned idx = threadIdx.x; idx < (unsigned)(nnz1 * nnz2); idx += GDB_BLOCK) {
+                unsigned e1, e2;
+                gdb_divmod(idx, (unsigned)nnz2, inv, e1, e2);
+                W[e1 * wstride + e2] = gdb_edge_value(P, g1.edge[e1], g2.edge[e2]);
+            }
+            for (int e1 = threadIdx.x; e1 < nnz1; e1 += GDB_BLOCK) W[e1 * wstride + nnz2] = 0.f;
         }
-        // ---- diagonal, right-hand sides, CG start ---------------------------------
+
+        // ---- per-worker setup: adjacency of column i2, diagonal, rhs, CG start ------
         const float Q = 1.0f / (1.0f - F.q), Q2 = Q * Q;
+        const int n_worker = g1.n_tile * n2;
+        int w_row0[GDB_WPT], w_col[GDB_WPT];            // first row (8 T1) and column; row0 >= n1: idle slot
+        unsigned w_woff[GDB_WPT][GDB_ADJ];              // byte offsets into a W row
+        unsigned w_xoff[GDB_WPT][GDB_ADJ];              // byte offsets into a p row
+        unsigned w_kext[GDB_WPT], w_kend[GDB_WPT];      // neighbours beyond GDB_ADJ (rare)
+        float diag[GDB_WPT][8];
+        gv_t xv[GDB_WPT][8], rv[GDB_WPT][8], apv[GDB_WPT][8];
         float rho[GV_N];
 #pragma unroll
         for (int k = 0; k < GV_N; ++k) rho[k] = 0.f;
-        for (int i = threadIdx.x; i < N; i += GDB_BLOCK) {
-            const int i1 = i / n2, i2 = i - i1 * n2;
-            const node_t &u1 = g1.node[i1];
-            const node_t &u2 = g2.node[i2];
-            const float dx = g1.degree[i1] * g2.degree[i2] * Q2;
-            const float v = P.node_kernel(u1, u2);
-            const float d = __fdividef(dx, v);
-            diag[i] = d;
-#if GDB_GRADIENT
-            const gv_t ri = gv_make(dx, P.p_start(u1) * P.p_start(u2));
-#else
-            const gv_t ri = gv_make(dx, 0.f);
-#endif
-            const gv_t z = gv_scale(__fdividef(1.0f, d), ri);
-            x[i] = gv_make(0.f, 0.f);
-            r[i] = ri;
-            p[i] = z;
+        {
+            const float inv = __frcp_rn((float)n2);
 #pragma unroll
-            for (int k = 0; k < GV_N; ++k) rho[k] = fmaf(gv_get(ri, k), gv_get(z, k), rho[k]);
+            for (int s = 0; s < GDB_WPT; ++s) {
+                const unsigned w = threadIdx.x + s * GDB_BLOCK;
+                unsigned T1 = 0, i2 = 0;
+                if (w < (unsigned)n_worker) gdb_divmod(w, (unsigned)n2, inv, T1, i2);
+                w_row0[s] = w < (unsigned)n_worker ? (int)(8 * T1) : n1;
+                w_col[s] = (int)i2;
+                const unsigned kbeg = g2.rowptr[i2], kend = g2.rowptr[i2 + 1];
+#pragma unroll
+                for (int k = 0; k < GDB_ADJ; ++k) {
+                    const unsigned a = (kbeg + k < kend) ? g2.rowadj[kbeg + k] : ((unsigned)nnz2 << 16);
+                    w_woff[s][k] = (a >> 16) * 4u;
+                    w_xoff[s][k] = (a & 0xffffu) * (unsigned)sizeof(gv_t);
+                }
+                w_kext[s] = kbeg + GDB_ADJ;
+                w_kend[s] = kend;
+                const node_t &u2 = g2.node[i2];
+                const float d2 = g2.degree[i2] * Q2;
+#if GDB_GRADIENT
+                const float p2 = P.p_start(u2);
+#endif
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int i1 = w_row0[s] + r;
+                    diag[s][r] = 1.f;
+                    xv[s][r] = gv_make(0.f, 0.f);
+                    rv[s][r] = gv_make(0.f, 0.f);
+                    apv[s][r] = gv_make(0.f, 0.f);
+                    if (i1 < n1) {
+                        const node_t &u1 = g1.node[i1];
+                        const float dx = g1.degree[i1] * d2;
+                        const float d = __fdividef(dx, P.node_kernel(u1, u2));
+                        diag[s][r] = d;
+#if GDB_GRADIENT
+                        const gv_t ri = gv_make(dx, P.p_start(u1) * p2);
+#else
+                        const gv_t ri = gv_make(dx, 0.f);
+#endif
+                        const gv_t z = gv_scale(__fdividef(1.0f, d), ri);
+                        rv[s][r] = ri;
+                        pbuf[i1 * n2 + (int)i2] = z;
+#pragma unroll
+                        for (int k = 0; k < GV_N; ++k) rho[k] = fmaf(gv_get(ri, k), gv_get(z, k), rho[k]);
+                    }
+                }
+            }
         }
         gdb_group_sum_n(rho, s_red, flip);
-        gdb_group_sync();  // W, p complete
+        gdb_group_sync();  // W and p complete
 
         // ---- Jacobi-PCG, both systems at once ---------------------------------------
         const float thresh = F.ftol * (float)N;
@@ -172,7 +239,9 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
 #pragma unroll
         for (int k = 0; k < GV_N; ++k) active[k] = rho[k] != 0.f;
         int iters = 0;  // summed over the systems that were still active
-        const int n_worker = g1.n_tile * n2;
+        const unsigned char *Wb = reinterpret_cast<const unsigned char *>(W);
+        const unsigned char *pb = reinterpret_cast<const unsigned char *>(pbuf);
+        const unsigned prow_bytes = (unsigned)n2 * (unsigned)sizeof(gv_t);
         for (int it = 0; it < N; ++it) {
             bool any = false;
 #pragma unroll
@@ -180,35 +249,43 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
             if (!any) break;
 #pragma unroll
             for (int k = 0; k < GV_N; ++k) iters += active[k] ? 1 : 0;
-            // matvec: Ap = diag p - W p
+
+            // matvec: A p = diag p - W p for the 8 elements of every worker
             float pAp[GV_N];
 #pragma unroll
             for (int k = 0; k < GV_N; ++k) pAp[k] = 0.f;
-            for (int w = threadIdx.x; w < n_worker; w += GDB_BLOCK) {
-                const int T1 = w / n2, i2 = w - T1 * n2;
-                const int row_end = min(8 * T1 + 8, n1);
-                for (int i1 = 8 * T1; i1 < row_end; ++i1) Ap[i1 * n2 + i2] = gv_scale(diag[i1 * n2 + i2], p[i1 * n2 + i2]);
-                const unsigned kbeg = g2.rowptr[i2], kend = g2.rowptr[i2 + 1];
-                const unsigned eend = g1.tileelem[T1 + 1];
-                for (unsigned e1 = g1.tileelem[T1]; e1 < eend; ++e1) {
-                    const unsigned m = g1.emeta[e1];
-                    const float *Wrow = W + e1 * nnz2;
-                    const gv_t *prow = p + (m >> 16) * n2;
-                    gv_t acc = gv_make(0.f, 0.f);
-                    for (unsigned k = kbeg; k < kend; ++k) {
-                        const unsigned a = g2.rowadj[k];
-                        acc = gv_fma(Wrow[a >> 16], prow[a & 0xffffu], acc);
-                    }
-                    gv_t *dst = Ap + (m & 0xffffu) * n2 + i2;
-                    *dst = gv_sub(*dst, acc);
-                }
-                for (int i1 = 8 * T1; i1 < row_end; ++i1) {
-                    const gv_t pv = p[i1 * n2 + i2], av = Ap[i1 * n2 + i2];
 #pragma unroll
-                    for (int k = 0; k < GV_N; ++k) pAp[k] = fmaf(gv_get(pv, k), gv_get(av, k), pAp[k]);
+            for (int s = 0; s < GDB_WPT; ++s) {
+                const int i2 = w_col[s];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int i1 = w_row0[s] + r;
+                    if (i1 < n1) {
+                        gv_t acc = gv_make(0.f, 0.f);
+                        const unsigned k1end = g1.rowptr[i1 + 1];
+                        for (unsigned k1 = g1.rowptr[i1]; k1 < k1end; ++k1) {
+                            const unsigned a1 = g1.rowadj[k1];
+                            const unsigned char *Wrow = Wb + (a1 >> 16) * (unsigned)(wstride * 4);
+                            const unsigned char *prow = pb + (a1 & 0xffffu) * prow_bytes;
+#pragma unroll
+                            for (int k = 0; k < GDB_ADJ; ++k)
+                                acc = gv_fma(*reinterpret_cast<const float *>(Wrow + w_woff[s][k]),
+                                             *reinterpret_cast<const gv_t *>(prow + w_xoff[s][k]), acc);
+                            for (unsigned k = w_kext[s]; k < w_kend[s]; ++k) {  // degree > GDB_ADJ
+                                const unsigned a2 = g2.rowadj[k];
+                                acc = gv_fma(*reinterpret_cast<const float *>(Wrow + (a2 >> 16) * 4u),
+                                             *reinterpret_cast<const gv_t *>(prow + (a2 & 0xffffu) * (unsigned)sizeof(gv_t)), acc);
+                            }
+                        }
+                        const gv_t pv = pbuf[i1 * n2 + i2];
+                        const gv_t av = gv_fma2(gv_make(diag[s][r], diag[s][r]), pv, gv_neg(acc));
+                        apv[s][r] = av;
+#pragma unroll
+                        for (int k = 0; k < GV_N; ++k) pAp[k] = fmaf(gv_get(pv, k), gv_get(av, k), pAp[k]);
+                    }
                 }
             }
-            gdb_group_sum_n(pAp, s_red, flip);  // barrier: Ap complete
+            gdb_group_sum_n(pAp, s_red, flip);  // barrier: every read of p is done
             float alpha[GV_N];
 #pragma unroll
             for (int k = 0; k < GV_N; ++k) {
@@ -216,34 +293,48 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
                 alpha[k] = active[k] ? __fdividef(rho[k], pAp[k]) : 0.f;
             }
             const gv_t al = gv_make(alpha[0], alpha[GV_N - 1]);
-            float s[2 * GV_N];
+            float sums[2 * GV_N];
 #pragma unroll
-            for (int k = 0; k < 2 * GV_N; ++k) s[k] = 0.f;
-            for (int i = threadIdx.x; i < N; i += GDB_BLOCK) {
-                x[i] = gv_fma2(al, p[i], x[i]);
-                const gv_t ri = gv_fma2(gv_neg(al), Ap[i], r[i]);
-                r[i] = ri;
-                const float dinv = __fdividef(1.0f, diag[i]);
+            for (int k = 0; k < 2 * GV_N; ++k) sums[k] = 0.f;
 #pragma unroll
-                for (int k = 0; k < GV_N; ++k) {
-                    const float rk = gv_get(ri, k);
-                    s[2 * k] = fmaf(rk, rk, s[2 * k]);
-                    s[2 * k + 1] = fmaf(rk * dinv, rk, s[2 * k + 1]);
+            for (int s = 0; s < GDB_WPT; ++s) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int i1 = w_row0[s] + r;
+                    if (i1 < n1) {
+                        xv[s][r] = gv_fma2(al, pbuf[i1 * n2 + w_col[s]], xv[s][r]);
+                        const gv_t ri = gv_fma2(gv_neg(al), apv[s][r], rv[s][r]);
+                        rv[s][r] = ri;
+                        const float dinv = __fdividef(1.0f, diag[s][r]);
+#pragma unroll
+                        for (int k = 0; k < GV_N; ++k) {
+                            const float rk = gv_get(ri, k);
+                            sums[2 * k] = fmaf(rk, rk, sums[2 * k]);
+                            sums[2 * k + 1] = fmaf(rk * dinv, rk, sums[2 * k + 1]);
+                        }
+                    }
                 }
             }
-            gdb_group_sum_n(s, s_red, flip);
+            gdb_group_sum_n(sums, s_red, flip);
             float beta[GV_N];
 #pragma unroll
             for (int k = 0; k < GV_N; ++k) {
-                if (active[k] && sqrtf(s[2 * k]) < thresh) active[k] = false;
-                beta[k] = active[k] ? __fdividef(s[2 * k + 1], rho[k]) : 0.f;
-                if (active[k]) rho[k] = s[2 * k + 1];
+                if (active[k] && sqrtf(sums[2 * k]) < thresh) active[k] = false;
+                beta[k] = active[k] ? __fdividef(sums[2 * k + 1], rho[k]) : 0.f;
+                if (active[k]) rho[k] = sums[2 * k + 1];
                 if (rho[k] == 0.f) active[k] = false;
             }
             const gv_t be = gv_make(beta[0], beta[GV_N - 1]);
-            for (int i = threadIdx.x; i < N; i += GDB_BLOCK) {
-                const gv_t z = gv_scale(__fdividef(1.0f, diag[i]), r[i]);
-                p[i] = gv_fma2(be, p[i], z);
+#pragma unroll
+            for (int s = 0; s < GDB_WPT; ++s) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int i1 = w_row0[s] + r;
+                    if (i1 < n1) {
+                        gv_t *pp = pbuf + i1 * n2 + w_col[s];
+                        *pp = gv_fma2(be, *pp, gv_scale(__fdividef(1.0f, diag[s][r]), rv[s][r]));
+                    }
+                }
             }
             gdb_group_sync();  // p complete before the next matvec
         }
@@ -257,12 +348,28 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
         const unsigned I1 = F.starts[ja] - F.row0, I2 = F.starts[jb] - F.col0;
         const unsigned long long plane = (unsigned long long)F.nX * F.nY;
         (void)plane;
+        (void)I2;
+
+#if GDB_NODAL != 0 || (GDB_GRADIENT && GDB_NE > 0)
+        // publish x (both systems) in shared memory: the nodal epilogues and the
+        // edge-Jacobian pass read elements owned by other threads
+        gv_t *xs = pbuf;
+#pragma unroll
+        for (int s = 0; s < GDB_WPT; ++s) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int i1 = w_row0[s] + r;
+                if (i1 < n1) xs[i1 * n2 + w_col[s]] = xv[s][r];
+            }
+        }
+        gdb_group_sync();
+#endif
 
         // ---- epilogue: starting probabilities, Gram entry ----------------------------
 #if GDB_NODAL == 2
         for (int i = threadIdx.x; i < N; i += GDB_BLOCK) {
             const int i1 = i / n2, i2 = i - i1 * n2;
-            float xi = 0.5f * (gv_get(x[i], 0) + gv_get(x[i2 * n2 + i1], 0));  // self pair: bit-exact symmetry
+            float xi = 0.5f * (gv_get(xs[i], 0) + gv_get(xs[i2 * n2 + i1], 0));  // self pair: bit-exact symmetry
 #if GDB_LMIN == 1
             xi -= P.node_kernel(g1.node[i1], g2.node[i2]);
 #endif
@@ -270,7 +377,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
         }
 #elif GDB_NODAL == 1 && GDB_DIAGONAL
         for (int i1 = threadIdx.x; i1 < n1; i1 += GDB_BLOCK) {
-            float xi = gv_get(x[i1 * n2 + i1], 0);
+            float xi = gv_get(xs[i1 * n2 + i1], 0);
 #if GDB_LMIN == 1
             xi -= P.node_kernel(g1.node[i1], g2.node[i1]);
 #endif
@@ -280,9 +387,9 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
 #elif GDB_NODAL == 1
         for (int i = threadIdx.x; i < N; i += GDB_BLOCK) {
             const int i1 = i / n2, i2 = i - i1 * n2;
-            float xi = gv_get(x[i], 0);
+            float xi = gv_get(xs[i], 0);
 #if GDB_SYMMETRIC
-            if (same) xi = 0.5f * (xi + gv_get(x[i2 * n2 + i1], 0));  // bit-exact symmetry of self pairs
+            if (same) xi = 0.5f * (xi + gv_get(xs[i2 * n2 + i1], 0));  // bit-exact symmetry of self pairs
 #endif
 #if GDB_LMIN == 1
             xi -= P.node_kernel(g1.node[i1], g2.node[i2]);
@@ -294,81 +401,94 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
 #endif
         }
 #else
-        // graph level: K = sum xs p1 p2; with gradients also the node-side Jacobian terms
+        // graph level: K = sum xs p1 p2; with gradients also the node-side Jacobian
+        // terms, all from the registers of the owning worker
         {
-            float acc[1 + (GDB_GRADIENT ? GDB_NP + 1 + GDB_NV : 0)];
+            constexpr int NACC = 1 + (GDB_GRADIENT ? GDB_NP + 1 + GDB_NV : 0);
+            float acc[NACC];
 #pragma unroll
-            for (int m = 0; m < (int)(sizeof(acc) / sizeof(float)); ++m) acc[m] = 0.f;
-            for (int i = threadIdx.x; i < N; i += GDB_BLOCK) {
-                const int i1 = i / n2, i2 = i - i1 * n2;
-                const node_t &u1 = g1.node[i1];
-                const node_t &u2 = g2.node[i2];
-                const float p1 = P.p_start(u1), p2 = P.p_start(u2);
-                const float xi = gv_get(x[i], 0);
-                float xs = xi;
+            for (int m = 0; m < NACC; ++m) acc[m] = 0.f;
+#pragma unroll
+            for (int s = 0; s < GDB_WPT; ++s) {
+                const node_t &u2 = g2.node[w_col[s]];
+                const float p2 = P.p_start(u2);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int i1 = w_row0[s] + r;
+                    if (i1 < n1) {
+                        const node_t &u1 = g1.node[i1];
+                        const float p1 = P.p_start(u1);
+                        const float xi = gv_get(xv[s][r], 0);
+                        float xsft = xi;
 #if GDB_LMIN == 1 || GDB_GRADIENT
-                const float v = P.node_kernel(u1, u2);
+                        const float v = P.node_kernel(u1, u2);
 #endif
 #if GDB_LMIN == 1
-                xs -= v;
+                        xsft -= v;
 #endif
-                acc[0] = fmaf(xs, p1 * p2, acc[0]);
+                        acc[0] = fmaf(xsft, p1 * p2, acc[0]);
 #if GDB_GRADIENT
-                // dK/dp_m  = sum (dp1 p2 + p1 dp2) xs
-                // dK/dq    = sum y (2Q Dx) (1 - x / Vx)
-                // dK/dtv_m = sum y x Dx / Vx^2 dVx  [- p1 p2 dVx if lmin]
-                const float yi = gv_get(x[i], 1);
-                const float dx = diag[i] * v;
+                        // dK/dp_m  = sum (dp1 p2 + p1 dp2) xs
+                        // dK/dq    = sum y (2Q Dx) (1 - x / Vx)
+                        // dK/dtv_m = sum y x Dx / Vx^2 dVx  [- p1 p2 dVx if lmin]
+                        const float yi = gv_get(xv[s][r], 1);
+                        const float dx = diag[s][r] * v;
 #if GDB_NP > 0
-                {
-                    float d1[GDB_NP], d2[GDB_NP];
-                    P.p_start.jacobian(u1, d1);
-                    P.p_start.jacobian(u2, d2);
+                        {
+                            float d1[GDB_NP], d2[GDB_NP];
+                            P.p_start.jacobian(u1, d1);
+                            P.p_start.jacobian(u2, d2);
 #pragma unroll
-                    for (int m = 0; m < GDB_NP; ++m) acc[1 + m] = fmaf(fmaf(d1[m], p2, p1 * d2[m]), xs, acc[1 + m]);
-                }
+                            for (int m = 0; m < GDB_NP; ++m)
+                                acc[1 + m] = fmaf(fmaf(d1[m], p2, p1 * d2[m]), xsft, acc[1 + m]);
+                        }
 #endif
-                acc[1 + GDB_NP] += 2.f * Q * dx * yi * (1.f - __fdividef(xi, v));
+                        acc[1 + GDB_NP] += 2.f * Q * dx * yi * (1.f - __fdividef(xi, v));
 #if GDB_NV > 0
-                {
-                    float dv[GDB_NV];
-                    P.node_kernel.jacobian(u1, u2, dv);
-                    const float c = yi * xi * __fdividef(dx, v * v);
+                        {
+                            float dv[GDB_NV];
+                            P.node_kernel.jacobian(u1, u2, dv);
+                            const float c = yi * xi * __fdividef(dx, v * v);
 #pragma unroll
-                    for (int m = 0; m < GDB_NV; ++m) {
-                        float t = c * dv[m];
+                            for (int m = 0; m < GDB_NV; ++m) {
+                                float t = c * dv[m];
 #if GDB_LMIN == 1
-                        t -= p1 * p2 * dv[m];
+                                t -= p1 * p2 * dv[m];
 #endif
-                        acc[2 + GDB_NP + m] += t;
+                                acc[2 + GDB_NP + m] += t;
+                            }
+                        }
+#endif
+#endif
                     }
                 }
-#endif
-#endif
             }
 #if GDB_GRADIENT && GDB_NE > 0
-            // dK/dte_m = sum_{i,j} y_i x_j w1 w2 dkE_m(e1, e2): one balanced pass
-            // over all element pairs
+            // dK/dte_m = sum_{i,j} y_i x_j w1 w2 dkE_m(e1, e2): one balanced pass over
+            // all element pairs
             float eacc[GDB_NE];
 #pragma unroll
             for (int m = 0; m < GDB_NE; ++m) eacc[m] = 0.f;
-            for (int idx = threadIdx.x; idx < nnz1 * nnz2; idx += GDB_BLOCK) {
-                const int e1 = idx / nnz2, e2 = idx - e1 * nnz2;
-                const unsigned m1 = g1.emeta[e1], m2 = g2.emeta[e2];
-                const float yi = gv_get(x[(m1 & 0xffffu) * n2 + (m2 & 0xffffu)], 1);
-                float xj = gv_get(x[(m1 >> 16) * n2 + (m2 >> 16)], 0);
-                const edge_t &a = g1.edge[e1];
-                const edge_t &b = g2.edge[e2];
+            {
+                const float inv = __frcp_rn((float)nnz2);
+                for (unsigned idx = threadIdx.x; idx < (unsigned)(nnz1 * nnz2); idx += GDB_BLOCK) {
+                    unsigned e1, e2;
+                    gdb_divmod(idx, (unsigned)nnz2, inv, e1, e2);
+                    const unsigned m1 = g1.emeta[e1], m2 = g2.emeta[e2];
+                    const float yi = gv_get(xs[(m1 & 0xffffu) * n2 + (m2 & 0xffffu)], 1);
+                    float xj = gv_get(xs[(m1 >> 16) * n2 + (m2 >> 16)], 0);
+                    const edge_t &a = g1.edge[e1];
+                    const edge_t &b = g2.edge[e2];
 #if GDB_WEIGHTED
-                xj *= a.weight * b.weight;
+                    xj *= a.weight * b.weight;
 #endif
-                float de[GDB_NE];
-                P.edge_kernel.jacobian(a.label, b.label, de);
+                    float de[GDB_NE];
+                    P.edge_kernel.jacobian(a.label, b.label, de);
 #pragma unroll
-                for (int m = 0; m < GDB_NE; ++m) eacc[m] = fmaf(de[m] * yi, xj, eacc[m]);
+                    for (int m = 0; m < GDB_NE; ++m) eacc[m] = fmaf(de[m] * yi, xj, eacc[m]);
+                }
             }
 #endif
-            constexpr int NACC = (int)(sizeof(acc) / sizeof(float));
 #pragma unroll
             for (int m0 = 0; m0 < NACC; m0 += 4) {
                 float part[4];

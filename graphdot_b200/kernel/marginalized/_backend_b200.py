@@ -388,18 +388,25 @@ class B200Backend(Backend):
         return gs
 
     # -- programs ----------------------------------------------------------
-    def _pick_block(self, sizes):
-        if self.block_size:
-            return int(self.block_size)
+    def _pick_block(self, sizes, eval_gradient=False):
+        """(threads per pair, workers per thread).  The small-pair kernel
+        needs block * workers >= (tile rows) * (nodes) of the largest graph;
+        larger sets run the general kernel, sized by N = n^2."""
         n = int(np.max(sizes))
+        workers = -(-n // 8) * n
+        max_wpt = 1 if eval_gradient else 2
+        if self.block_size:
+            block = int(self.block_size)
+            wpt = min(max_wpt, max(1, -(-workers // block)))
+            return block, wpt
+        for block in (64, 96, 128, 160, 192, 224, 256):
+            if workers <= block:
+                return block, 1
+        for block in (128, 192, 256):
+            if workers <= block * max_wpt:
+                return block, max_wpt
         N = n * n
-        if N <= 1024:
-            return 32
-        if N <= 4096:
-            return 64
-        if N <= 16384:
-            return 128
-        return 256
+        return (128 if N <= 16384 else 256), 1
 
     @staticmethod
     def _desc(nl, el, weighted, node_kernel, edge_kernel, p, traits, block,
@@ -420,11 +427,13 @@ class B200Backend(Backend):
         d.nodal = native.NODAL_CODES[traits.nodal]
         d.lmin = int(traits.lmin)
         d.eval_gradient = int(traits.eval_gradient is True)
+        block, wpt = block if isinstance(block, tuple) else (block, 1)
         d.block_size = int(block)
+        d.workers_per_thread = int(wpt)
         d.extra_options = ' '.join(extra).encode() if extra else None
         keep = (fn, fe, fp)
         key = (nl.key, el.key, weighted, fn.key, fe.key, fp.key,
-               tuple(traits), block, tuple(extra))
+               tuple(traits), block, wpt, tuple(extra))
         return d, keep, key
 
     def program(self, gs, node_kernel, edge_kernel, p, traits):
@@ -434,7 +443,7 @@ class B200Backend(Backend):
             raise NotImplementedError(
                 'nodal gradients are not implemented by the B200 engine yet')
         nl, el, weighted = gs.layouts
-        block = self._pick_block(gs.sizes)
+        block = self._pick_block(gs.sizes, traits.eval_gradient is True)
         d, keep, key = self._desc(nl, el, weighted, node_kernel, edge_kernel,
                                   p, traits, block, self.nvrtc_extra)
         prog = self._programs.get(key)
@@ -536,14 +545,16 @@ def preset_sources():
             TensorProduct(length=SquareExponential(0.2)))
     presets = {
         'c1_unlabeled': ('C1', (Constant(1.0), Constant(1.0)),
-                         T(symmetric=True), 32),
-        'c2_molecular': ('C2', mol, T(symmetric=True), 32),
-        'c2_molecular_diag': ('C2', mol, T(diagonal=True), 32),
+                         T(symmetric=True), (64, 1)),
+        'c2_molecular': ('C2', mol, T(symmetric=True), (96, 1)),
+        'c2_molecular_diag': ('C2', mol, T(diagonal=True), (96, 1)),
         'c3_molecular_grad': ('C2', mol, T(symmetric=True,
-                                           eval_gradient=True), 32),
-        'c4_convolution': ('C4', conv, T(symmetric=True), 256),
-        'c5_offdiag': ('C2', mol, T(), 32),
-        'c2_nodal': ('C2', mol, T(symmetric=True, nodal=True), 32),
+                                           eval_gradient=True), (96, 1)),
+        'c3_tile_grad': ('C2', mol, T(eval_gradient=True), (96, 1)),
+        'c4_convolution': ('C4', conv, T(symmetric=True), (256, 1)),
+        'c5_offdiag': ('C2', mol, T(), (96, 1)),
+        'c2_nodal': ('C2', mol, T(symmetric=True, nodal=True), (96, 1)),
+        'c2_wpt2': ('C2', mol, T(symmetric=True), (128, 2)),
     }
     out = {}
     for name, (cfg, (kn, ke), traits, block) in presets.items():

@@ -49,6 +49,7 @@ class ProgramDesc(C.Structure):
                 ('diagonal', C.c_int32), ('symmetric', C.c_int32),
                 ('nodal', C.c_int32), ('lmin', C.c_int32),
                 ('eval_gradient', C.c_int32), ('block_size', C.c_int32),
+                ('workers_per_thread', C.c_int32),
                 ('extra_options', C.c_char_p)]
 
 

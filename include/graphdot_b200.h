@@ -95,6 +95,10 @@ typedef struct gdb_program_desc {
     /* traits (reference _kernel.py:48-58) -- compile-time specialisation  */
     int32_t diagonal, symmetric, nodal, lmin, eval_gradient;
     int32_t block_size;      /* threads cooperating on one pair; 0 = auto  */
+    int32_t workers_per_thread; /* small-pair kernel: (tile row, column)
+                                workers per thread, 1..4; 0 = 1.  The kernel
+                                is used when block_size * workers_per_thread
+                                covers max tile rows * max nodes            */
     const char *extra_options; /* extra NVRTC options, space separated     */
 } gdb_program_desc;
 
