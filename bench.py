@@ -252,6 +252,7 @@ def run_gpu(args, rank, world, local_rank):
     worker = GramTileWorker(kernel, G, backend, eval_gradient=True,
                             max_rows=args.tile_rows,
                             stream=stream.cuda_stream)
+    worker.diag(store=True)     # self-similarities for the fused normalization
     tiles = row_tiles(n, args.tile_rows)
     total_pairs = n * (n + 1) // 2
     assert sum(tile_pairs(a, b, n) for a, b in tiles) == total_pairs
@@ -276,15 +277,16 @@ def run_gpu(args, rank, world, local_rank):
 
     def step_device():
         for i0, i1 in tile_queue():
-            worker.run_tile(i0, i1, keep_on_device=True)
+            worker.run_tile(i0, i1, keep_on_device=True, normalize=True)
 
     def step_e2e():
-        d, dd = worker.diag(upload=True)           # H2D of the packed graphs
+        # H2D of the packed graphs; self-similarities stay on the device
+        worker.diag(upload=True, store=True)
         checksum = 0.0
         for i0, i1 in tile_queue():
-            K, dK = worker.run_tile(i0, i1)        # D2H of the tile
-            Kn, dKn = worker.normalize_tile(K, dK, i0, d, dd)
-            checksum += float(Kn[0, i0])
+            # normalized in the solver epilogue; D2H of the tile
+            Kn, dKn = worker.run_tile(i0, i1, normalize=True)
+            checksum += float(Kn[0, i0]) + float(dKn[0, i0, 1])
         return checksum
 
     # ---- device-resident throughput -----------------------------------------
@@ -374,8 +376,8 @@ def run_gpu(args, rank, world, local_rank):
                 'h2d_bytes_per_step': int(h2d / e2e_steps),
                 'd2h_bytes_per_step': int(d2h / e2e_steps),
                 'steps': e2e_steps,
-                'note': 'tile worker with host buffers: graphs H2D, '
-                        'Gram+Jacobian tiles D2H, host normalization'},
+                'note': 'tile worker with host buffers: graphs H2D, diagonal '
+                        'solve, normalized Gram+Jacobian tiles D2H'},
         'gpu_launches': int(launches),
         'roofline': {
             'bound': 'fp32', 'achieved': achieved, 'peak': peak_tflops,
@@ -386,8 +388,11 @@ def run_gpu(args, rank, world, local_rank):
             'matvec_tflops': fl['matvec'] / world / kernel_s / 1e12,
             'kernel_ms_per_step': kernel_ms / args.steps / world,
             'cg_iterations_per_pair': cg_it / args.steps / total_pairs,
-            'kernel': f'mlgk_solve block={pinfo.block_size} '
-                      f'regs={pinfo.num_regs}',
+            'kernel': (f'mlgk_solve_small block={pinfo.block_size} '
+                       f'regs={pinfo.num_regs_small}'
+                       if backend.last.get('small_kernel') else
+                       f'mlgk_solve block={pinfo.block_size} '
+                       f'regs={pinfo.num_regs}'),
         },
         'clocks': clocks,
     }

@@ -96,7 +96,9 @@ struct gdb_context_s {
     CUresult (*cuOccupancyMaxActiveBlocksPerMultiprocessor)(int *, CUfunction, int, size_t) = nullptr;
     CUresult (*cuGetErrorString)(CUresult, const char **) = nullptr;
     // persistent device buffers, grown on demand
-    DevBuf jobs, starts, gram, grad, scratch, counters;
+    DevBuf jobs, starts, gram, grad, scratch, counters, norm_diag, norm_ddiag;
+    uint32_t norm_n = 0, norm_nj = 0;
+    gdb_graphset_t norm_gs = nullptr;  // graph set the stored self-similarities belong to
     std::mutex mu;
     std::map<std::string, gdb_program_t> programs;  // source text -> program
 };
@@ -189,7 +191,7 @@ extern "C" int gdb_context_destroy(gdb_context_t c) {
         kv.second = nullptr;
         (void)p;  // programs are owned by their handles; the cache only aliases them
     }
-    for (DevBuf *b : {&c->jobs, &c->starts, &c->gram, &c->grad, &c->scratch, &c->counters})
+    for (DevBuf *b : {&c->jobs, &c->starts, &c->gram, &c->grad, &c->scratch, &c->counters, &c->norm_diag, &c->norm_ddiag})
         if (b->ptr) cudaFree(b->ptr);
     for (auto &e : c->ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -444,6 +446,7 @@ struct gdb_graphset_s {
     uint32_t max_blob[2] = {0, 0};  // two largest blobs
     uint32_t max_node[2] = {0, 0};  // two largest node counts
     uint32_t max_nnz[2] = {0, 0};   // two largest element counts
+    uint32_t max_ell = 0;           // largest n_node * pad4(max_degree): floats per W row
     bool index16 = true;            // every graph carries a valid 16-bit row index
 };
 
@@ -511,6 +514,7 @@ extern "C" int gdb_graphset_create(gdb_context_t c, const gdb_layout *L, uint32_
         top2(gs->max_blob, (uint32_t)blob_bytes[k]);
         top2(gs->max_node, (uint32_t)h->n_node);
         top2(gs->max_nnz, (uint32_t)h->nnz);
+        gs->max_ell = std::max<uint32_t>(gs->max_ell, (uint32_t)h->n_node * ((h->max_degree + 3u) & ~3u));
         if (!(h->flags & 2u)) gs->index16 = false;
         off += blob_bytes[k];
     }
@@ -539,6 +543,7 @@ extern "C" int gdb_graphset_bytes(gdb_graphset_t gs, uint64_t *bytes) {
 
 extern "C" int gdb_graphset_destroy(gdb_graphset_t gs) {
     if (!gs) return GDB_OK;
+    if (gs->ctx && gs->ctx->norm_gs == gs) gs->ctx->norm_gs = nullptr;
     cudaSetDevice(gs->ctx->device);
     if (gs->dev) cudaFree(gs->dev);
     if (gs->host) cudaFreeHost(gs->host);
@@ -578,6 +583,13 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     a->h2d_bytes = a->d2h_bytes = 0;
     a->n_launches = 0;
     if (n_jobs == 0) return GDB_OK;
+    if (a->store_diag && (a->nX != gs->n || a->nY != 1 || n_jobs != gs->n))
+        return gdb_fail(GDB_ERR_INVALID, "store_diag needs one (i, i) job per graph and nX = number of graphs");
+    if (a->normalize) {
+        if (p->nodal) return gdb_fail(GDB_ERR_INVALID, "fused normalization is defined for graph-level outputs only");
+        if (c->norm_gs != gs || c->norm_n != gs->n) return gdb_fail(GDB_ERR_INVALID, "normalize: no self-similarities stored for this graph set");
+        if (p->eval_gradient && c->norm_nj != a->nJ) return gdb_fail(GDB_ERR_INVALID, "normalize: stored self-similarities carry no matching Jacobian");
+    }
 
     RT(cudaSetDevice(c->device));
     cudaStream_t st = a->stream ? static_cast<cudaStream_t>(a->stream) : c->stream;
@@ -616,12 +628,13 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     CUfunction fn = p->fn;
     {
         const uint64_t nrhs = p->eval_gradient ? 2 : 1;
-        const uint64_t wmax = ((uint64_t)gs->max_nnz[0] * (gs->max_nnz[0] + 1) + 3) & ~3ull;
+        const uint64_t wmax = (uint64_t)gs->max_nnz[0] * gs->max_ell;  // W[k1][column slots]
         const uint64_t small_need = graphs_need + wmax * 4 + nrhs * maxNpad * 4;
-        const uint64_t max_workers = (uint64_t)((gs->max_node[0] + 7) / 8) * gs->max_node[0];
         const uint64_t small_cap = std::min<uint64_t>(cap, (uint64_t)c->prop.sharedMemPerBlockOptin - p->small_static_smem);
-        if (gs->index16 && small_need <= small_cap && max_workers <= (uint64_t)block * p->wpt &&
-            !getenv("GDB_FORCE_GENERAL")) {
+        // one warp per tile row of G1, lanes (x workers per thread) over the columns of G2
+        const bool mapped = (uint64_t)((gs->max_node[0] + 7) / 8) * 32 <= (uint64_t)block &&
+                            (uint64_t)gs->max_node[0] <= 32ull * p->wpt;
+        if (gs->index16 && small_need <= small_cap && mapped && wmax < (1u << 24) && !getenv("GDB_FORCE_GENERAL")) {
             fn = p->fn_small;
             smem = small_need;
             spill = false;
@@ -673,6 +686,11 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     f.q = a->q, f.eps = a->eps, f.ftol = a->ftol, f.gtol = a->gtol;
     f.smem_bytes = (uint32_t)smem;
     f.row0 = a->row0, f.col0 = a->col0;
+    if (a->normalize) {
+        f.norm_n = c->norm_n;
+        f.norm_diag = reinterpret_cast<uint64_t>(c->norm_diag.ptr);
+        f.norm_ddiag = reinterpret_cast<uint64_t>(c->norm_ddiag.ptr);
+    }
     memcpy(params.data(), &f, sizeof f);
     const void *thetas[3] = {a->node_theta, a->edge_theta, a->p_theta};
     for (int k = 0; k < 3; ++k) {
@@ -689,6 +707,18 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     a->grid = (uint32_t)grid;
     a->smem_bytes = (uint32_t)smem;
     RT(cudaEventRecord(c->ev[2], st));
+    if (a->store_diag) {
+        if ((rc = dev_reserve(c->norm_diag, plane * 4))) return rc;
+        RT(cudaMemcpyAsync(c->norm_diag.ptr, c->gram.ptr, plane * 4, cudaMemcpyDeviceToDevice, st));
+        c->norm_nj = 0;
+        if (grad_floats) {
+            if ((rc = dev_reserve(c->norm_ddiag, grad_floats * 4))) return rc;
+            RT(cudaMemcpyAsync(c->norm_ddiag.ptr, c->grad.ptr, grad_floats * 4, cudaMemcpyDeviceToDevice, st));
+            c->norm_nj = a->nJ;
+        }
+        c->norm_n = gs->n;
+        c->norm_gs = gs;
+    }
     unsigned long long counters[4] = {0, 0, 0, 0};
     RT(cudaMemcpyAsync(counters, c->counters.ptr, sizeof counters, cudaMemcpyDeviceToHost, st));
     if (!a->keep_on_device) {

@@ -4,7 +4,7 @@
 
 #include "../../include/graphdot_b200.h"
 
-#define GDB_HDR_BYTES 64
+#define GDB_HDR_BYTES 80
 
 // Host mirrors of the device structs in mlgk_solver.cuh.
 struct gdb_graph_hdr_host {
@@ -12,6 +12,7 @@ struct gdb_graph_hdr_host {
     uint32_t off_degree, off_node, off_octile, off_tilerow;
     uint32_t off_edge, off_pool, blob_bytes, flags;
     uint32_t off_emeta, off_rowptr, off_rowadj, off_tileelem;
+    uint32_t max_degree, reserved[3];  // largest number of stored elements in a row
 };
 static_assert(sizeof(gdb_graph_hdr_host) == GDB_HDR_BYTES, "header layout");
 
@@ -33,9 +34,10 @@ struct gdb_params_fixed_host {
     uint64_t scratch_stride, n_jobs;
     uint32_t job_mode, i0, i1, j0, j1, nX, nY, nJ;
     float q, eps, ftol, gtol;
-    uint32_t smem_bytes, row0, col0, pad2;
+    uint32_t smem_bytes, row0, col0, norm_n;
+    uint64_t norm_diag, norm_ddiag;
 };
-static_assert(sizeof(gdb_params_fixed_host) == 136, "params layout");
+static_assert(sizeof(gdb_params_fixed_host) == 152, "params layout");
 
 // Records `msg` as the calling thread's last error and returns `code`.
 int gdb_fail(int code, const char *fmt, ...);

@@ -186,6 +186,9 @@ extern "C" int gdb_graph_pack(const gdb_layout *L, const gdb_graph_src *g, void 
             emeta[k] = (nz[k].i & 0xffffu) | (nz[k].j << 16);
             fill[nz[k].i + 1]++;
         }
+        uint32_t max_degree = 0;
+        for (uint32_t i = 0; i < g->n_node; ++i) max_degree = std::max(max_degree, fill[i + 1]);
+        h->max_degree = max_degree;
         for (uint32_t i = 0; i < g->n_node; ++i) fill[i + 1] += fill[i];
         for (uint32_t i = 0; i <= g->n_node; ++i) rowptr[i] = fill[i];
         // nz is sorted by (tile row, tile col, row, col): filling in this order

@@ -154,50 +154,59 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         gdb_group_sync();
         const gdb_small_graph g1 = gdb_small_view(gdb_smem), g2 = gdb_small_view(base2);
         const int n1 = g1.n, n2 = g2.n, N = n1 * n2, nnz1 = g1.nnz, nnz2 = g2.nnz;
-        const int wstride = nnz2 + 1;  // + one zero column for padded adjacency slots
+        // W is indexed [k1][i2 * wd + k]: k1 = position of the G1 element in row
+        // (CSR) order, (i2, k) = k-th neighbour of column i2 of G2, padded with
+        // zeros to wd = 4 * ceil(max degree / 4) slots per column.  A worker's
+        // four slots are one aligned 128-bit load, and W rows are visited with a
+        // constant stride.
+        const gdb_graph_hdr *h2 = reinterpret_cast<const gdb_graph_hdr *>(base2);
+        const int wd = (int)((h2->max_degree + 3u) & ~3u);
+        const int wstride = n2 * wd;  // floats per W row (multiple of 4)
         float *W = reinterpret_cast<float *>(gdb_smem + used);
-        gv_t *pbuf = reinterpret_cast<gv_t *>(W + ((nnz1 * wstride + 3) & ~3));
+        gv_t *pbuf = reinterpret_cast<gv_t *>(W + nnz1 * wstride);
 
         // ---- W = w1 w2 kE(e1, e2), once per pair ---------------------------------
         {
-            const float inv = __frcp_rn((float)nnz2);
-            for (unsigned idx = threadIdx.x; idx < (unsigned)(nnz1 * nnz2); idx += GDB_BLOCK) {
-                unsigned e1, e2;
-                gdb_divmod(idx, (unsigned)nnz2, inv, e1, e2);
-                W[e1 * wstride + e2] = gdb_edge_value(P, g1.edge[e1], g2.edge[e2]);
+            const float inv_s = __frcp_rn((float)wstride), inv_d = __frcp_rn((float)wd);
+            for (unsigned idx = threadIdx.x; idx < (unsigned)(nnz1 * wstride); idx += GDB_BLOCK) {
+                unsigned k1, slot, i2, k;
+                gdb_divmod(idx, (unsigned)wstride, inv_s, k1, slot);
+                gdb_divmod(slot, (unsigned)wd, inv_d, i2, k);
+                const unsigned kbeg = g2.rowptr[i2];
+                float w = 0.f;
+                if (kbeg + k < g2.rowptr[i2 + 1])
+                    w = gdb_edge_value(P, g1.edge[g1.rowadj[k1] >> 16], g2.edge[g2.rowadj[kbeg + k] >> 16]);
+                W[idx] = w;
             }
-            for (int e1 = threadIdx.x; e1 < nnz1; e1 += GDB_BLOCK) W[e1 * wstride + nnz2] = 0.f;
         }
 
         // ---- per-worker setup: adjacency of column i2, diagonal, rhs, CG start ------
         const float Q = 1.0f / (1.0f - F.q), Q2 = Q * Q;
-        const int n_worker = g1.n_tile * n2;
-        int w_row0[GDB_WPT], w_col[GDB_WPT];            // first row (8 T1) and column; row0 >= n1: idle slot
-        unsigned w_woff[GDB_WPT][GDB_ADJ];              // byte offsets into a W row
-        unsigned w_xoff[GDB_WPT][GDB_ADJ];              // byte offsets into a p row
-        unsigned w_kext[GDB_WPT], w_kend[GDB_WPT];      // neighbours beyond GDB_ADJ (rare)
+        // worker mapping: warp = tile row T1 of G1, lane (+ 32 s) = column i2 of G2,
+        // so every loop over the elements of a row is warp-uniform
+        const int w_row0 = (int)(threadIdx.x >> 5) < g1.n_tile ? 8 * (int)(threadIdx.x >> 5) : n1;
+        int w_col[GDB_WPT];                             // column; >= n2: idle slot
+        unsigned w_woff[GDB_WPT];                       // byte offset of the column's slots in a W row
+        unsigned w_xoff[GDB_WPT][GDB_ADJ];              // byte offsets of the neighbours in a p row
+        unsigned w_kbeg[GDB_WPT], w_kend[GDB_WPT];      // row of the column in G2's row index
         float diag[GDB_WPT][8];
         gv_t xv[GDB_WPT][8], rv[GDB_WPT][8], apv[GDB_WPT][8];
         float rho[GV_N];
 #pragma unroll
         for (int k = 0; k < GV_N; ++k) rho[k] = 0.f;
         {
-            const float inv = __frcp_rn((float)n2);
 #pragma unroll
             for (int s = 0; s < GDB_WPT; ++s) {
-                const unsigned w = threadIdx.x + s * GDB_BLOCK;
-                unsigned T1 = 0, i2 = 0;
-                if (w < (unsigned)n_worker) gdb_divmod(w, (unsigned)n2, inv, T1, i2);
-                w_row0[s] = w < (unsigned)n_worker ? (int)(8 * T1) : n1;
-                w_col[s] = (int)i2;
+                const int col = (int)(threadIdx.x & 31) + 32 * s;
+                const bool live = col < n2 && w_row0 < n1;
+                const int i2 = live ? col : 0;
+                w_col[s] = live ? col : n2;
                 const unsigned kbeg = g2.rowptr[i2], kend = g2.rowptr[i2 + 1];
+                w_woff[s] = (unsigned)(i2 * wd) * 4u;
 #pragma unroll
-                for (int k = 0; k < GDB_ADJ; ++k) {
-                    const unsigned a = (kbeg + k < kend) ? g2.rowadj[kbeg + k] : ((unsigned)nnz2 << 16);
-                    w_woff[s][k] = (a >> 16) * 4u;
-                    w_xoff[s][k] = (a & 0xffffu) * (unsigned)sizeof(gv_t);
-                }
-                w_kext[s] = kbeg + GDB_ADJ;
+                for (int k = 0; k < GDB_ADJ; ++k)
+                    w_xoff[s][k] = (kbeg + k < kend) ? (g2.rowadj[kbeg + k] & 0xffffu) * (unsigned)sizeof(gv_t) : 0u;
+                w_kbeg[s] = kbeg;
                 w_kend[s] = kend;
                 const node_t &u2 = g2.node[i2];
                 const float d2 = g2.degree[i2] * Q2;
@@ -206,12 +215,12 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #endif
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    const int i1 = w_row0[s] + r;
+                    const int i1 = w_row0 + r;
                     diag[s][r] = 1.f;
                     xv[s][r] = gv_make(0.f, 0.f);
                     rv[s][r] = gv_make(0.f, 0.f);
                     apv[s][r] = gv_make(0.f, 0.f);
-                    if (i1 < n1) {
+                    if (live && i1 < n1) {
                         const node_t &u1 = g1.node[i1];
                         const float dx = g1.degree[i1] * d2;
                         const float d = __fdividef(dx, P.node_kernel(u1, u2));
@@ -255,33 +264,40 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll
             for (int k = 0; k < GV_N; ++k) pAp[k] = 0.f;
 #pragma unroll
-            for (int s = 0; s < GDB_WPT; ++s) {
-                const int i2 = w_col[s];
+            for (int r = 0; r < 8; ++r) {
+                const int i1 = w_row0 + r;
+                if (i1 < n1) {  // warp-uniform
+                    gv_t acc[GDB_WPT];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int i1 = w_row0[s] + r;
-                    if (i1 < n1) {
-                        gv_t acc = gv_make(0.f, 0.f);
-                        const unsigned k1end = g1.rowptr[i1 + 1];
-                        for (unsigned k1 = g1.rowptr[i1]; k1 < k1end; ++k1) {
-                            const unsigned a1 = g1.rowadj[k1];
-                            const unsigned char *Wrow = Wb + (a1 >> 16) * (unsigned)(wstride * 4);
-                            const unsigned char *prow = pb + (a1 & 0xffffu) * prow_bytes;
+                    for (int s = 0; s < GDB_WPT; ++s) acc[s] = gv_make(0.f, 0.f);
+                    const unsigned k1end = g1.rowptr[i1 + 1];
+                    for (unsigned k1 = g1.rowptr[i1]; k1 < k1end; ++k1) {  // warp-uniform trip count
+                        const unsigned char *Wrow = Wb + k1 * (unsigned)(wstride * 4);
+                        const unsigned char *prow = pb + (g1.rowadj[k1] & 0xffffu) * prow_bytes;
 #pragma unroll
-                            for (int k = 0; k < GDB_ADJ; ++k)
-                                acc = gv_fma(*reinterpret_cast<const float *>(Wrow + w_woff[s][k]),
-                                             *reinterpret_cast<const gv_t *>(prow + w_xoff[s][k]), acc);
-                            for (unsigned k = w_kext[s]; k < w_kend[s]; ++k) {  // degree > GDB_ADJ
-                                const unsigned a2 = g2.rowadj[k];
-                                acc = gv_fma(*reinterpret_cast<const float *>(Wrow + (a2 >> 16) * 4u),
-                                             *reinterpret_cast<const gv_t *>(prow + (a2 & 0xffffu) * (unsigned)sizeof(gv_t)), acc);
+                        for (int s = 0; s < GDB_WPT; ++s) {
+                            if (w_col[s] < n2) {
+                                const float4 w4 = *reinterpret_cast<const float4 *>(Wrow + w_woff[s]);
+                                acc[s] = gv_fma(w4.x, *reinterpret_cast<const gv_t *>(prow + w_xoff[s][0]), acc[s]);
+                                acc[s] = gv_fma(w4.y, *reinterpret_cast<const gv_t *>(prow + w_xoff[s][1]), acc[s]);
+                                acc[s] = gv_fma(w4.z, *reinterpret_cast<const gv_t *>(prow + w_xoff[s][2]), acc[s]);
+                                acc[s] = gv_fma(w4.w, *reinterpret_cast<const gv_t *>(prow + w_xoff[s][3]), acc[s]);
+                                for (unsigned k = w_kbeg[s] + GDB_ADJ; k < w_kend[s]; ++k) {  // degree > GDB_ADJ
+                                    const float w = *reinterpret_cast<const float *>(Wrow + w_woff[s] + (k - w_kbeg[s]) * 4u);
+                                    acc[s] = gv_fma(w, *reinterpret_cast<const gv_t *>(prow + (g2.rowadj[k] & 0xffffu) * (unsigned)sizeof(gv_t)), acc[s]);
+                                }
                             }
                         }
-                        const gv_t pv = pbuf[i1 * n2 + i2];
-                        const gv_t av = gv_fma2(gv_make(diag[s][r], diag[s][r]), pv, gv_neg(acc));
-                        apv[s][r] = av;
+                    }
 #pragma unroll
-                        for (int k = 0; k < GV_N; ++k) pAp[k] = fmaf(gv_get(pv, k), gv_get(av, k), pAp[k]);
+                    for (int s = 0; s < GDB_WPT; ++s) {
+                        if (w_col[s] < n2) {
+                            const gv_t pv = pbuf[i1 * n2 + w_col[s]];
+                            const gv_t av = gv_fma2(gv_make(diag[s][r], diag[s][r]), pv, gv_neg(acc[s]));
+                            apv[s][r] = av;
+#pragma unroll
+                            for (int k = 0; k < GV_N; ++k) pAp[k] = fmaf(gv_get(pv, k), gv_get(av, k), pAp[k]);
+                        }
                     }
                 }
             }
@@ -300,8 +316,8 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             for (int s = 0; s < GDB_WPT; ++s) {
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    const int i1 = w_row0[s] + r;
-                    if (i1 < n1) {
+                    const int i1 = w_row0 + r;
+                    if (i1 < n1 && w_col[s] < n2) {
                         xv[s][r] = gv_fma2(al, pbuf[i1 * n2 + w_col[s]], xv[s][r]);
                         const gv_t ri = gv_fma2(gv_neg(al), apv[s][r], rv[s][r]);
                         rv[s][r] = ri;
@@ -329,8 +345,8 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             for (int s = 0; s < GDB_WPT; ++s) {
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    const int i1 = w_row0[s] + r;
-                    if (i1 < n1) {
+                    const int i1 = w_row0 + r;
+                    if (i1 < n1 && w_col[s] < n2) {
                         gv_t *pp = pbuf + i1 * n2 + w_col[s];
                         *pp = gv_fma2(be, *pp, gv_scale(__fdividef(1.0f, diag[s][r]), rv[s][r]));
                     }
@@ -358,8 +374,8 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         for (int s = 0; s < GDB_WPT; ++s) {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const int i1 = w_row0[s] + r;
-                if (i1 < n1) xs[i1 * n2 + w_col[s]] = xv[s][r];
+                const int i1 = w_row0 + r;
+                if (i1 < n1 && w_col[s] < n2) xs[i1 * n2 + w_col[s]] = xv[s][r];
             }
         }
         gdb_group_sync();
@@ -410,12 +426,12 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             for (int m = 0; m < NACC; ++m) acc[m] = 0.f;
 #pragma unroll
             for (int s = 0; s < GDB_WPT; ++s) {
-                const node_t &u2 = g2.node[w_col[s]];
+                const node_t &u2 = g2.node[w_col[s] < n2 ? w_col[s] : 0];
                 const float p2 = P.p_start(u2);
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    const int i1 = w_row0[s] + r;
-                    if (i1 < n1) {
+                    const int i1 = w_row0 + r;
+                    if (i1 < n1 && w_col[s] < n2) {
                         const node_t &u1 = g1.node[i1];
                         const float p1 = P.p_start(u1);
                         const float xi = gv_get(xv[s][r], 0);
@@ -512,6 +528,10 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             }
 #endif
             if (threadIdx.x == 0) {
+#if !GDB_DIAGONAL
+                const float norm_rs = gdb_norm_scale(F, ja, jb);
+                acc[0] *= norm_rs;
+#endif
 #if GDB_DIAGONAL
                 F.gram[I1] = acc[0];
 #else
@@ -536,6 +556,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #if GDB_DIAGONAL
                     F.grad[(unsigned long long)I1 + (unsigned long long)m * F.nX] = val;
 #else
+                    val = gdb_norm_grad(F, ja, jb, m, norm_rs, acc[0], val);
                     F.grad[(unsigned long long)I1 + (unsigned long long)I2 * F.nX + m * plane] = val;
 #if GDB_SYMMETRIC
                     if (!same) F.grad[(unsigned long long)I2 + (unsigned long long)I1 * F.nX + m * plane] = val;

@@ -56,6 +56,7 @@ struct gdb_graph_hdr {
     unsigned off_degree, off_node, off_octile, off_tilerow;
     unsigned off_edge, off_pool, blob_bytes, flags;
     unsigned off_emeta, off_rowptr, off_rowadj, off_tileelem;
+    unsigned max_degree, reserved[3];
 };
 
 struct gdb_octile {
@@ -81,7 +82,11 @@ struct gdb_params_fixed {
     unsigned long long n_jobs;
     unsigned job_mode, i0, i1, j0, j1, nX, nY, nJ;
     float q, eps, ftol, gtol;
-    unsigned smem_bytes, row0, col0, pad2;
+    unsigned smem_bytes, row0, col0, norm_n;
+    // fused normalization K_ij / sqrt(K_ii K_jj) (reference kernel/fix.py:46-73):
+    // self-similarities and their Jacobians per graph, or null
+    const float *norm_diag;
+    const float *norm_ddiag;  // [m * norm_n + graph]
 };
 
 struct gdb_params {
@@ -125,6 +130,19 @@ __device__ __forceinline__ gdb_graph_view gdb_view(const unsigned char *base) {
     v.n_octile = h->n_octile;
     v.nnz = h->nnz;
     return v;
+}
+
+// Normalization of a graph-level Gram entry and of its Jacobian, applied in
+// the epilogue when the self-similarities are available on the device.
+__device__ __forceinline__ float gdb_norm_scale(const gdb_params_fixed &F, unsigned ja, unsigned jb) {
+    return F.norm_diag ? 1.0f / sqrtf(F.norm_diag[ja] * F.norm_diag[jb]) : 1.0f;
+}
+__device__ __forceinline__ float gdb_norm_grad(const gdb_params_fixed &F, unsigned ja, unsigned jb, int m, float rs,
+                                               float kn, float raw) {
+    if (!F.norm_diag) return raw;
+    const float la = __fdividef(F.norm_ddiag[(unsigned long long)m * F.norm_n + ja], F.norm_diag[ja]);
+    const float lb = __fdividef(F.norm_ddiag[(unsigned long long)m * F.norm_n + jb], F.norm_diag[jb]);
+    return fmaf(raw, rs, -0.5f * kn * (la + lb));
 }
 
 __device__ __forceinline__ float gdb_warp_sum(float v) {
@@ -370,6 +388,9 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
         const unsigned long long plane = (unsigned long long)F.nX * F.nY;
 
         // ---- epilogue: apply starting probabilities, write the Gram entry ----
+        float norm_rs = 1.f, norm_k = 0.f;
+        (void)norm_rs;
+        (void)norm_k;
 #if GDB_NODAL == 2
         for (int i = threadIdx.x; i < (int)N; i += GDB_BLOCK) {
             const int i1 = i / n2, i2 = i - i1 * n2;
@@ -417,6 +438,11 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
                 sum = fmaf(xi, P.p_start(g1.node[i1]) * P.p_start(g2.node[i2]), sum);
             }
             sum = gdb_group_sum(sum, s_red, flip);
+#if !GDB_DIAGONAL
+            norm_rs = gdb_norm_scale(F, ja, jb);
+            sum *= norm_rs;
+            norm_k = sum;
+#endif
             if (threadIdx.x == 0) {
 #if GDB_DIAGONAL
                 F.gram[I1] = sum;
@@ -518,7 +544,10 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
         }
 #pragma unroll
         for (int m = 0; m < GDB_NJ; ++m) {
-            const float s = gdb_group_sum(jac[m], s_red, flip);
+            float s = gdb_group_sum(jac[m], s_red, flip);
+#if !GDB_DIAGONAL
+            s = gdb_norm_grad(F, ja, jb, m, norm_rs, norm_k, s);
+#endif
             if (threadIdx.x == 0) {
 #if GDB_DIAGONAL
                 F.grad[(unsigned long long)I1 + (unsigned long long)m * F.nX] = s;

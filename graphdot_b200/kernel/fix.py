@@ -14,6 +14,14 @@ class Normalization:
         self.kernel = kernel
 
     def __call__(self, X, Y=None, eval_gradient=False, **options):
+        fused = getattr(self.kernel, 'normalized_gram', None)
+        if fused is not None and not options.get('nodal', False):
+            out = fused(X, Y, eval_gradient=eval_gradient, **options)
+            if out is not NotImplemented:
+                return out
+        return self._host_normalized(X, Y, eval_gradient, **options)
+
+    def _host_normalized(self, X, Y=None, eval_gradient=False, **options):
         if eval_gradient is True:
             R, dR = self.kernel(X, Y, eval_gradient=True, **options)
             if Y is None:

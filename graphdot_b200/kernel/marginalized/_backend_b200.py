@@ -256,6 +256,7 @@ class B200Backend(Backend):
     """
 
     pair_jobs = PairJobs     # front ends may hand over implicit job grids
+    fused_normalization = True   # store_diag= / normalize= are honoured
 
     @staticmethod
     def array(ndarray):
@@ -390,21 +391,16 @@ class B200Backend(Backend):
     # -- programs ----------------------------------------------------------
     def _pick_block(self, sizes, eval_gradient=False):
         """(threads per pair, workers per thread).  The small-pair kernel
-        needs block * workers >= (tile rows) * (nodes) of the largest graph;
-        larger sets run the general kernel, sized by N = n^2."""
+        needs block >= 32 * (tile rows) and 32 * workers >= nodes of the
+        largest graph; larger sets run the general kernel, sized by N = n^2."""
         n = int(np.max(sizes))
-        workers = -(-n // 8) * n
         max_wpt = 1 if eval_gradient else 2
         if self.block_size:
-            block = int(self.block_size)
-            wpt = min(max_wpt, max(1, -(-workers // block)))
-            return block, wpt
-        for block in (64, 96, 128, 160, 192, 224, 256):
-            if workers <= block:
-                return block, 1
-        for block in (128, 192, 256):
-            if workers <= block * max_wpt:
-                return block, max_wpt
+            return int(self.block_size), min(max_wpt, max(1, -(-n // 32)))
+        # small-pair kernel: one warp per 8-row tile of G1, lanes x workers per
+        # thread over the columns of G2
+        if n <= 32 * max_wpt and n <= 256:
+            return max(64, 32 * -(-n // 8)), -(-n // 32)
         N = n * n
         return (128 if N <= 16384 else 256), 1
 
@@ -462,7 +458,8 @@ class B200Backend(Backend):
     # -- the back-end call ---------------------------------------------------
     def __call__(self, graphs, node_kernel, edge_kernel, p, q, eps, ftol,
                  gtol, jobs, starts, gramian, gradient, nX, nY, nJ, traits,
-                 timer, stream=None, keep_on_device=False):
+                 timer, stream=None, keep_on_device=False, store_diag=False,
+                 normalize=False):
         lib = native.load()
         timer.tic('transferring graphs to GPU')
         gs = self.graphset(list(graphs))
@@ -475,13 +472,15 @@ class B200Backend(Backend):
         timer.tic('GPU kernel execution')
         a = self.launch(gs, prog, node_kernel, edge_kernel, p, q, eps, ftol,
                         gtol, jobs, starts, gramian, gradient, nX, nY, nJ,
-                        stream=stream, keep_on_device=keep_on_device)
+                        stream=stream, keep_on_device=keep_on_device,
+                        store_diag=store_diag, normalize=normalize)
         timer.toc('GPU kernel execution')
         return a
 
     def launch(self, gs, prog, node_kernel, edge_kernel, p, q, eps, ftol,
                gtol, jobs, starts, gramian, gradient, nX, nY, nJ, row0=0,
-               col0=0, stream=None, keep_on_device=False, upload=False):
+               col0=0, stream=None, keep_on_device=False, upload=False,
+               store_diag=False, normalize=False):
         """One ``gdb_solve`` call.  ``jobs`` is an explicit (i, j) array or a
         ``PairJobs`` grid descriptor (no per-pair host data)."""
         lib = native.load()
@@ -497,6 +496,7 @@ class B200Backend(Backend):
             a.n_jobs = n_jobs = len(jobs)
         a.row0, a.col0 = int(row0), int(col0)
         a.upload_graphs = int(upload)
+        a.store_diag, a.normalize = int(store_diag), int(normalize)
         starts = np.ascontiguousarray(starts, dtype=np.uint32)
         a.starts = starts.ctypes.data
         a.n_starts = len(starts)

@@ -121,8 +121,21 @@ class MarginalizedGraphKernel:
                 'in type, try `Graph.unify_datatype` as an automatic fix.\n'
                 f'First graph: {first}\nSecond graph: {second}\n')
 
+    def normalized_gram(self, X, Y=None, eval_gradient=False, lmin=0,
+                        timing=False, **unsupported):
+        """K_ij / sqrt(K_ii K_jj) (and its Jacobian) with the normalization
+        fused into the solver's epilogue: one extra launch for the
+        self-similarities, no host post-processing.  Returns NotImplemented
+        when the back end cannot do it (``Normalization`` then falls back to
+        the reference's host formulas, reference kernel/fix.py:46-73)."""
+        if unsupported or not getattr(self.backend, 'fused_normalization',
+                                      False):
+            return NotImplemented
+        return self.__call__(X, Y, eval_gradient=eval_gradient, lmin=lmin,
+                             timing=timing, _fused_normalization=True)
+
     def __call__(self, X, Y=None, eval_gradient=False, nodal=False, lmin=0,
-                 timing=False):
+                 timing=False, _fused_normalization=False):
         """Pairwise similarity matrix between the graphs in ``X`` (and ``Y``).
 
         Returns the (len(X), len(Y)) matrix -- node-by-node if ``nodal`` --
@@ -177,9 +190,27 @@ class MarginalizedGraphKernel:
         timer.toc('creating output buffer')
 
         timer.tic('calling GPU kernel (overall)')
+        extra = {}
+        if _fused_normalization:
+            # self-similarities of every graph stay on the device ...
+            n = len(graphs)
+            djobs = np.empty(n, dtype=JOB_DTYPE)
+            djobs['i'] = djobs['j'] = np.arange(n)
+            backend(graphs, self.node_kernel, self.edge_kernel, self.p,
+                    self.q, self.eps, self.ftol, self.gtol,
+                    backend.array(djobs),
+                    np.arange(n + 1, dtype=np.uint32),
+                    backend.empty(n, np.float32),
+                    backend.empty(n * self.n_dims, np.float32)
+                    if traits.eval_gradient is True else None,
+                    n, 1, self.n_dims,
+                    self.traits(diagonal=True, lmin=lmin,
+                                eval_gradient=eval_gradient),
+                    timer, store_diag=True, keep_on_device=True)
+            extra['normalize'] = True   # ... and scale the main solve
         backend(graphs, self.node_kernel, self.edge_kernel, self.p, self.q,
                 self.eps, self.ftol, self.gtol, jobs, starts, gramian,
-                gradient, rows, cols, self.n_dims, traits, timer)
+                gradient, rows, cols, self.n_dims, traits, timer, **extra)
         timer.toc('calling GPU kernel (overall)')
 
         timer.tic('collecting result')

@@ -28,6 +28,41 @@ def tile_pairs(i0, i1, n):
     return rows * m - rows * (rows - 1) // 2
 
 
+class LocalTileQueue:
+    """Dynamic tile queue for worker threads of one process."""
+
+    def __init__(self, tiles):
+        self.tiles = list(tiles)
+        self._lock = threading.Lock()
+        self._next = 0
+
+    def __iter__(self):
+        while True:
+            with self._lock:
+                t = self._next
+                self._next += 1
+            if t >= len(self.tiles):
+                return
+            yield self.tiles[t]
+
+
+class StoreTileQueue:
+    """Dynamic tile queue shared by the ranks of a ``torch.distributed`` job
+    (one process per GPU): an atomic counter in the rendezvous store hands out
+    tile indices, so faster ranks simply take more tiles.  No collective and no
+    tensor traffic is involved; ``key`` must be unique per pass."""
+
+    def __init__(self, store, tiles, key):
+        self.store, self.tiles, self.key = store, list(tiles), key
+
+    def __iter__(self):
+        while True:
+            t = self.store.add(self.key, 1) - 1
+            if t >= len(self.tiles):
+                return
+            yield self.tiles[t]
+
+
 class GramTileWorker:
     """Evaluates tiles of the symmetric Gram matrix of ``graphs`` on one
     device.  All graphs are resident on the device; outputs are tile-sized
@@ -79,30 +114,34 @@ class GramTileWorker:
         s['pairs'] += len(jobs)
         return a
 
-    def diag(self, upload=False):
-        """Self-similarities (and their Jacobians) of all graphs."""
+    def diag(self, upload=False, store=False):
+        """Self-similarities (and their Jacobians) of all graphs; ``store``
+        keeps them on the device for ``run_tile(normalize=True)``."""
         n = self.n
         jobs = np.empty(n, dtype=[('i', np.uint32), ('j', np.uint32)])
         jobs['i'] = jobs['j'] = np.arange(n)
         d = self.backend.empty(n, np.float32)
         dd = (self.backend.empty(n * self.nJ, np.float32)
               if self.eval_gradient else None)
-        self._launch(self.prog_diag, jobs, d, dd, n, 1, upload=upload)
+        self._launch(self.prog_diag, jobs, d, dd, n, 1, upload=upload,
+                     store_diag=store)
         d = np.array(d, dtype=float)
         if dd is not None:
             dd = np.array(dd, dtype=float).reshape(n, self.nJ, order='F')
         return d, dd
 
-    def run_tile(self, i0, i1, keep_on_device=False):
-        """Raw tile: ``K[i - i0, j]`` for i in [i0,i1), j in [i,n) (zeros
-        left of the diagonal); views into reused pinned buffers."""
+    def run_tile(self, i0, i1, keep_on_device=False, normalize=False):
+        """Tile ``K[i - i0, j]`` for i in [i0,i1), j in [i,n) (zeros left of
+        the diagonal), raw or -- after ``diag(store=True)`` -- normalized on
+        the device; views into reused pinned buffers."""
         rows = i1 - i0
         assert rows <= self.max_rows
         out = self.out[:rows * self.n]
         dout = (self.dout[:rows * self.n * self.nJ]
                 if self.dout is not None else None)
         self._launch(self.prog, PairJobs.triu(i0, i1, self.n), out, dout,
-                     rows, self.n, row0=i0, keep_on_device=keep_on_device)
+                     rows, self.n, row0=i0, keep_on_device=keep_on_device,
+                     normalize=normalize)
         if keep_on_device:
             return None, None
         K = out.reshape(rows, self.n, order='F')
@@ -146,9 +185,8 @@ def gram_tiled(kernel, graphs, devices=(0,), eval_gradient=False,
             be = B200Backend(device=dev, block_size=getattr(
                 kernel.backend, 'block_size', None))
             w = GramTileWorker(kernel, graphs, be, eval_gradient, tile_rows)
-            d = dd = None
             if normalize:
-                d, dd = w.diag()
+                w.diag(store=True)
             while True:
                 with lock:
                     t = cursor[0]
@@ -156,9 +194,7 @@ def gram_tiled(kernel, graphs, devices=(0,), eval_gradient=False,
                 if t >= len(tiles):
                     break
                 i0, i1 = tiles[t]
-                Kt, dKt = w.run_tile(i0, i1)
-                if normalize:
-                    Kt, dKt = w.normalize_tile(Kt, dKt, i0, d, dd)
+                Kt, dKt = w.run_tile(i0, i1, normalize=normalize)
                 K[i0:i1] = Kt
                 if dK is not None:
                     dK[i0:i1] = dKt

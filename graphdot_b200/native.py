@@ -90,6 +90,7 @@ class SolveArgs(C.Structure):
                 ('gramian', C.c_void_p), ('gradient', C.c_void_p),
                 ('nX', C.c_uint32), ('nY', C.c_uint32), ('nJ', C.c_uint32),
                 ('row0', C.c_uint32), ('col0', C.c_uint32),
+                ('store_diag', C.c_int32), ('normalize', C.c_int32),
                 ('upload_graphs', C.c_int32),
                 ('stream', C.c_void_p), ('keep_on_device', C.c_int32),
                 ('kernel_ms', C.c_float), ('h2d_ms', C.c_float),

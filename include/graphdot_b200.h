@@ -95,10 +95,12 @@ typedef struct gdb_program_desc {
     /* traits (reference _kernel.py:48-58) -- compile-time specialisation  */
     int32_t diagonal, symmetric, nodal, lmin, eval_gradient;
     int32_t block_size;      /* threads cooperating on one pair; 0 = auto  */
-    int32_t workers_per_thread; /* small-pair kernel: (tile row, column)
-                                workers per thread, 1..4; 0 = 1.  The kernel
-                                is used when block_size * workers_per_thread
-                                covers max tile rows * max nodes            */
+    int32_t workers_per_thread; /* small-pair kernel: columns per lane, 1..4;
+                                0 = 1.  That kernel maps one warp to each
+                                8-row tile of the first graph and lanes to the
+                                columns (nodes of the second graph); it is used
+                                when block_size >= 32 * tile rows and
+                                32 * workers_per_thread >= nodes             */
     const char *extra_options; /* extra NVRTC options, space separated     */
 } gdb_program_desc;
 
@@ -200,6 +202,15 @@ typedef struct gdb_solve_args {
     uint32_t row0, col0;      /* subtracted from starts[i] / starts[j]: lets
                                  a tile of a larger Gram use a tile-sized
                                  output                                    */
+    int32_t store_diag;       /* 1 (diagonal programs): keep this solve's
+                                 self-similarities (and Jacobians) on the
+                                 device for later `normalize` solves over the
+                                 same graph set; jobs must be (i, i) for every
+                                 graph with starts[i] = i                   */
+    int32_t normalize;        /* 1 (graph-level, non-diagonal programs):
+                                 write K_ij / sqrt(K_ii K_jj) and its Jacobian
+                                 (reference kernel/fix.py:46-73) using the
+                                 stored self-similarities                   */
     int32_t upload_graphs;    /* 1: re-send the graph set's pinned host image
                                  first (host->device leg of an end-to-end
                                  call)                                     */

@@ -376,6 +376,36 @@ def test_implicit_job_grids_match_explicit_lists(backend):
     assert np.array_equal(rect, K[2:4, 5:9])
 
 
+def test_fused_normalization_matches_host_formulas(backend):
+    """Normalization fused into the solver epilogue (self-similarities kept
+    on the device) against the reference's host formulas (reference
+    kernel/fix.py:46-73) applied to the raw outputs, and against the tiled
+    multi-worker evaluation."""
+    from graphdot_b200.kernel.marginalized._tiles import gram_tiled
+    G = make_config_graphs('C2', 10)
+    kernel = make_config_kernel('C2', backend=backend)
+    norm = Normalization(kernel)
+    for X, Y in ((G, None), (G[:4], G[4:])):
+        K, dK = norm(X, Y, eval_gradient=True)
+        Kh, dKh = norm._host_normalized(X, Y, eval_gradient=True)
+        assert np.allclose(K, Kh, rtol=2e-6)
+        assert np.allclose(dK, dKh, rtol=1e-4, atol=2e-6)
+        assert np.allclose(norm(X, Y), Kh, rtol=2e-6)
+    K, dK = norm(G, eval_gradient=True)
+    assert np.allclose(np.diag(K), 1.0, atol=1e-6)
+    assert np.count_nonzero(K - K.T) == 0
+    Kt, dKt = gram_tiled(kernel, G, devices=(0,), eval_gradient=True,
+                         tile_rows=4)
+    assert np.allclose(Kt, K, rtol=1e-6)
+    assert np.allclose(dKt[:, :, kernel.active_theta_mask], dK, rtol=1e-5,
+                       atol=1e-6)
+    raw = gram_tiled(kernel, G, devices=(0,), normalize=False, tile_rows=3)
+    assert np.allclose(raw, kernel(G), rtol=1e-6)
+    # nodal outputs are normalized on the host as in the reference
+    Kn = norm(G[:2], nodal=True)
+    assert Kn.shape[0] == sum(len(g.nodes) for g in G[:2])
+
+
 def test_block_sizes_agree(backend):
     G = make_config_graphs('C2', 6)
     ref = None

@@ -46,7 +46,7 @@ def test_no_device_is_reported_not_hidden():
 
 def _unpack(blob, edge_size, label_off):
     """Decode a packed blob back into (degree, dense weight/label index)."""
-    hdr = np.frombuffer(blob[:64], dtype=np.uint32)
+    hdr = np.frombuffer(blob[:80], dtype=np.uint32)
     n, n_oct, nnz, n_tile = hdr[:4].astype(int)
     off_deg, off_node, off_oct, off_trow, off_edge, off_pool, total = \
         hdr[4:11].astype(int)
@@ -127,7 +127,7 @@ def test_variable_length_features_are_pooled(mlgk_golden):
     assert el.decl == 'frozen_array<int16> spectrum;'
     assert nl.dtype.itemsize == 16 and nl.ptr_offsets == [0] and weighted
     blob = be.pack_graph(G[0]).blob.tobytes()
-    hdr = np.frombuffer(blob[:64], dtype=np.uint32)
+    hdr = np.frombuffer(blob[:80], dtype=np.uint32)
     off_node, off_pool = int(hdr[5]), int(hdr[9])
     rows = np.frombuffer(blob[off_node:off_node + 3 * 16], dtype=nl.dtype)
     want = [[5, 6], [3], [2, 3, 4]]
