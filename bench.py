@@ -227,6 +227,8 @@ def run_gpu(args, rank, world, local_rank):
     import torch.distributed as dist
     from graphdot_b200.kernel.marginalized._backend_b200 import B200Backend
     from graphdot_b200.kernel.marginalized._tiles import (GramTileWorker,
+                                                          LocalTileQueue,
+                                                          StoreTileQueue,
                                                           row_tiles,
                                                           tile_pairs)
     from graphdot_b200.synthetic import make_config_graphs, make_config_kernel
@@ -246,7 +248,8 @@ def run_gpu(args, rank, world, local_rank):
     n = n_graphs_for(world)
     G = make_config_graphs('C2', n)
     backend = B200Backend(device=local_rank,
-                          block_size=args.block_size or None)
+                          block_size=args.block_size or None,
+                          nvrtc_extra=args.nvrtc_extra.split())
     kernel = make_config_kernel('C3', backend=backend)
     stream = torch.cuda.current_stream()
     worker = GramTileWorker(kernel, G, backend, eval_gradient=True,
@@ -267,13 +270,8 @@ def run_gpu(args, rank, world, local_rank):
         key = f'tiles{step_no[0]}'
         step_no[0] += 1
         if store is None:
-            yield from tiles
-            return
-        while True:
-            t = store.add(key, 1) - 1
-            if t >= len(tiles):
-                return
-            yield tiles[t]
+            return iter(LocalTileQueue(tiles))
+        return iter(StoreTileQueue(store, tiles, key))
 
     def step_device():
         for i0, i1 in tile_queue():
@@ -418,6 +416,8 @@ def main():
     ap.add_argument('--block-size', type=int, default=0)
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--nvrtc-extra', default='',
+                    help='extra NVRTC options (tuning), space separated')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     rank = int(os.environ.get('RANK', 0))

@@ -24,7 +24,7 @@ struct Sizes {
     uint32_t edge_size, label_off;
     uint32_t nnz, n_octile, n_tile;
     uint64_t off_degree, off_node, off_octile, off_tilerow, off_edge, off_pool, total;
-    uint64_t off_emeta, off_rowptr, off_rowadj, off_tileelem;
+    uint64_t off_emeta, off_rowptr, off_rowadj, off_tileelem, off_ellslot;
 };
 
 struct Nz {
@@ -83,7 +83,8 @@ void plan(const gdb_layout *L, const gdb_graph_src *g, const std::vector<Nz> &nz
     s.off_rowptr = s.off_emeta + pad16(4ull * s.nnz);
     s.off_rowadj = s.off_rowptr + pad16(4ull * (g->n_node + 1));
     s.off_tileelem = s.off_rowadj + pad16(4ull * s.nnz);
-    s.off_pool = s.off_tileelem + pad16(4ull * (s.n_tile + 1));
+    s.off_ellslot = s.off_tileelem + pad16(4ull * (s.n_tile + 1));
+    s.off_pool = s.off_ellslot + pad16(4ull * s.nnz);
     s.total = s.off_pool + pad16(g->pool_bytes);
 }
 
@@ -189,6 +190,13 @@ extern "C" int gdb_graph_pack(const gdb_layout *L, const gdb_graph_src *g, void 
         uint32_t max_degree = 0;
         for (uint32_t i = 0; i < g->n_node; ++i) max_degree = std::max(max_degree, fill[i + 1]);
         h->max_degree = max_degree;
+        h->off_ellslot = (uint32_t)s.off_ellslot;
+        {
+            uint32_t *ellslot = reinterpret_cast<uint32_t *>(base + s.off_ellslot);
+            const uint32_t wd = (max_degree + 3u) & ~3u;
+            for (uint32_t i = 0; i < g->n_node; ++i)
+                for (uint32_t k = fill[i]; k < fill[i + 1]; ++k) ellslot[k] = i * wd + (k - fill[i]);
+        }
         for (uint32_t i = 0; i < g->n_node; ++i) fill[i + 1] += fill[i];
         for (uint32_t i = 0; i <= g->n_node; ++i) rowptr[i] = fill[i];
         // nz is sorted by (tile row, tile col, row, col): filling in this order

@@ -38,6 +38,10 @@
 #define GDB_WPT 1
 #endif
 #define GDB_ADJ 4  // neighbours of a column kept in registers
+#ifdef GDB_SMALL_MINB  // tuning hook: -DGDB_SMALL_MINB=<resident CTAs per SM>
+#undef GDB_MIN_BLOCKS_SMALL
+#define GDB_MIN_BLOCKS_SMALL GDB_SMALL_MINB
+#endif
 
 #if GDB_GRADIENT
 typedef float2 gv_t;
@@ -100,7 +104,7 @@ struct gdb_small_graph {
     const float *degree;
     const node_t *node;
     const edge_t *edge;
-    const unsigned *emeta, *rowptr, *rowadj;
+    const unsigned *emeta, *rowptr, *rowadj, *ellslot;
     int n, nnz, n_tile;
 };
 
@@ -113,6 +117,7 @@ __device__ __forceinline__ gdb_small_graph gdb_small_view(const unsigned char *b
     v.emeta = reinterpret_cast<const unsigned *>(base + h->off_emeta);
     v.rowptr = reinterpret_cast<const unsigned *>(base + h->off_rowptr);
     v.rowadj = reinterpret_cast<const unsigned *>(base + h->off_rowadj);
+    v.ellslot = reinterpret_cast<const unsigned *>(base + h->off_ellslot);
     v.n = h->n_node;
     v.nnz = h->nnz;
     v.n_tile = h->n_tile;
@@ -165,18 +170,18 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         float *W = reinterpret_cast<float *>(gdb_smem + used);
         gv_t *pbuf = reinterpret_cast<gv_t *>(W + nnz1 * wstride);
 
-        // ---- W = w1 w2 kE(e1, e2), once per pair ---------------------------------
+        // ---- W = w1 w2 kE(e1, e2), once per pair: zero fill, then one balanced pass
+        //      over the nnz1 x nnz2 real element pairs (both in row order) ------------
         {
-            const float inv_s = __frcp_rn((float)wstride), inv_d = __frcp_rn((float)wd);
-            for (unsigned idx = threadIdx.x; idx < (unsigned)(nnz1 * wstride); idx += GDB_BLOCK) {
-                unsigned k1, slot, i2, k;
-                gdb_divmod(idx, (unsigned)wstride, inv_s, k1, slot);
-                gdb_divmod(slot, (unsigned)wd, inv_d, i2, k);
-                const unsigned kbeg = g2.rowptr[i2];
-                float w = 0.f;
-                if (kbeg + k < g2.rowptr[i2 + 1])
-                    w = gdb_edge_value(P, g1.edge[g1.rowadj[k1] >> 16], g2.edge[g2.rowadj[kbeg + k] >> 16]);
-                W[idx] = w;
+            float4 *W4 = reinterpret_cast<float4 *>(W);
+            for (int idx = threadIdx.x; idx < (nnz1 * wstride) / 4; idx += GDB_BLOCK) W4[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            gdb_group_sync();
+            const float inv = __frcp_rn((float)nnz2);
+            for (unsigned idx = threadIdx.x; idx < (unsigned)(nnz1 * nnz2); idx += GDB_BLOCK) {
+                unsigned k1, k2;
+                gdb_divmod(idx, (unsigned)nnz2, inv, k1, k2);
+                W[k1 * wstride + g2.ellslot[k2]] =
+                    gdb_edge_value(P, g1.edge[g1.rowadj[k1] >> 16], g2.edge[g2.rowadj[k2] >> 16]);
             }
         }
 

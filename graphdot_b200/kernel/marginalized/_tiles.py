@@ -172,9 +172,7 @@ def gram_tiled(kernel, graphs, devices=(0,), eval_gradient=False,
     hyper-parameters -- of ``graphs`` using one worker thread per device that
     pull row-block tiles from a shared queue."""
     n = len(graphs)
-    tiles = row_tiles(n, tile_rows)
-    lock = threading.Lock()
-    cursor = [0]
+    queue = LocalTileQueue(row_tiles(n, tile_rows))
     K = np.zeros((n, n), dtype=np.float32)
     dK = (np.zeros((n, n, kernel.n_dims), dtype=np.float32)
           if eval_gradient else None)
@@ -187,13 +185,7 @@ def gram_tiled(kernel, graphs, devices=(0,), eval_gradient=False,
             w = GramTileWorker(kernel, graphs, be, eval_gradient, tile_rows)
             if normalize:
                 w.diag(store=True)
-            while True:
-                with lock:
-                    t = cursor[0]
-                    cursor[0] += 1
-                if t >= len(tiles):
-                    break
-                i0, i1 = tiles[t]
+            for i0, i1 in queue:
                 Kt, dKt = w.run_tile(i0, i1, normalize=normalize)
                 K[i0:i1] = Kt
                 if dK is not None:
