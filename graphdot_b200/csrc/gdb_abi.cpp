@@ -256,8 +256,6 @@ static int render(const gdb_program_desc *d, std::string &src) {
     if (block < 0) return gdb_fail(GDB_ERR_INVALID, "block_size must be a multiple of 32 up to 1024");
     if (d->nodal < 0 || d->nodal > 2 || d->lmin < 0 || d->lmin > 1) return gdb_fail(GDB_ERR_INVALID, "invalid traits");
     if (pick_wpt(d) > 4) return gdb_fail(GDB_ERR_INVALID, "workers_per_thread must be 1..4");
-    if (d->eval_gradient && d->nodal != GDB_NODAL_NONE)
-        return gdb_fail(GDB_ERR_INVALID, "nodal gradients are not implemented by this engine yet");
     std::ostringstream o;
     o << gdb_embedded_prelude << "\n";
     o << "// ---- generated splice ----\n";
@@ -634,7 +632,10 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
         // one warp per tile row of G1, lanes (x workers per thread) over the columns of G2
         const bool mapped = (uint64_t)((gs->max_node[0] + 7) / 8) * 32 <= (uint64_t)block &&
                             (uint64_t)gs->max_node[0] <= 32ull * p->wpt;
-        if (gs->index16 && small_need <= small_cap && mapped && wmax < (1u << 24) && !getenv("GDB_FORCE_GENERAL")) {
+        // nodal Jacobians (forward sensitivities) are implemented by the general kernel only
+        const bool nodal_grad = p->eval_gradient && p->nodal != GDB_NODAL_NONE;
+        if (gs->index16 && small_need <= small_cap && mapped && wmax < (1u << 24) && !nodal_grad &&
+            !getenv("GDB_FORCE_GENERAL")) {
             fn = p->fn_small;
             smem = small_need;
             spill = false;

@@ -191,14 +191,14 @@ extern "C" int gdb_graph_pack(const gdb_layout *L, const gdb_graph_src *g, void 
         for (uint32_t i = 0; i < g->n_node; ++i) max_degree = std::max(max_degree, fill[i + 1]);
         h->max_degree = max_degree;
         h->off_ellslot = (uint32_t)s.off_ellslot;
+        for (uint32_t i = 0; i < g->n_node; ++i) fill[i + 1] += fill[i];
+        for (uint32_t i = 0; i <= g->n_node; ++i) rowptr[i] = fill[i];
         {
             uint32_t *ellslot = reinterpret_cast<uint32_t *>(base + s.off_ellslot);
             const uint32_t wd = (max_degree + 3u) & ~3u;
             for (uint32_t i = 0; i < g->n_node; ++i)
-                for (uint32_t k = fill[i]; k < fill[i + 1]; ++k) ellslot[k] = i * wd + (k - fill[i]);
+                for (uint32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) ellslot[k] = i * wd + (k - rowptr[i]);
         }
-        for (uint32_t i = 0; i < g->n_node; ++i) fill[i + 1] += fill[i];
-        for (uint32_t i = 0; i <= g->n_node; ++i) rowptr[i] = fill[i];
         // nz is sorted by (tile row, tile col, row, col): filling in this order
         // leaves every row's neighbours sorted by column
         for (uint32_t k = 0; k < s.nnz; ++k) rowadj[fill[nz[k].i]++] = (nz[k].j & 0xffffu) | (k << 16);

@@ -368,8 +368,10 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
         int iters = gdb_pcg(P, g1, g2, diag, x, r, p, Ap, F.ftol, s_red, flip);
 
 #if GDB_GRADIENT
-        // ---- adjoint solve  y = A^-1 (p1 (x) p2)  (A is symmetric) -----------
         float *y = vec + 5 * Npad;
+#endif
+#if GDB_GRADIENT && GDB_NODAL == 0
+        // ---- adjoint solve  y = A^-1 (p1 (x) p2)  (A is symmetric) -----------
         for (int i = threadIdx.x; i < (int)N; i += GDB_BLOCK) {
             const int i1 = i / n2, i2 = i - i1 * n2;
             r[i] = P.p_start(g1.node[i1]) * P.p_start(g2.node[i2]);
@@ -557,6 +559,136 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
                 if (ja != jb) F.grad[(unsigned long long)I2 + (unsigned long long)I1 * F.nX + m * plane] = s;
 #endif
 #endif
+            }
+        }
+#endif
+#if GDB_GRADIENT && GDB_NODAL != 0
+        // ---- nodal Jacobian by forward sensitivities ------------------------------
+        // R_i = xs_i p1 p2.  d/dp_m is explicit; for q, node and edge parameters
+        //     dx/dt = A^-1 (db/dt - dA/dt x)
+        // is one more solve with the same operator per parameter (the reference
+        // instead re-solves twice per parameter for a central difference,
+        // template.cu:226-418):
+        //   q:      rhs = 2Q Dx (1 - x / Vx)
+        //   node m: rhs = Dx / Vx^2 dVx_m x          (+ lmin: R -= dVx_m p1 p2)
+        //   edge m: rhs = (dW_m) x = sum_j w1 w2 dkE_m x_j
+        {
+            auto write_nodal = [&](int i, int i1, int i2, int m, float val) {
+#if GDB_NODAL == 2
+                if (true) F.grad[(unsigned long long)(I1 + i1 + i2 * n1) + (unsigned long long)m * F.nX] = val;
+#elif GDB_DIAGONAL
+                if (i1 == i2) F.grad[(unsigned long long)(I1 + i1) + (unsigned long long)m * F.nX] = val;
+#else
+                F.grad[(unsigned long long)(I1 + i1) + (unsigned long long)(I2 + i2) * F.nX + m * plane] = val;
+#if GDB_SYMMETRIC
+                if (ja != jb) F.grad[(unsigned long long)(I2 + i2) + (unsigned long long)(I1 + i1) * F.nX + m * plane] = val;
+#endif
+#endif
+                (void)i;
+            };
+#if GDB_NP > 0
+            for (int i = threadIdx.x; i < (int)N; i += GDB_BLOCK) {
+                const int i1 = i / n2, i2 = i - i1 * n2;
+                const node_t &u1 = g1.node[i1];
+                const node_t &u2 = g2.node[i2];
+                float xs = x[i];
+#if GDB_LMIN == 1
+                xs -= P.node_kernel(u1, u2);
+#endif
+                float d1[GDB_NP], d2[GDB_NP];
+                P.p_start.jacobian(u1, d1);
+                P.p_start.jacobian(u2, d2);
+                const float p1 = P.p_start(u1), p2 = P.p_start(u2);
+#pragma unroll
+                for (int m = 0; m < GDB_NP; ++m) write_nodal(i, i1, i2, m, xs * fmaf(d1[m], p2, p1 * d2[m]));
+            }
+#endif
+            int extra_iters = 0;
+#pragma unroll 1
+            for (int m = GDB_NP; m < GDB_NJ; ++m) {
+                gdb_group_sync();  // x stable, r free
+                for (int i = threadIdx.x; i < (int)N; i += GDB_BLOCK) {
+                    const int i1 = i / n2, i2 = i - i1 * n2;
+                    const node_t &u1 = g1.node[i1];
+                    const node_t &u2 = g2.node[i2];
+                    const float dx = g1.degree[i1] * g2.degree[i2] * Q2;
+                    float rhs = 0.f;
+                    if (m == GDB_NP) {
+                        rhs = 2.f * Q * dx * (1.f - __fdividef(x[i], P.node_kernel(u1, u2)));
+                    }
+#if GDB_NV > 0
+                    else if (m < GDB_NP + 1 + GDB_NV) {
+                        float dv[GDB_NV];
+                        P.node_kernel.jacobian(u1, u2, dv);
+                        float dvm = 0.f;
+#pragma unroll
+                        for (int k = 0; k < GDB_NV; ++k) dvm = (k == m - GDB_NP - 1) ? dv[k] : dvm;
+                        const float v = P.node_kernel(u1, u2);
+                        rhs = __fdividef(dx, v * v) * dvm * x[i];
+                    }
+#endif
+#if GDB_NE > 0
+                    else {
+                        const int r1 = (i1 & 7) * 8, r2 = (i2 & 7) * 8;
+                        const unsigned o1_end = g1.trow[(i1 >> 3) + 1], o2_beg = g2.trow[i2 >> 3],
+                                       o2_end = g2.trow[(i2 >> 3) + 1];
+                        for (unsigned o1 = g1.trow[i1 >> 3]; o1 < o1_end; ++o1) {
+                            const gdb_octile t1 = g1.oct[o1];
+                            unsigned m1 = (unsigned)(t1.mask >> r1) & 0xffu;
+                            if (!m1) continue;
+                            const edge_t *e1 = g1.edge + t1.start + __popcll(t1.mask & ((1ull << r1) - 1ull));
+                            const float *x1 = x + (int)t1.tcol * 8 * n2;
+                            for (; m1; m1 &= m1 - 1, ++e1) {
+                                const float *xrow = x1 + (__ffs(m1) - 1) * n2;
+                                for (unsigned o2 = o2_beg; o2 < o2_end; ++o2) {
+                                    const gdb_octile t2 = g2.oct[o2];
+                                    unsigned m2 = (unsigned)(t2.mask >> r2) & 0xffu;
+                                    if (!m2) continue;
+                                    const edge_t *e2 = g2.edge + t2.start + __popcll(t2.mask & ((1ull << r2) - 1ull));
+                                    const float *xp = xrow + (int)t2.tcol * 8;
+                                    for (; m2; m2 &= m2 - 1, ++e2) {
+                                        float de[GDB_NE];
+                                        P.edge_kernel.jacobian(e1->label, e2->label, de);
+                                        float dem = 0.f;
+#pragma unroll
+                                        for (int k = 0; k < GDB_NE; ++k) dem = (k == m - GDB_NP - 1 - GDB_NV) ? de[k] : dem;
+#if GDB_WEIGHTED
+                                        dem *= e1->weight * e2->weight;
+#endif
+                                        rhs = fmaf(dem, xp[__ffs(m2) - 1], rhs);
+                                    }
+                                }
+                            }
+                        }
+                    }
+#endif
+                    r[i] = rhs;
+                }
+                extra_iters += gdb_pcg(P, g1, g2, diag, y, r, p, Ap, F.ftol, s_red, flip);
+                gdb_group_sync();
+                for (int i = threadIdx.x; i < (int)N; i += GDB_BLOCK) {
+                    const int i1 = i / n2, i2 = i - i1 * n2;
+                    const node_t &u1 = g1.node[i1];
+                    const node_t &u2 = g2.node[i2];
+                    float val = y[i];
+#if GDB_NODAL == 2 || GDB_SYMMETRIC
+                    if (ja == jb) val = 0.5f * (val + y[i2 * n2 + i1]);  // self pair: bit-exact symmetry
+#endif
+#if GDB_LMIN == 1 && GDB_NV > 0
+                    if (m > GDB_NP && m < GDB_NP + 1 + GDB_NV) {
+                        float dv[GDB_NV];
+                        P.node_kernel.jacobian(u1, u2, dv);
+#pragma unroll
+                        for (int k = 0; k < GDB_NV; ++k) val -= (k == m - GDB_NP - 1) ? dv[k] : 0.f;
+                    }
+#endif
+                    write_nodal(i, i1, i2, m, val * P.p_start(u1) * P.p_start(u2));
+                }
+            }
+            if (threadIdx.x == 0) {
+                atomicAdd(F.counters + 1, (unsigned long long)extra_iters);
+                atomicAdd(F.counters + 2, (unsigned long long)extra_iters * (unsigned long long)g1.nnz * (unsigned long long)g2.nnz);
+                atomicAdd(F.counters + 3, (unsigned long long)extra_iters * (unsigned long long)N);
             }
         }
 #endif

@@ -435,9 +435,6 @@ class B200Backend(Backend):
     def program(self, gs, node_kernel, edge_kernel, p, traits):
         if traits.lmin not in (0, 1):
             raise ValueError(f'lmin must be 0 or 1, got {traits.lmin}')
-        if traits.eval_gradient is True and traits.nodal is not False:
-            raise NotImplementedError(
-                'nodal gradients are not implemented by the B200 engine yet')
         nl, el, weighted = gs.layouts
         block = self._pick_block(gs.sizes, traits.eval_gradient is True)
         d, keep, key = self._desc(nl, el, weighted, node_kernel, edge_kernel,

@@ -137,6 +137,60 @@ def test_gradient_vs_finite_differences_of_the_kernel(mlgk_golden, backend,
         assert np.allclose(dR[:, :, i], dR_dt, rtol=0.05, atol=0.05)
 
 
+@pytest.mark.parametrize('name', ['labeled', 'weighted', 'vario-features',
+                                  'molecular'])
+@pytest.mark.parametrize('lmin', [0, 1])
+def test_nodal_gradient_vs_oracle(mlgk_golden, backend, name, lmin):
+    """Nodal Jacobian (forward sensitivities on the device; the reference uses
+    finite differences, reference template.cu:226-418, and only checks them to
+    5 %, test_kernel.py:244-289) against central differences of the float64
+    oracle, for the full matrix, an X-by-Y block and the nodal diagonal."""
+    from graphdot_b200.util import flatten, fold_like
+    case = mlgk_golden['cases'][name]
+    G = golden_graphs(case)
+    knode, kedge = golden_kernels(name)
+    q, pv = 0.1, 1.3
+    mlgk = MarginalizedGraphKernel(knode, kedge, q=q, p=Uniform(pv),
+                                   backend=backend)
+    R, dR = mlgk(G, nodal=True, eval_gradient=True, lmin=lmin)
+    assert dR.shape == (*R.shape, mlgk.active_theta_mask.sum())
+    assert np.count_nonzero(dR - dR.transpose(1, 0, 2)) == 0
+
+    def value(pv, qv, tv, te):
+        kn, ke = golden_kernels(name)
+        kn.theta = fold_like(tv, kn.theta)
+        ke.theta = fold_like(te, ke.theta)
+        return oracle.gram(G, knode=kn, kedge=ke, q=qv, p=Uniform(pv),
+                           nodal=True, lmin=lmin)
+
+    assert rel_err(R, value(pv, q, list(flatten(knode.theta)),
+                            list(flatten(kedge.theta)))) < GRAM_RTOL
+    base = [np.array([pv]), np.array([q]),
+            np.array(list(flatten(knode.theta)), float),
+            np.array(list(flatten(kedge.theta)), float)]
+    fd = []
+    for blk in range(4):
+        for i in range(len(base[blk])):
+            h = 1e-6 * max(1.0, abs(base[blk][i]))
+            hi = [b.copy() for b in base]
+            lo = [b.copy() for b in base]
+            hi[blk][i] += h
+            lo[blk][i] -= h
+            fd.append((value(hi[0][0], hi[1][0], hi[2], hi[3]) -
+                       value(lo[0][0], lo[1][0], lo[2], lo[3])) / (2 * h))
+    fd = np.stack(fd, axis=2)[:, :, mlgk.active_theta_mask]
+    for k in range(dR.shape[2]):
+        scale = np.abs(fd[:, :, k]).max()
+        assert np.abs(dR[:, :, k] - fd[:, :, k]).max() < \
+            GRAD_RTOL * max(scale, 1e-6), (name, lmin, k)
+    n0 = len(G[0].nodes)
+    Rxy, dRxy = mlgk(G[:1], G[1:], nodal=True, eval_gradient=True, lmin=lmin)
+    assert np.allclose(dRxy, dR[:n0, n0:], rtol=1e-4, atol=1e-6)
+    D, dD = mlgk.diag(G, nodal=True, eval_gradient=True, lmin=lmin)
+    assert np.allclose(D, np.diag(R), rtol=1e-6)
+    assert np.allclose(dD, np.einsum('iik->ik', dR), rtol=1e-4, atol=1e-6)
+
+
 @pytest.mark.parametrize('name', CASES)
 def test_diag_and_nodal(mlgk_golden, backend, name):
     """reference test_kernel.py:292-340"""

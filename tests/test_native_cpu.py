@@ -110,6 +110,46 @@ def test_octile_packer_roundtrip():
     assert be.uuid not in g.cookie
 
 
+def test_row_index_sections_of_the_blob():
+    """elem_meta / row_ptr / row_adj / tile_elem / ell_slot are consistent with
+    the octile-ordered element array (the small-pair kernel indexes through
+    them instead of decoding bit masks)."""
+    be = B200Backend()
+    for g in make_config_graphs('C2', 4) + make_config_graphs('C1', 2):
+        blob = be.pack_graph(g).blob.tobytes()
+        hdr = np.frombuffer(blob[:80], dtype=np.uint32)
+        n, n_oct, nnz, n_tile = hdr[:4].astype(int)
+        off = {k: int(v) for k, v in zip(
+            ('emeta', 'rowptr', 'rowadj', 'tileelem', 'maxdeg', 'ellslot'),
+            hdr[12:18])}
+        u32 = lambda o, c: np.frombuffer(blob[o:o + 4 * c], dtype=np.uint32)
+        emeta, rowptr = u32(off['emeta'], nnz), u32(off['rowptr'], n + 1)
+        rowadj, tileelem = u32(off['rowadj'], nnz), u32(off['tileelem'],
+                                                        n_tile + 1)
+        ellslot = u32(off['ellslot'], nnz)
+        rows, cols = emeta & 0xffff, emeta >> 16
+        ei, ej = np.asarray(g.edges['!i']), np.asarray(g.edges['!j'])
+        want = sorted(set(zip(ei.tolist(), ej.tolist()))
+                      | set(zip(ej.tolist(), ei.tolist())))
+        assert sorted(zip(rows.tolist(), cols.tolist())) == want
+        assert rowptr[0] == 0 and rowptr[-1] == nnz
+        deg = np.diff(rowptr.astype(int))
+        assert off['maxdeg'] == deg.max()
+        wd = (int(deg.max()) + 3) // 4 * 4
+        for i in range(n):
+            adj = rowadj[rowptr[i]:rowptr[i + 1]]
+            elem = adj >> 16
+            assert np.all(rows[elem] == i)                 # elements of row i
+            assert np.array_equal(cols[elem], adj & 0xffff)
+            assert np.all(np.diff((adj & 0xffff).astype(int)) > 0)
+            assert np.array_equal(ellslot[rowptr[i]:rowptr[i + 1]],
+                                  i * wd + np.arange(deg[i]))
+        for t in range(n_tile):
+            sel = rows[tileelem[t]:tileelem[t + 1]]
+            assert np.all(sel // 8 == t)
+        assert tileelem[-1] == nnz
+
+
 def test_isolated_node_gets_unit_degree():
     from graphdot_b200 import Graph
     g = Graph({'!i': np.arange(3, dtype=np.uint32)},
@@ -194,8 +234,12 @@ def test_compile_errors_are_reported():
     assert lib.gdb_program_compile_only(C.byref(d), None) == -1
     d, keep, _ = B200Backend._desc(
         nl, el, weighted, k.node_kernel, k.edge_kernel, Uniform(1.0),
-        T(nodal=True, eval_gradient=True), 32, ())
-    assert lib.gdb_program_compile_only(C.byref(d), None) == -1
+        T(nodal=True, eval_gradient=True), (96, 5), ())
+    assert lib.gdb_program_compile_only(C.byref(d), None) == -1   # wpt > 4
+    d, keep, _ = B200Backend._desc(
+        nl, el, weighted, k.node_kernel, k.edge_kernel, Uniform(1.0),
+        T(nodal=True, eval_gradient=True), (96, 1), ())
+    assert lib.gdb_program_compile_only(C.byref(d), None) == 0    # nodal Jacobian
 
 
 def test_pair_jobs_descriptor_matches_explicit_lists():
