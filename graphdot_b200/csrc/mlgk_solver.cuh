@@ -592,6 +592,9 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
                 const node_t &u1 = g1.node[i1];
                 const node_t &u2 = g2.node[i2];
                 float xs = x[i];
+#if GDB_NODAL == 2 || GDB_SYMMETRIC
+                if (ja == jb) xs = 0.5f * (xs + x[i2 * n2 + i1]);  // self pair: bit-exact symmetry
+#endif
 #if GDB_LMIN == 1
                 xs -= P.node_kernel(u1, u2);
 #endif
@@ -600,7 +603,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
                 P.p_start.jacobian(u2, d2);
                 const float p1 = P.p_start(u1), p2 = P.p_start(u2);
 #pragma unroll
-                for (int m = 0; m < GDB_NP; ++m) write_nodal(i, i1, i2, m, xs * fmaf(d1[m], p2, p1 * d2[m]));
+                for (int m = 0; m < GDB_NP; ++m) write_nodal(i, i1, i2, m, xs * __fadd_rn(__fmul_rn(d1[m], p2), __fmul_rn(p1, d2[m])));  // no FMA: symmetric under swap
             }
 #endif
             int extra_iters = 0;
