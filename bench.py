@@ -209,6 +209,29 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def reference_gpu_rate(n, q):
+    """pairs/s of the REFERENCE's own device code (unmodified template.cu +
+    graphdot/cpp compiled for sm_100a, oracle/_ref/c3_grad) on this GPU for the
+    same graphs: symmetric Gram + Jacobian of the first n graphs, one warm-up
+    and one timed launch, device time of graph_kernel_solver."""
+    from oracle import ref_device
+    if not ref_device.available('c3_grad'):
+        return {'unavailable': 'oracle/_ref/c3_grad not built'}
+    try:
+        ref = ref_device.RefDeviceSolver('c3_grad')
+        n = min(n, ref.n_graphs)
+        jobs = ref_device.triu_jobs(n)
+        ref.solve(ref_device.triu_jobs(64), q, n=n)
+        K, dK, ms = ref.solve(jobs, q, n=n)
+        return {'value': len(jobs) / (ms * 1e-3), 'unit': UNIT,
+                'kernel_ms': ms, 'pairs': len(jobs), 'n_graphs': n,
+                'what': 'reference graph_kernel_solver (grid SMs x 8, block '
+                        '128, --maxrregcount=64) launched through the CUDA '
+                        'driver API; raw (un-normalized) Gram + Jacobian'}
+    except Exception as e:       # the comparator must never break the bench
+        return {'unavailable': f'{type(e).__name__}: {e}'}
+
+
 def algorithmic_flops(stats, sum_N, sum_nnzx, nJ):
     """FP32 flops of the solver per SURVEY.md 8(d): matvec
     W_mv = nnzx (2 + F_e) + 2N per application, plus 13 N per CG iteration,
@@ -401,6 +424,8 @@ def run_gpu(args, rank, world, local_rank):
             'sample': f'{n_pairs} pairs (upper triangle of the first 96 '
                       f'graphs), {dt:.1f} s, float64 dense Kronecker solve + '
                       'adjoint Jacobian (oracle/mlgk_oracle.py)'}
+    if world == 1 and not args.no_reference_gpu:
+        line['reference_gpu'] = reference_gpu_rate(n, kernel.q)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -416,6 +441,7 @@ def main():
     ap.add_argument('--block-size', type=int, default=0)
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-reference-gpu', action='store_true')
     ap.add_argument('--nvrtc-extra', default='',
                     help='extra NVRTC options (tuning), space separated')
     args = ap.parse_args()

@@ -1,0 +1,56 @@
+"""GPU parity against the REFERENCE's own device code: the reference's
+unmodified template.cu + graphdot/cpp, rendered by its own code generator and
+compiled for sm_100a in the build container (oracle/build_ref_device.py),
+launched here without pycuda (oracle/ref_device.py) on the reference's own
+OctileGraph layout of the same synthetic graphs."""
+import numpy as np
+import pytest
+
+from graphdot_b200.kernel.marginalized._backend_b200 import B200Backend
+from graphdot_b200.synthetic import make_config_graphs, make_config_kernel
+from oracle import ref_device
+
+pytestmark = pytest.mark.gpu
+
+
+def _need(name):
+    if not ref_device.available(name):
+        pytest.skip(f'oracle/_ref/{name} not built (build container only)')
+
+
+def test_gram_matches_reference_device_code():
+    _need('c2_gram')
+    n = 80
+    ref = ref_device.RefDeviceSolver('c2_gram')
+    Kr, _, ms = ref.solve(ref_device.triu_jobs(n), q=0.05, n=n)
+    kernel = make_config_kernel('C2', backend=B200Backend())
+    K = kernel(make_config_graphs('C2', n))
+    assert np.allclose(K, Kr, rtol=1e-5), np.abs(K / Kr - 1).max()
+    assert np.count_nonzero(Kr - Kr.T) == 0
+
+
+def test_gradient_matches_reference_device_code():
+    _need('c3_grad')
+    n = 60
+    ref = ref_device.RefDeviceSolver('c3_grad')
+    Kr, dKr, ms = ref.solve(ref_device.triu_jobs(n), q=0.05, n=n)
+    kernel = make_config_kernel('C3', backend=B200Backend())
+    K, dK = kernel(make_config_graphs('C2', n), eval_gradient=True)
+    assert np.allclose(K, Kr, rtol=1e-5)
+    dKr = dKr[:, :, kernel.active_theta_mask]
+    for k in range(dK.shape[2]):
+        scale = np.abs(dKr[:, :, k]).max()
+        assert np.abs(dK[:, :, k] - dKr[:, :, k]).max() < 1e-4 * scale, k
+
+
+def test_unlabeled_closed_form_reference_device_code():
+    _need('c1_gram')
+    ref = ref_device.RefDeviceSolver('c1_gram')
+    n = ref.n_graphs
+    Kr, _, ms = ref.solve(ref_device.triu_jobs(n), q=0.05, n=n)
+    sizes = ref.sizes.astype(float)
+    want = np.outer(sizes, sizes) / (1 - 0.95 ** 2)
+    assert np.allclose(Kr, want, rtol=1e-5)
+    kernel = make_config_kernel('C1', backend=B200Backend())
+    K = kernel(make_config_graphs('C1', n))
+    assert np.allclose(K, Kr, rtol=1e-5)
