@@ -26,7 +26,11 @@ def test_gram_matches_reference_device_code():
     kernel = make_config_kernel('C2', backend=B200Backend())
     K = kernel(make_config_graphs('C2', n))
     assert np.allclose(K, Kr, rtol=1e-5), np.abs(K / Kr - 1).max()
-    assert np.count_nonzero(Kr - Kr.T) == 0
+    # The reference accumulates K(i,j) and K(j,i) with separate float atomics
+    # (reference template.cu:195-201), so its own output is symmetric only to
+    # rounding; ours is bit-exactly symmetric and bit-reproducible.
+    assert np.allclose(Kr, Kr.T, rtol=1e-6)
+    assert np.count_nonzero(K - K.T) == 0
 
 
 def test_gradient_matches_reference_device_code():

@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""Throughput of every BASELINE.json configuration on one GPU (not the
+contract bench -- that is bench.py; this fills the table in DESIGN.md).
+
+    python tools/bench_configs.py [--c4-graphs 24] [--c5-graphs 4000]
+
+C1  100 unlabeled graphs, symmetric normalized Gram (all 5 050 pairs)
+C2  2000 molecules, symmetric normalized Gram
+C3  C2 + Jacobian
+C4  NWS graphs of 200-500 nodes with a Convolution node kernel (subset)
+C5  X x Y off-diagonal block of C2-style molecules (subset of the 20k set)
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from graphdot_b200.kernel.fix import Normalization  # noqa: E402
+from graphdot_b200.kernel.marginalized._backend_b200 import B200Backend  # noqa: E402
+from graphdot_b200.synthetic import make_config_graphs, make_config_kernel  # noqa: E402
+
+
+def timed(fn, repeat=2):
+    fn()
+    best = 1e99
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        out = fn()
+        best = min(best, time.perf_counter() - t0)
+    return out, best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--c4-graphs', type=int, default=24)
+    ap.add_argument('--c5-graphs', type=int, default=4000)
+    ap.add_argument('--only', default='')
+    args = ap.parse_args()
+    be = B200Backend()
+    rows = []
+
+    def record(name, pairs, secs, **extra):
+        last = be.last
+        row = dict(config=name, pairs=pairs, seconds=secs,
+                   pairs_per_s=pairs / secs,
+                   kernel_ms=last.get('kernel_ms'),
+                   small_kernel=last.get('small_kernel'),
+                   cg_iterations_per_pair=last.get('cg_iterations', 0) / max(1, last.get('n_jobs', 1)),
+                   **extra)
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+
+    only = set(args.only.split(',')) if args.only else None
+
+    if not only or 'C1' in only:
+        G = make_config_graphs('C1')
+        k = Normalization(make_config_kernel('C1', backend=be))
+        K, t = timed(lambda: k(G))
+        record('C1', len(G) * (len(G) + 1) // 2, t,
+               max_abs_dev_from_one=float(np.abs(K - 1).max()))
+    if not only or 'C2' in only:
+        G = make_config_graphs('C2')
+        k = Normalization(make_config_kernel('C2', backend=be))
+        K, t = timed(lambda: k(G))
+        record('C2', len(G) * (len(G) + 1) // 2, t)
+    if not only or 'C3' in only:
+        G = make_config_graphs('C2')
+        k = Normalization(make_config_kernel('C3', backend=be))
+        (K, dK), t = timed(lambda: k(G, eval_gradient=True))
+        record('C3', len(G) * (len(G) + 1) // 2, t)
+    if not only or 'C4' in only:
+        G = make_config_graphs('C4', args.c4_graphs)
+        k = make_config_kernel('C4', backend=be)
+        K, t = timed(lambda: k(G), repeat=1)
+        n = np.array([len(g.nodes) for g in G])
+        record('C4', len(G) * (len(G) + 1) // 2, t, n_graphs=len(G),
+               mean_N=float(np.mean(np.outer(n, n))))
+    if not only or 'C5' in only:
+        G = make_config_graphs('C5', args.c5_graphs)
+        h = len(G) // 2
+        k = Normalization(make_config_kernel('C5', backend=be))
+        K, t = timed(lambda: k(G[:h], G[h:]), repeat=1)
+        record('C5', h * (len(G) - h), t, block=f'{h}x{len(G) - h}')
+    return rows
+
+
+if __name__ == '__main__':
+    main()
