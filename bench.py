@@ -256,6 +256,9 @@ def run_gpu(args, rank, world, local_rank):
                                                           tile_pairs)
     from graphdot_b200.synthetic import make_config_graphs, make_config_kernel
 
+    # keep stdout clean for the single JSON line (NCCL prints its version there)
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     store = None
     if world > 1:
@@ -426,7 +429,8 @@ def run_gpu(args, rank, world, local_rank):
                       'adjoint Jacobian (oracle/mlgk_oracle.py)'}
     if world == 1 and not args.no_reference_gpu:
         line['reference_gpu'] = reference_gpu_rate(n, kernel.q)
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.destroy_process_group()
 
