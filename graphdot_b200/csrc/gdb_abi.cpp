@@ -260,7 +260,7 @@ static int render(const gdb_program_desc *d, std::string &src) {
     o << gdb_embedded_prelude << "\n";
     o << "// ---- generated splice ----\n";
     o << "#define GDB_BLOCK " << block << "\n";
-    o << "#define GDB_MIN_BLOCKS " << std::max(1, std::min(16, 640 / block)) << "\n";
+    o << "#define GDB_MIN_BLOCKS " << std::max(1, std::min(16, 1024 / block)) << "\n";
     o << "#define GDB_MIN_BLOCKS_SMALL " << std::max(1, 512 / block) << "\n";
     o << "#define GDB_WPT " << pick_wpt(d) << "\n";
     o << "#define GDB_WEIGHTED " << (d->weighted ? 1 : 0) << "\n";
@@ -445,6 +445,7 @@ struct gdb_graphset_s {
     uint32_t max_node[2] = {0, 0};  // two largest node counts
     uint32_t max_nnz[2] = {0, 0};   // two largest element counts
     uint32_t max_ell = 0;           // largest n_node * pad4(max_degree): floats per W row
+    uint32_t max_idx[2] = {0, 0};   // two largest (row index + edge elements) byte counts
     bool index16 = true;            // every graph carries a valid 16-bit row index
 };
 
@@ -514,12 +515,15 @@ extern "C" int gdb_graphset_create(gdb_context_t c, const gdb_layout *L, uint32_
         top2(gs->max_nnz, (uint32_t)h->nnz);
         gs->max_ell = std::max<uint32_t>(gs->max_ell, (uint32_t)h->n_node * ((h->max_degree + 3u) & ~3u));
         if (!(h->flags & 2u)) gs->index16 = false;
+        top2(gs->max_idx, (uint32_t)(((h->n_node + 1) * 4u + 15u) & ~15u) +
+                              (uint32_t)((h->nnz * 4u + 15u) & ~15u) + (uint32_t)(h->off_emeta - h->off_edge));
         off += blob_bytes[k];
     }
     if (n == 1) {
         gs->max_blob[1] = gs->max_blob[0];
         gs->max_node[1] = gs->max_node[0];
         gs->max_nnz[1] = gs->max_nnz[0];
+        gs->max_idx[1] = gs->max_idx[0];
     }
     *out = gs;
     return gdb_graphset_upload(gs);
@@ -604,8 +608,9 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     const int nvec = p->eval_gradient ? 6 : 5;
     const uint64_t maxN = (uint64_t)gs->max_node[0] * (a->job_mode == GDB_JOBS_LIST || true ? gs->max_node[0] : gs->max_node[1]);
     const uint64_t maxNpad = (maxN + 3) & ~3ull;
-    const uint64_t graphs_need = (uint64_t)gs->max_blob[0] + gs->max_blob[1];
-    const uint64_t full_need = graphs_need + nvec * maxNpad * 4;
+    const uint64_t graphs_need = (uint64_t)gs->max_blob[0] + gs->max_blob[1];  // small kernel: whole blobs
+    const uint64_t idx_need = (uint64_t)gs->max_idx[0] + gs->max_idx[1];       // general kernel: row index + edges
+    const uint64_t full_need = idx_need + nvec * maxNpad * 4;
     uint64_t cap = (uint64_t)p->info.max_dynamic_smem;
     if (const char *env = getenv("GDB_SMEM_CAP")) {  // testing / tuning hook
         const uint64_t v = strtoull(env, nullptr, 10);
@@ -616,8 +621,8 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     if (full_need <= cap) {
         smem = full_need;
         spill = false;
-    } else if (graphs_need <= cap / 2) {
-        smem = graphs_need;  // graphs staged, vectors in the global arena
+    } else if (idx_need <= std::min<uint64_t>(cap, 72 * 1024)) {
+        smem = idx_need;  // index staged, vectors in the global arena
     } else {
         smem = 0;
     }

@@ -115,7 +115,9 @@ struct gdb_graph_view {
     const gdb_octile *oct;
     const unsigned *trow;
     const edge_t *edge;
+    const unsigned *rowptr, *rowadj;  // row index: (col | element << 16) per row
     int n, n_octile, nnz;
+    bool index16;                     // row index valid (n, nnz < 65536)
 };
 
 __device__ __forceinline__ gdb_graph_view gdb_view(const unsigned char *base) {
@@ -126,9 +128,12 @@ __device__ __forceinline__ gdb_graph_view gdb_view(const unsigned char *base) {
     v.oct = reinterpret_cast<const gdb_octile *>(base + h->off_octile);
     v.trow = reinterpret_cast<const unsigned *>(base + h->off_tilerow);
     v.edge = reinterpret_cast<const edge_t *>(base + h->off_edge);
+    v.rowptr = reinterpret_cast<const unsigned *>(base + h->off_rowptr);
+    v.rowadj = reinterpret_cast<const unsigned *>(base + h->off_rowadj);
     v.n = h->n_node;
     v.n_octile = h->n_octile;
     v.nnz = h->nnz;
+    v.index16 = (h->flags & 2u) != 0;
     return v;
 }
 
@@ -226,6 +231,44 @@ __device__ __forceinline__ float gdb_matvec(const gdb_params &P, const gdb_graph
     return dot;
 }
 
+// Same product through the row index (CSR x CSR): no bit-mask decoding, two
+// nested loops over the neighbours of i1 and i2; the edge microkernel is
+// evaluated on the fly (the cached-W variant lives in mlgk_small.cuh).
+__device__ __forceinline__ float gdb_matvec_csr(const gdb_params &P, const gdb_graph_view &g1,
+                                                const gdb_graph_view &g2, const float *__restrict__ diag,
+                                                const float *in, float *__restrict__ out) {
+    const unsigned n2 = (unsigned)g2.n, N = (unsigned)(g1.n * g2.n);
+    const float inv_n2 = __frcp_rn((float)n2);
+    float dot = 0.f;
+    for (unsigned i = threadIdx.x; i < N; i += GDB_BLOCK) {
+        unsigned i1 = (unsigned)(__uint2float_rz(i) * inv_n2);
+        unsigned i2 = i - i1 * n2;
+        if ((int)i2 < 0) {
+            --i1;
+            i2 += n2;
+        } else if (i2 >= n2) {
+            ++i1;
+            i2 -= n2;
+        }
+        const unsigned k1end = g1.rowptr[i1 + 1], k2beg = g2.rowptr[i2], k2end = g2.rowptr[i2 + 1];
+        float acc = 0.f;
+        for (unsigned k1 = g1.rowptr[i1]; k1 < k1end; ++k1) {
+            const unsigned a1 = g1.rowadj[k1];
+            const edge_t &e1 = g1.edge[a1 >> 16];
+            const float *inrow = in + (a1 & 0xffffu) * n2;
+            for (unsigned k2 = k2beg; k2 < k2end; ++k2) {
+                const unsigned a2 = g2.rowadj[k2];
+                acc = fmaf(gdb_edge_value(P, e1, g2.edge[a2 >> 16]), inrow[a2 & 0xffffu], acc);
+            }
+        }
+        const float v = in[i];
+        const float r = fmaf(diag[i], v, -acc);
+        out[i] = r;
+        dot = fmaf(v, r, dot);
+    }
+    return dot;
+}
+
 // Jacobi-PCG for A x = rhs with x0 = 0.  On entry r = rhs; on exit x holds the
 // solution; r, p, Ap are clobbered.  Returns the number of iterations.
 __device__ __forceinline__ int gdb_pcg(const gdb_params &P, const gdb_graph_view &g1, const gdb_graph_view &g2,
@@ -245,7 +288,7 @@ __device__ __forceinline__ int gdb_pcg(const gdb_params &P, const gdb_graph_view
     const float thresh = tol * (float)N;
     int k = 0;
     while (k < N && rho != 0.f) {
-        float pAp = gdb_matvec(P, g1, g2, diag, p, Ap);
+        float pAp = (g1.index16 && g2.index16) ? gdb_matvec_csr(P, g1, g2, diag, p, Ap) : gdb_matvec(P, g1, g2, diag, p, Ap);
         pAp = gdb_group_sum(pAp, red, flip);
         if (pAp == 0.f) break;
         ++k;
@@ -325,22 +368,43 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
         const gdb_graph_ref ref1 = F.graphs[ja], ref2 = F.graphs[jb];
         const unsigned N = ref1.n_node * ref2.n_node;
 
-        // ---- placement: graphs and vectors in shared memory when they fit ----
-        const unsigned char *base1 = ref1.blob, *base2 = ref2.blob;
-        unsigned used = 0;
+        // ---- placement ---------------------------------------------------------
+        // The row index and the edge elements of both graphs (what every matvec
+        // reads) are staged in shared memory when they fit; the rest of the blob
+        // (nodes, feature pools, octiles) is read from global memory.  The CG
+        // vectors live in shared memory when they fit as well, else in this
+        // CTA's slice of the global arena.
         const bool same = (ja == jb);
-        const unsigned gbytes = same ? ref1.bytes : ref1.bytes + ref2.bytes;
-        if (gbytes <= F.smem_bytes) {
-            gdb_copy16(gdb_smem, ref1.blob, ref1.bytes);
-            base1 = gdb_smem;
-            if (same) {
-                base2 = base1;
-            } else {
-                gdb_copy16(gdb_smem + ref1.bytes, ref2.blob, ref2.bytes);
-                base2 = gdb_smem + ref1.bytes;
+        gdb_graph_view g1 = gdb_view(ref1.blob), g2 = gdb_view(ref2.blob);
+        unsigned used = 0;
+        {
+            auto idx_bytes = [](const gdb_graph_view &g) {
+                return (((unsigned)(g.n + 1) * 4u + 15u) & ~15u) + (((unsigned)g.nnz * 4u + 15u) & ~15u) +
+                       (((unsigned)g.nnz * (unsigned)sizeof(edge_t) + 15u) & ~15u);
+            };
+            auto stage = [&](gdb_graph_view &g, unsigned char *dst) {
+                const unsigned b0 = ((unsigned)(g.n + 1) * 4u + 15u) & ~15u, b1 = ((unsigned)g.nnz * 4u + 15u) & ~15u,
+                               b2 = ((unsigned)g.nnz * (unsigned)sizeof(edge_t) + 15u) & ~15u;
+                gdb_copy16(dst, g.rowptr, b0);
+                gdb_copy16(dst + b0, g.rowadj, b1);
+                gdb_copy16(dst + b0 + b1, g.edge, b2);
+                g.rowptr = reinterpret_cast<const unsigned *>(dst);
+                g.rowadj = reinterpret_cast<const unsigned *>(dst + b0);
+                g.edge = reinterpret_cast<const edge_t *>(dst + b0 + b1);
+            };
+            const unsigned need = idx_bytes(g1) + (same ? 0u : idx_bytes(g2));
+            if (g1.index16 && g2.index16 && need <= F.smem_bytes) {
+                stage(g1, gdb_smem);
+                if (same) {
+                    g2.rowptr = g1.rowptr;
+                    g2.rowadj = g1.rowadj;
+                    g2.edge = g1.edge;
+                } else {
+                    stage(g2, gdb_smem + idx_bytes(g1));
+                }
+                used = need;
+                gdb_group_sync();
             }
-            used = gbytes;
-            gdb_group_sync();
         }
         const unsigned Npad = (N + 3u) & ~3u;
         float *vec;
@@ -351,7 +415,6 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
         }
         float *x = vec, *r = vec + Npad, *p = vec + 2 * Npad, *Ap = vec + 3 * Npad, *diag = vec + 4 * Npad;
 
-        const gdb_graph_view g1 = gdb_view(base1), g2 = gdb_view(base2);
         const int n1 = g1.n, n2 = g2.n;
         (void)n1;
         const float Q = 1.0f / (1.0f - F.q);
