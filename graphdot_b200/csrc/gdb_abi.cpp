@@ -632,7 +632,8 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     {
         const uint64_t nrhs = p->eval_gradient ? 2 : 1;
         const uint64_t wmax = (uint64_t)gs->max_nnz[0] * gs->max_ell;  // W[k1][column slots]
-        const uint64_t small_need = graphs_need + wmax * 4 + nrhs * maxNpad * 4;
+        // two blob staging buffers (double-buffered TMA prefetch) + W + one vector
+        const uint64_t small_need = 2 * graphs_need + wmax * 4 + nrhs * maxNpad * 4;
         const uint64_t small_cap = std::min<uint64_t>(cap, (uint64_t)c->prop.sharedMemPerBlockOptin - p->small_static_smem);
         // one warp per tile row of G1, lanes (x workers per thread) over the columns of G2
         const bool mapped = (uint64_t)((gs->max_node[0] + 7) / 8) * 32 <= (uint64_t)block &&
@@ -692,6 +693,7 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     f.q = a->q, f.eps = a->eps, f.ftol = a->ftol, f.gtol = a->gtol;
     f.smem_bytes = (uint32_t)smem;
     f.row0 = a->row0, f.col0 = a->col0;
+    f.blob_slot = (uint32_t)graphs_need;
     if (a->normalize) {
         f.norm_n = c->norm_n;
         f.norm_diag = reinterpret_cast<uint64_t>(c->norm_diag.ptr);

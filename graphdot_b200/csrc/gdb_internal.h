@@ -38,8 +38,9 @@ struct gdb_params_fixed_host {
     float q, eps, ftol, gtol;
     uint32_t smem_bytes, row0, col0, norm_n;
     uint64_t norm_diag, norm_ddiag;
+    uint32_t blob_slot, pad3;
 };
-static_assert(sizeof(gdb_params_fixed_host) == 152, "params layout");
+static_assert(sizeof(gdb_params_fixed_host) == 160, "params layout");
 
 // Records `msg` as the calling thread's last error and returns `code`.
 int gdb_fail(int code, const char *fmt, ...);

@@ -63,6 +63,36 @@ __device__ __forceinline__ gv_t gv_neg(gv_t a) { return -a; }
 __device__ __forceinline__ float gv_get(gv_t a, int) { return a; }
 #endif
 
+// ---- mbarrier / TMA bulk copy (cp.async.bulk) helpers --------------------------
+__device__ __forceinline__ unsigned gdb_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gdb_mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gdb_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gdb_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void gdb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void gdb_mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gdb_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gdb_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     gdb_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(gdb_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void gdb_mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "GDB_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra GDB_DONE_%=;\n\t"
+        "bra GDB_WAIT_%=;\n\t"
+        "GDB_DONE_%=:\n\t"
+        "}" ::"r"(gdb_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // Group sum of K <= 4 values at once (one barrier); fixed summation order.
 template<int K> __device__ __forceinline__ void gdb_group_sum_n(float (&v)[K], float *red, int &flip) {
 #pragma unroll
@@ -127,37 +157,58 @@ __device__ __forceinline__ gdb_small_graph gdb_small_view(const unsigned char *b
 extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
     mlgk_solve_small(const __grid_constant__ gdb_params P) {
     extern __shared__ __align__(16) unsigned char gdb_smem[];
-    __shared__ unsigned s_job[2];
+    __shared__ unsigned s_job[2][2];                     // (ja, jb) of the two pipeline slots
+    __shared__ __align__(8) unsigned long long s_bar[2]; // mbarriers: blob bytes have landed
     __shared__ float s_red[2 * 4 * (GDB_WARPS > 0 ? GDB_WARPS : 1)];
     int flip = 0;
     const gdb_params_fixed &F = P.f;
 
-    while (true) {
-        gdb_group_sync();  // previous job's shared memory is dead
-        if (threadIdx.x == 0) {
-            const unsigned long long job = atomicAdd(F.counters, 1ull);
-            unsigned a = 0xffffffffu, b = 0;
-            if (job < F.n_jobs) gdb_decode_job(F, job, a, b);
-            s_job[0] = a;
-            s_job[1] = b;
+    // Staging pipeline.  The dynamic shared memory starts with TWO blob buffers
+    // of F.blob_slot bytes.  Thread 0 claims the next job and issues one TMA
+    // bulk copy per graph blob (cp.async.bulk, global -> shared, completion on
+    // an mbarrier) into the idle buffer while the CTA solves the current pair,
+    // so the global-memory latency of staging is hidden behind the solve.
+    unsigned char *const blob_buf[2] = {gdb_smem, gdb_smem + F.blob_slot};
+    unsigned char *const work = gdb_smem + 2 * F.blob_slot;
+    if (threadIdx.x == 0) {
+        gdb_mbar_init(&s_bar[0], 1);
+        gdb_mbar_init(&s_bar[1], 1);
+        gdb_fence_mbar_init();
+    }
+    auto prefetch = [&](int slot) {  // thread 0 only
+        const unsigned long long job = atomicAdd(F.counters, 1ull);
+        unsigned a = 0xffffffffu, b = 0;
+        if (job < F.n_jobs) {
+            gdb_decode_job(F, job, a, b);
+            const gdb_graph_ref r1 = F.graphs[a], r2 = F.graphs[b];
+            const unsigned bytes = r1.bytes + (a == b ? 0u : r2.bytes);
+            gdb_fence_proxy_async();  // earlier generic reads of this buffer are done
+            gdb_mbar_expect_tx(&s_bar[slot], bytes);
+            gdb_bulk_g2s(blob_buf[slot], r1.blob, r1.bytes, &s_bar[slot]);
+            if (a != b) gdb_bulk_g2s(blob_buf[slot] + r1.bytes, r2.blob, r2.bytes, &s_bar[slot]);
         }
-        gdb_group_sync();
-        const unsigned ja = s_job[0], jb = s_job[1];
-        if (ja == 0xffffffffu) break;
-        const gdb_graph_ref ref1 = F.graphs[ja], ref2 = F.graphs[jb];
-        const bool same = (ja == jb);
+        s_job[slot][0] = a;
+        s_job[slot][1] = b;
+    };
+    gdb_group_sync();
+    if (threadIdx.x == 0) prefetch(0);
+    int slot = 0;
+    unsigned phase[2] = {0u, 0u};
 
-        // ---- stage both graphs ------------------------------------------------
-        gdb_copy16(gdb_smem, ref1.blob, ref1.bytes);
-        unsigned used = ref1.bytes;
-        const unsigned char *base2 = gdb_smem;
-        if (!same) {
-            gdb_copy16(gdb_smem + used, ref2.blob, ref2.bytes);
-            base2 = gdb_smem + used;
-            used += ref2.bytes;
-        }
-        gdb_group_sync();
-        const gdb_small_graph g1 = gdb_small_view(gdb_smem), g2 = gdb_small_view(base2);
+    while (true) {
+        gdb_group_sync();  // previous pair finished everywhere; s_job[slot] is visible
+        const unsigned ja = s_job[slot][0], jb = s_job[slot][1];
+        if (ja == 0xffffffffu) break;
+        if (threadIdx.x == 0) prefetch(slot ^ 1);
+        const bool same = (ja == jb);
+        gdb_mbar_wait(&s_bar[slot], phase[slot]);
+        phase[slot] ^= 1u;
+        unsigned char *const base1 = blob_buf[slot];
+        const unsigned char *base2 = same ? base1 : base1 + reinterpret_cast<const gdb_graph_hdr *>(base1)->blob_bytes;
+        slot ^= 1;
+        const unsigned used = 0;
+        unsigned char *const gdb_smem_work = work;
+        const gdb_small_graph g1 = gdb_small_view(base1), g2 = gdb_small_view(base2);
         const int n1 = g1.n, n2 = g2.n, N = n1 * n2, nnz1 = g1.nnz, nnz2 = g2.nnz;
         // W is indexed [k1][i2 * wd + k]: k1 = position of the G1 element in row
         // (CSR) order, (i2, k) = k-th neighbour of column i2 of G2, padded with
@@ -167,7 +218,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         const gdb_graph_hdr *h2 = reinterpret_cast<const gdb_graph_hdr *>(base2);
         const int wd = (int)((h2->max_degree + 3u) & ~3u);
         const int wstride = n2 * wd;  // floats per W row (multiple of 4)
-        float *W = reinterpret_cast<float *>(gdb_smem + used);
+        float *W = reinterpret_cast<float *>(gdb_smem_work + used);
         gv_t *pbuf = reinterpret_cast<gv_t *>(W + nnz1 * wstride);
 
         // ---- W = w1 w2 kE(e1, e2), once per pair: zero fill, then one balanced pass

@@ -87,6 +87,8 @@ struct gdb_params_fixed {
     // self-similarities and their Jacobians per graph, or null
     const float *norm_diag;
     const float *norm_ddiag;  // [m * norm_n + graph]
+    unsigned blob_slot;       // small kernel: bytes of one blob staging buffer (two graphs)
+    unsigned pad3;
 };
 
 struct gdb_params {
