@@ -38,6 +38,9 @@
 #define GDB_WPT 1
 #endif
 #define GDB_ADJ 4  // neighbours of a column kept in registers
+#ifndef GDB_TMA_STAGE
+#define GDB_TMA_STAGE 1  // 0: synchronous uint4 staging (tuning / A-B hook)
+#endif
 #ifdef GDB_SMALL_MINB  // tuning hook: -DGDB_SMALL_MINB=<resident CTAs per SM>
 #undef GDB_MIN_BLOCKS_SMALL
 #define GDB_MIN_BLOCKS_SMALL GDB_SMALL_MINB
@@ -180,12 +183,14 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         unsigned a = 0xffffffffu, b = 0;
         if (job < F.n_jobs) {
             gdb_decode_job(F, job, a, b);
+#if GDB_TMA_STAGE
             const gdb_graph_ref r1 = F.graphs[a], r2 = F.graphs[b];
             const unsigned bytes = r1.bytes + (a == b ? 0u : r2.bytes);
             gdb_fence_proxy_async();  // earlier generic reads of this buffer are done
             gdb_mbar_expect_tx(&s_bar[slot], bytes);
             gdb_bulk_g2s(blob_buf[slot], r1.blob, r1.bytes, &s_bar[slot]);
             if (a != b) gdb_bulk_g2s(blob_buf[slot] + r1.bytes, r2.blob, r2.bytes, &s_bar[slot]);
+#endif
         }
         s_job[slot][0] = a;
         s_job[slot][1] = b;
@@ -199,13 +204,31 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         gdb_group_sync();  // previous pair finished everywhere; s_job[slot] is visible
         const unsigned ja = s_job[slot][0], jb = s_job[slot][1];
         if (ja == 0xffffffffu) break;
+#if GDB_TMA_STAGE
         if (threadIdx.x == 0) prefetch(slot ^ 1);
+#endif
         const bool same = (ja == jb);
+#if GDB_TMA_STAGE
         gdb_mbar_wait(&s_bar[slot], phase[slot]);
         phase[slot] ^= 1u;
         unsigned char *const base1 = blob_buf[slot];
         const unsigned char *base2 = same ? base1 : base1 + reinterpret_cast<const gdb_graph_hdr *>(base1)->blob_bytes;
         slot ^= 1;
+#else
+        // synchronous staging (A/B reference for the TMA pipeline)
+        unsigned char *const base1 = blob_buf[0];
+        const unsigned char *base2 = base1;
+        {
+            const gdb_graph_ref r1 = F.graphs[ja], r2 = F.graphs[jb];
+            gdb_copy16(base1, r1.blob, r1.bytes);
+            if (!same) {
+                gdb_copy16(base1 + r1.bytes, r2.blob, r2.bytes);
+                base2 = base1 + r1.bytes;
+            }
+            gdb_group_sync();
+            if (threadIdx.x == 0) prefetch(0);  // claims the next job only
+        }
+#endif
         const unsigned used = 0;
         unsigned char *const gdb_smem_work = work;
         const gdb_small_graph g1 = gdb_small_view(base1), g2 = gdb_small_view(base2);
@@ -240,7 +263,11 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         const float Q = 1.0f / (1.0f - F.q), Q2 = Q * Q;
         // worker mapping: warp = tile row T1 of G1, lane (+ 32 s) = column i2 of G2,
         // so every loop over the elements of a row is warp-uniform
-        const int w_row0 = (int)(threadIdx.x >> 5) < g1.n_tile ? 8 * (int)(threadIdx.x >> 5) : n1;
+        // rows of G1 are dealt to the ceil(n1 / 8) working warps in equal blocks of
+        // at most 8 (balanced: 20 rows on 3 warps = 7 + 7 + 6, not 8 + 8 + 4)
+        const int w_rows = (n1 + g1.n_tile - 1) / g1.n_tile;
+        const int w_row0 = min((int)(threadIdx.x >> 5) * w_rows, n1);
+        const int w_row1 = min(w_row0 + w_rows, n1);  // one past this warp's last row
         int w_col[GDB_WPT];                             // column; >= n2: idle slot
         unsigned w_woff[GDB_WPT];                       // byte offset of the column's slots in a W row
         unsigned w_xoff[GDB_WPT][GDB_ADJ];              // byte offsets of the neighbours in a p row
@@ -276,7 +303,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
                     xv[s][r] = gv_make(0.f, 0.f);
                     rv[s][r] = gv_make(0.f, 0.f);
                     apv[s][r] = gv_make(0.f, 0.f);
-                    if (live && i1 < n1) {
+                    if (live && i1 < w_row1) {
                         const node_t &u1 = g1.node[i1];
                         const float dx = g1.degree[i1] * d2;
                         const float d = __fdividef(dx, P.node_kernel(u1, u2));
@@ -322,7 +349,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const int i1 = w_row0 + r;
-                if (i1 < n1) {  // warp-uniform
+                if (i1 < w_row1) {  // warp-uniform
                     gv_t acc[GDB_WPT];
 #pragma unroll
                     for (int s = 0; s < GDB_WPT; ++s) acc[s] = gv_make(0.f, 0.f);
@@ -373,7 +400,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     const int i1 = w_row0 + r;
-                    if (i1 < n1 && w_col[s] < n2) {
+                    if (i1 < w_row1 && w_col[s] < n2) {
                         xv[s][r] = gv_fma2(al, pbuf[i1 * n2 + w_col[s]], xv[s][r]);
                         const gv_t ri = gv_fma2(gv_neg(al), apv[s][r], rv[s][r]);
                         rv[s][r] = ri;
@@ -402,7 +429,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     const int i1 = w_row0 + r;
-                    if (i1 < n1 && w_col[s] < n2) {
+                    if (i1 < w_row1 && w_col[s] < n2) {
                         gv_t *pp = pbuf + i1 * n2 + w_col[s];
                         *pp = gv_fma2(be, *pp, gv_scale(__fdividef(1.0f, diag[s][r]), rv[s][r]));
                     }
@@ -431,7 +458,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const int i1 = w_row0 + r;
-                if (i1 < n1 && w_col[s] < n2) xs[i1 * n2 + w_col[s]] = xv[s][r];
+                if (i1 < w_row1 && w_col[s] < n2) xs[i1 * n2 + w_col[s]] = xv[s][r];
             }
         }
         gdb_group_sync();
@@ -487,7 +514,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     const int i1 = w_row0 + r;
-                    if (i1 < n1 && w_col[s] < n2) {
+                    if (i1 < w_row1 && w_col[s] < n2) {
                         const node_t &u1 = g1.node[i1];
                         const float p1 = P.p_start(u1);
                         const float xi = gv_get(xv[s][r], 0);
