@@ -171,7 +171,8 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
     // bulk copy per graph blob (cp.async.bulk, global -> shared, completion on
     // an mbarrier) into the idle buffer while the CTA solves the current pair,
     // so the global-memory latency of staging is hidden behind the solve.
-    unsigned char *const blob_buf[2] = {gdb_smem, gdb_smem + F.blob_slot};
+    // (buffers are addressed as gdb_smem + slot * blob_slot so that the compiler keeps
+    // the shared address space and emits LDS, not generic LD)
     unsigned char *const work = gdb_smem + 2 * F.blob_slot;
     if (threadIdx.x == 0) {
         gdb_mbar_init(&s_bar[0], 1);
@@ -188,8 +189,9 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             const unsigned bytes = r1.bytes + (a == b ? 0u : r2.bytes);
             gdb_fence_proxy_async();  // earlier generic reads of this buffer are done
             gdb_mbar_expect_tx(&s_bar[slot], bytes);
-            gdb_bulk_g2s(blob_buf[slot], r1.blob, r1.bytes, &s_bar[slot]);
-            if (a != b) gdb_bulk_g2s(blob_buf[slot] + r1.bytes, r2.blob, r2.bytes, &s_bar[slot]);
+            unsigned char *const dst = gdb_smem + slot * F.blob_slot;
+            gdb_bulk_g2s(dst, r1.blob, r1.bytes, &s_bar[slot]);
+            if (a != b) gdb_bulk_g2s(dst + r1.bytes, r2.blob, r2.bytes, &s_bar[slot]);
 #endif
         }
         s_job[slot][0] = a;
@@ -211,12 +213,12 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #if GDB_TMA_STAGE
         gdb_mbar_wait(&s_bar[slot], phase[slot]);
         phase[slot] ^= 1u;
-        unsigned char *const base1 = blob_buf[slot];
+        unsigned char *const base1 = gdb_smem + slot * F.blob_slot;
         const unsigned char *base2 = same ? base1 : base1 + reinterpret_cast<const gdb_graph_hdr *>(base1)->blob_bytes;
         slot ^= 1;
 #else
         // synchronous staging (A/B reference for the TMA pipeline)
-        unsigned char *const base1 = blob_buf[0];
+        unsigned char *const base1 = gdb_smem;
         const unsigned char *base2 = base1;
         {
             const gdb_graph_ref r1 = F.graphs[ja], r2 = F.graphs[jb];
