@@ -390,6 +390,12 @@ def run_gpu(args, rank, world, local_rank):
     kernel_s = kernel_ms * 1e-3 / args.steps / world   # avg per rank & step
     achieved = fl['total'] / world / kernel_s / 1e12
     pinfo = backend.program_info(worker.prog)
+    traffic = None      # DRAM bytes of one launch from the committed ncu capture
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))
+        traffic = tr['dram_bytes_per_launch']
+    except (OSError, KeyError, ValueError):
+        pass
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup,
@@ -406,7 +412,11 @@ def run_gpu(args, rank, world, local_rank):
         'roofline': {
             'bound': 'fp32', 'achieved': achieved, 'peak': peak_tflops,
             'unit': 'TFLOP/s', 'frac': achieved / peak_tflops,
-            'traffic': None,
+            'traffic': traffic,
+            'traffic_note': 'dram read+write bytes of ONE launch (row-block tile '
+                            'of 125 984 pairs) from profiles/r1_small_final_ncu_'
+                            'summary.md; the kernel is on-chip bound, the blobs '
+                            'stream in once',
             'peak_source': f'{info.sm_count} SMs x 128 lanes x 2 x '
                            f'{sm_mhz:.0f} MHz (measured sm_max_mhz)',
             'matvec_tflops': fl['matvec'] / world / kernel_s / 1e12,

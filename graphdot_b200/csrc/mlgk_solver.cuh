@@ -238,7 +238,7 @@ __device__ __forceinline__ float gdb_matvec(const gdb_params &P, const gdb_graph
 // evaluated on the fly (the cached-W variant lives in mlgk_small.cuh).
 __device__ __forceinline__ float gdb_matvec_csr(const gdb_params &P, const gdb_graph_view &g1,
                                                 const gdb_graph_view &g2, const float *__restrict__ diag,
-                                                const float *in, float *__restrict__ out) {
+                                                const float *__restrict__ in, float *__restrict__ out) {
     const unsigned n2 = (unsigned)g2.n, N = (unsigned)(g1.n * g2.n);
     const float inv_n2 = __frcp_rn((float)n2);
     float dot = 0.f;
@@ -271,13 +271,41 @@ __device__ __forceinline__ float gdb_matvec_csr(const gdb_params &P, const gdb_g
     return dot;
 }
 
+// Sum of two values over the group with one barrier.
+__device__ __forceinline__ void gdb_group_sum2(float &a, float &b, float *red, int &flip) {
+    a = gdb_warp_sum(a);
+    b = gdb_warp_sum(b);
+#if GDB_BLOCK > 32
+    float *buf = red + flip * GDB_WARPS;  // red holds 2 x 2 x GDB_WARPS floats
+    flip ^= 1;
+    if ((threadIdx.x & 31) == 0) {
+        buf[threadIdx.x >> 5] = a;
+        buf[2 * GDB_WARPS + (threadIdx.x >> 5)] = b;
+    }
+    __syncthreads();
+    float ta = 0.f, tb = 0.f;
+#pragma unroll
+    for (int w = 0; w < GDB_WARPS; ++w) {
+        ta += buf[w];
+        tb += buf[2 * GDB_WARPS + w];
+    }
+    a = ta;
+    b = tb;
+#endif
+}
+
 // Jacobi-PCG for A x = rhs with x0 = 0.  On entry r = rhs; on exit x holds the
-// solution; r, p, Ap are clobbered.  Returns the number of iterations.
+// solution; r, p, Ap are clobbered.  Returns the number of iterations.  The
+// vectors do not alias (__restrict__) and the streaming loops are unrolled by
+// four with all loads issued before the first store, so that a thread keeps
+// several independent global/L2 requests in flight (large pairs stream their
+// vectors from L2/HBM).
 __device__ __forceinline__ int gdb_pcg(const gdb_params &P, const gdb_graph_view &g1, const gdb_graph_view &g2,
-                                       const float *__restrict__ diag, float *x, float *r, float *p, float *Ap,
-                                       float tol, float *red, int &flip) {
+                                       const float *__restrict__ diag, float *__restrict__ x, float *__restrict__ r,
+                                       float *__restrict__ p, float *__restrict__ Ap, float tol, float *red, int &flip) {
     const int N = g1.n * g2.n;
     float rho = 0.f;
+#pragma unroll 4
     for (int i = threadIdx.x; i < N; i += GDB_BLOCK) {
         const float ri = r[i];
         const float z = __fdividef(ri, diag[i]);
@@ -296,20 +324,49 @@ __device__ __forceinline__ int gdb_pcg(const gdb_params &P, const gdb_graph_view
         ++k;
         const float alpha = __fdividef(rho, pAp);
         float rr = 0.f, rz = 0.f;
-        for (int i = threadIdx.x; i < N; i += GDB_BLOCK) {
+        int i = threadIdx.x;
+        for (; i + 3 * GDB_BLOCK < N; i += 4 * GDB_BLOCK) {
+            float pv[4], av[4], xv[4], rv[4], dv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                pv[u] = p[i + u * GDB_BLOCK];
+                av[u] = Ap[i + u * GDB_BLOCK];
+                xv[u] = x[i + u * GDB_BLOCK];
+                rv[u] = r[i + u * GDB_BLOCK];
+                dv[u] = diag[i + u * GDB_BLOCK];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                x[i + u * GDB_BLOCK] = fmaf(alpha, pv[u], xv[u]);
+                const float ri = fmaf(-alpha, av[u], rv[u]);
+                r[i + u * GDB_BLOCK] = ri;
+                rr = fmaf(ri, ri, rr);
+                rz = fmaf(ri, __fdividef(ri, dv[u]), rz);
+            }
+        }
+        for (; i < N; i += GDB_BLOCK) {
             x[i] = fmaf(alpha, p[i], x[i]);
             const float ri = fmaf(-alpha, Ap[i], r[i]);
             r[i] = ri;
             rr = fmaf(ri, ri, rr);
             rz = fmaf(ri, __fdividef(ri, diag[i]), rz);
         }
-        rr = gdb_group_sum(rr, red, flip);
-        rz = gdb_group_sum(rz, red, flip);
+        gdb_group_sum2(rr, rz, red, flip);
         if (sqrtf(rr) < thresh) break;
         const float beta = __fdividef(rz, rho);
-        for (int i = threadIdx.x; i < N; i += GDB_BLOCK) {
-            p[i] = fmaf(beta, p[i], __fdividef(r[i], diag[i]));
+        i = threadIdx.x;
+        for (; i + 3 * GDB_BLOCK < N; i += 4 * GDB_BLOCK) {
+            float pv[4], rv[4], dv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                pv[u] = p[i + u * GDB_BLOCK];
+                rv[u] = r[i + u * GDB_BLOCK];
+                dv[u] = diag[i + u * GDB_BLOCK];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[i + u * GDB_BLOCK] = fmaf(beta, pv[u], __fdividef(rv[u], dv[u]));
         }
+        for (; i < N; i += GDB_BLOCK) p[i] = fmaf(beta, p[i], __fdividef(r[i], diag[i]));
         rho = rz;
         gdb_group_sync();  // p complete before the next matvec
     }
@@ -350,7 +407,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
     mlgk_solve(const __grid_constant__ gdb_params P) {
     extern __shared__ __align__(16) unsigned char gdb_smem[];
     __shared__ unsigned long long s_job;
-    __shared__ float s_red[2 * (GDB_WARPS > 0 ? GDB_WARPS : 1)];
+    __shared__ float s_red[4 * (GDB_WARPS > 0 ? GDB_WARPS : 1)];
     int flip = 0;
     const gdb_params_fixed &F = P.f;
 #if GDB_GRADIENT
