@@ -202,13 +202,14 @@ CASES = ['unlabeled', 'labeled', 'weighted', 'vario-features', 'molecular']
     dict(symmetric=True), dict(symmetric=True, eval_gradient=True),
     dict(diagonal=True, nodal=True), dict(nodal=True, lmin=1),
     dict(diagonal=True, nodal='block'), dict(diagonal=True, eval_gradient=True,
-                                             lmin=1)])
+                                             lmin=1),
+    dict(symmetric=True, nodal=True, eval_gradient=True)])
 def test_nvrtc_compiles_fixture_kernels_for_sm100a(mlgk_golden, name, traits):
     lib = native.load()
     G = golden_graphs(mlgk_golden['cases'][name])
     knode, kedge = golden_kernels(name)
     nl, el, weighted = B200Backend._layouts(G[0])
-    for block in (32, 128):
+    for block in ((96, 1),):
         d, keep, _ = B200Backend._desc(
             nl, el, weighted, knode, kedge, Uniform(1.0),
             MarginalizedGraphKernel.traits(**traits), block, ())
