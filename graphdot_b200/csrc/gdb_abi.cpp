@@ -224,7 +224,7 @@ struct gdb_program_s {
     std::string source, log;
     gdb_program_info info{};
     uint32_t theta_size[3] = {};
-    int eval_gradient = 0, nodal = 0, wpt = 1;
+    int eval_gradient = 0, nodal = 0, wpt = 1, rpw = 8;
     int refcount = 1;
 };
 
@@ -249,6 +249,8 @@ static int pick_block(const gdb_program_desc *d) {
 
 static int pick_wpt(const gdb_program_desc *d) { return d->workers_per_thread <= 0 ? 1 : d->workers_per_thread; }
 
+static int pick_rpw(const gdb_program_desc *d) { return d->rows_per_warp <= 0 ? 8 : d->rows_per_warp; }
+
 static int render(const gdb_program_desc *d, std::string &src) {
     if (!d || !d->node_decl || !d->edge_decl || !d->node_kernel.expr || !d->edge_kernel.expr || !d->p_start.expr)
         return gdb_fail(GDB_ERR_INVALID, "gdb_program_desc: missing source strings");
@@ -256,13 +258,25 @@ static int render(const gdb_program_desc *d, std::string &src) {
     if (block < 0) return gdb_fail(GDB_ERR_INVALID, "block_size must be a multiple of 32 up to 1024");
     if (d->nodal < 0 || d->nodal > 2 || d->lmin < 0 || d->lmin > 1) return gdb_fail(GDB_ERR_INVALID, "invalid traits");
     if (pick_wpt(d) > 4) return gdb_fail(GDB_ERR_INVALID, "workers_per_thread must be 1..4");
+    if (pick_rpw(d) > 8) return gdb_fail(GDB_ERR_INVALID, "rows_per_warp must be 1..8");
     std::ostringstream o;
     o << gdb_embedded_prelude << "\n";
     o << "// ---- generated splice ----\n";
     o << "#define GDB_BLOCK " << block << "\n";
     o << "#define GDB_MIN_BLOCKS " << std::max(1, std::min(16, 1024 / block)) << "\n";
-    o << "#define GDB_MIN_BLOCKS_SMALL " << std::max(1, 512 / block) << "\n";
+    {
+        // small-pair kernel: the per-thread state is rows_per_warp x (x, r, Ap, diag)
+        // [float2 with gradients] + ~50 registers of indices and loop state.  With
+        // at most 6 rows per warp 96 registers leave ptxas room to keep the five
+        // loads of a matvec step in flight together, so ask for 640 threads per SM
+        // instead of 512.  Measured on the C3 workload (pairs/s): block 96 / 8 rows /
+        // 128 regs 12.4 M; 128 / 6 / 80 regs 15.7 M; 128 / 6 / 96 regs 16.7 M -- the
+        // kernel is latency bound, more and lighter warps win.
+        const int threads = (pick_wpt(d) == 1 && pick_rpw(d) <= 6) ? 640 : 512;
+        o << "#define GDB_MIN_BLOCKS_SMALL " << std::max(1, threads / block) << "\n";
+    }
     o << "#define GDB_WPT " << pick_wpt(d) << "\n";
+    o << "#define GDB_RPW " << pick_rpw(d) << "\n";
     o << "#define GDB_WEIGHTED " << (d->weighted ? 1 : 0) << "\n";
     o << "#define GDB_DIAGONAL " << (d->diagonal ? 1 : 0) << "\n";
     o << "#define GDB_SYMMETRIC " << (d->symmetric ? 1 : 0) << "\n";
@@ -372,6 +386,7 @@ extern "C" int gdb_program_create(gdb_context_t c, const gdb_program_desc *d, gd
     p->eval_gradient = d->eval_gradient;
     p->nodal = d->nodal;
     p->wpt = pick_wpt(d);
+    p->rpw = pick_rpw(d);
     p->theta_size[0] = d->node_kernel.theta_size;
     p->theta_size[1] = d->edge_kernel.theta_size;
     p->theta_size[2] = d->p_start.theta_size;
@@ -636,7 +651,7 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
         const uint64_t small_need = 2 * graphs_need + wmax * 4 + nrhs * maxNpad * 4;
         const uint64_t small_cap = std::min<uint64_t>(cap, (uint64_t)c->prop.sharedMemPerBlockOptin - p->small_static_smem);
         // one warp per tile row of G1, lanes (x workers per thread) over the columns of G2
-        const bool mapped = (uint64_t)((gs->max_node[0] + 7) / 8) * 32 <= (uint64_t)block &&
+        const bool mapped = (uint64_t)gs->max_node[0] <= (uint64_t)p->rpw * (uint64_t)(block / 32) &&
                             (uint64_t)gs->max_node[0] <= 32ull * p->wpt;
         // nodal Jacobians (forward sensitivities) are implemented by the general kernel only
         const bool nodal_grad = p->eval_gradient && p->nodal != GDB_NODAL_NONE;

@@ -24,7 +24,7 @@ struct Sizes {
     uint32_t edge_size, label_off;
     uint32_t nnz, n_octile, n_tile;
     uint64_t off_degree, off_node, off_octile, off_tilerow, off_edge, off_pool, total;
-    uint64_t off_emeta, off_rowptr, off_rowadj, off_tileelem, off_ellslot;
+    uint64_t off_emeta, off_rowptr, off_rowadj, off_tileelem, off_ellslot, off_lanemap;
 };
 
 struct Nz {
@@ -84,7 +84,8 @@ void plan(const gdb_layout *L, const gdb_graph_src *g, const std::vector<Nz> &nz
     s.off_rowadj = s.off_rowptr + pad16(4ull * (g->n_node + 1));
     s.off_tileelem = s.off_rowadj + pad16(4ull * s.nnz);
     s.off_ellslot = s.off_tileelem + pad16(4ull * (s.n_tile + 1));
-    s.off_pool = s.off_ellslot + pad16(4ull * s.nnz);
+    s.off_lanemap = s.off_ellslot + pad16(4ull * s.nnz);
+    s.off_pool = s.off_lanemap + pad16(4ull * g->n_node);
     s.total = s.off_pool + pad16(g->pool_bytes);
 }
 
@@ -194,10 +195,26 @@ extern "C" int gdb_graph_pack(const gdb_layout *L, const gdb_graph_src *g, void 
         for (uint32_t i = 0; i < g->n_node; ++i) fill[i + 1] += fill[i];
         for (uint32_t i = 0; i <= g->n_node; ++i) rowptr[i] = fill[i];
         {
+            // lane map of the small-pair kernel: nodes in order of decreasing degree
+            // (stable), so that the lanes that own a 2nd, 3rd, 4th ... neighbour slot
+            // are the LOW lanes of a warp and the gathers of the higher slots touch
+            // one half-warp only.  lanemap[p] & 0xffff = node at position p,
+            // lanemap[i] >> 16 = position of node i; ellslot[k] = slot of CSR
+            // element k in a W row laid out by position.
             uint32_t *ellslot = reinterpret_cast<uint32_t *>(base + s.off_ellslot);
+            uint32_t *lanemap = reinterpret_cast<uint32_t *>(base + s.off_lanemap);
+            h->off_lanemap = (uint32_t)s.off_lanemap;
             const uint32_t wd = (max_degree + 3u) & ~3u;
+            std::vector<uint32_t> order(g->n_node);
+            for (uint32_t i = 0; i < g->n_node; ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+                return rowptr[a + 1] - rowptr[a] > rowptr[b + 1] - rowptr[b];
+            });
+            for (uint32_t pos = 0; pos < g->n_node; ++pos) lanemap[pos] = order[pos];
+            for (uint32_t pos = 0; pos < g->n_node; ++pos) lanemap[order[pos]] |= pos << 16;
             for (uint32_t i = 0; i < g->n_node; ++i)
-                for (uint32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) ellslot[k] = i * wd + (k - rowptr[i]);
+                for (uint32_t k = rowptr[i]; k < rowptr[i + 1]; ++k)
+                    ellslot[k] = (lanemap[i] >> 16) * wd + (k - rowptr[i]);
         }
         // nz is sorted by (tile row, tile col, row, col): filling in this order
         // leaves every row's neighbours sorted by column

@@ -13,14 +13,21 @@
 //    extra zero column so that padded adjacency slots need no predicate.  The
 //    reference re-evaluates the edge microkernel for every product in every CG
 //    iteration (marginalized_kernel.h:299-300, :346).
-//  * workers = (tile row T1 of G1: 8 rows) x (column i2 of G2), one or a few
-//    per thread.  A worker owns the 8 product-graph elements (rows of T1,
-//    column i2): their x, r, A p and diagonal live in REGISTERS for the whole
-//    solve; only the search direction p, which neighbours gather, is in shared
-//    memory.  The first GDB_ADJ neighbours of column i2 are held in registers
-//    as byte offsets, so one matvec product is
-//        LDS W[row + off_k], LDS p[row' + off'_k], FMA (x2 with gradients).
+//  * workers = (block of <= GDB_RPW rows of G1, dealt evenly to the warps) x
+//    (column of G2 = lane), one or a few per thread.  A worker owns the
+//    product-graph elements (its rows, its column): their x, r, A p and diagonal
+//    live in REGISTERS for the whole solve; only the search direction p, which
+//    neighbours gather, is in shared memory.  The first GDB_ADJ neighbours of
+//    the column are held in registers as byte offsets, so one matvec product is
+//        LDS.128 W[row + off], 4 x LDS p[row' + off'_k], FMA (x2 with gradients).
 //    No atomics, fixed summation order => bit-reproducible.
+//  * lanes follow the packer's degree-sorted lane map (gdb_pack.cpp): lane l
+//    owns the node with the l-th largest degree, p and W are laid out by that
+//    position.  The gathers of neighbour slot k are predicated on degree > k,
+//    so slots 1..3 touch only the low lanes: one shared-memory wavefront
+//    instead of two per 64-bit gather for typical molecular graphs.
+//  * K and its Jacobian are symmetric in the two graphs, so per pair the
+//    larger graph provides the columns and the smaller one the rows.
 //  * with gradients the value system (rhs Dx) and the adjoint system (rhs
 //    p1 (x) p2) are solved together on float2 data: one W load and one 64-bit
 //    load feed two FMAs.  Each system has its own CG scalars and convergence
@@ -34,10 +41,21 @@
 // GDB_BLOCK * GDB_WPT >= max tile rows * max nodes of the graph set).
 #pragma once
 
+#ifndef GDB_RPW
+#define GDB_RPW 8  // rows of G1 per warp (register arrays are sized by it)
+#endif
 #ifndef GDB_WPT
 #define GDB_WPT 1
 #endif
 #define GDB_ADJ 4  // neighbours of a column kept in registers
+#ifndef GDB_PRED_SLOTS
+#define GDB_PRED_SLOTS 1  // 0: gather all GDB_ADJ slots of every live column (A-B hook)
+#endif
+#if GDB_PRED_SLOTS
+#define GDB_SLOT_ON(k) (deg > (k))
+#else
+#define GDB_SLOT_ON(k) (GDB_LIVE(s))
+#endif
 #ifndef GDB_TMA_STAGE
 #define GDB_TMA_STAGE 1  // 0: synchronous uint4 staging (tuning / A-B hook)
 #endif
@@ -133,11 +151,37 @@ __device__ __forceinline__ void gdb_divmod(unsigned a, unsigned d, float inv_d, 
     }
 }
 
+// Predicated shared-memory loads by 32-bit shared-window address.  A lane whose
+// predicate is off issues no request (the wavefront count of a gather follows
+// the ACTIVE lanes) and gets zeros.  Written in PTX so that the compiler keeps
+// the five loads of a matvec step back to back instead of branching around
+// each one.
+__device__ __forceinline__ gv_t gdb_lds_gv(unsigned addr, bool on) {
+#if GDB_GRADIENT
+    float x = 0.f, y = 0.f;
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %3, 0; @q ld.shared.v2.f32 {%0, %1}, [%2]; }"
+                 : "+f"(x), "+f"(y)
+                 : "r"(addr), "r"((unsigned)on));
+    return make_float2(x, y);
+#else
+    float x = 0.f;
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q ld.shared.f32 %0, [%1]; }" : "+f"(x) : "r"(addr), "r"((unsigned)on));
+    return x;
+#endif
+}
+__device__ __forceinline__ float4 gdb_lds_f4(unsigned addr, bool on) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q ld.shared.v4.f32 {%0, %1, %2, %3}, [%4]; }"
+                 : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+                 : "r"(addr), "r"((unsigned)on));
+    return v;
+}
+
 struct gdb_small_graph {
     const float *degree;
     const node_t *node;
     const edge_t *edge;
-    const unsigned *emeta, *rowptr, *rowadj, *ellslot;
+    const unsigned *emeta, *rowptr, *rowadj, *ellslot, *lanemap;
     int n, nnz, n_tile;
 };
 
@@ -151,6 +195,7 @@ __device__ __forceinline__ gdb_small_graph gdb_small_view(const unsigned char *b
     v.rowptr = reinterpret_cast<const unsigned *>(base + h->off_rowptr);
     v.rowadj = reinterpret_cast<const unsigned *>(base + h->off_rowadj);
     v.ellslot = reinterpret_cast<const unsigned *>(base + h->off_ellslot);
+    v.lanemap = reinterpret_cast<const unsigned *>(base + h->off_lanemap);
     v.n = h->n_node;
     v.nnz = h->nnz;
     v.n_tile = h->n_tile;
@@ -233,14 +278,26 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #endif
         const unsigned used = 0;
         unsigned char *const gdb_smem_work = work;
+#if GDB_NODAL == 0 && !defined(GDB_NO_ROLE_SWAP)
+        // K and its Jacobian are symmetric in the two graphs, so the roles are chosen
+        // per pair: the LARGER graph provides the columns (lanes: better lane
+        // utilisation), the smaller one the rows (fewer rows per warp).  The output
+        // position still follows (ja, jb).
+        const bool swap_roles = reinterpret_cast<const gdb_graph_hdr *>(base1)->n_node >
+                                reinterpret_cast<const gdb_graph_hdr *>(base2)->n_node;
+        const gdb_small_graph g1 = gdb_small_view(swap_roles ? base2 : base1);
+        const gdb_small_graph g2 = gdb_small_view(swap_roles ? base1 : base2);
+        const gdb_graph_hdr *h2 = reinterpret_cast<const gdb_graph_hdr *>(swap_roles ? base1 : base2);
+#else
         const gdb_small_graph g1 = gdb_small_view(base1), g2 = gdb_small_view(base2);
+        const gdb_graph_hdr *h2 = reinterpret_cast<const gdb_graph_hdr *>(base2);
+#endif
         const int n1 = g1.n, n2 = g2.n, N = n1 * n2, nnz1 = g1.nnz, nnz2 = g2.nnz;
-        // W is indexed [k1][i2 * wd + k]: k1 = position of the G1 element in row
-        // (CSR) order, (i2, k) = k-th neighbour of column i2 of G2, padded with
+        // W is indexed [k1][pos2 * wd + k]: k1 = position of the G1 element in row
+        // (CSR) order, (pos2, k) = k-th neighbour of the column at lane position pos2, padded with
         // zeros to wd = 4 * ceil(max degree / 4) slots per column.  A worker's
         // four slots are one aligned 128-bit load, and W rows are visited with a
         // constant stride.
-        const gdb_graph_hdr *h2 = reinterpret_cast<const gdb_graph_hdr *>(base2);
         const int wd = (int)((h2->max_degree + 3u) & ~3u);
         const int wstride = n2 * wd;  // floats per W row (multiple of 4)
         float *W = reinterpret_cast<float *>(gdb_smem_work + used);
@@ -265,41 +322,44 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         const float Q = 1.0f / (1.0f - F.q), Q2 = Q * Q;
         // worker mapping: warp = tile row T1 of G1, lane (+ 32 s) = column i2 of G2,
         // so every loop over the elements of a row is warp-uniform
-        // rows of G1 are dealt to the ceil(n1 / 8) working warps in equal blocks of
-        // at most 8 (balanced: 20 rows on 3 warps = 7 + 7 + 6, not 8 + 8 + 4)
-        const int w_rows = (n1 + g1.n_tile - 1) / g1.n_tile;
+        // rows of G1 are dealt to ALL warps of the CTA in equal blocks of at most 8
+        // (balanced: 20 rows on 3 warps = 7 + 7 + 6; 16 rows = 6 + 6 + 4, not 8 + 8 + 0)
+        const int w_rows = (n1 + GDB_WARPS - 1) / GDB_WARPS;
         const int w_row0 = min((int)(threadIdx.x >> 5) * w_rows, n1);
         const int w_row1 = min(w_row0 + w_rows, n1);  // one past this warp's last row
-        int w_col[GDB_WPT];                             // column; >= n2: idle slot
+        // lane position pos = lane + 32 s owns column lanemap[pos] of G2; p and W are laid
+        // out by position, the graph data by node
+        const int lane = (int)(threadIdx.x & 31);
+#define GDB_POS(s) (lane + 32 * (s))
+#define GDB_LIVE(s) (GDB_POS(s) < n2)
+        unsigned w_deg[GDB_WPT];                        // degree of the column; 0 also for idle slots
         unsigned w_woff[GDB_WPT];                       // byte offset of the column's slots in a W row
         unsigned w_xoff[GDB_WPT][GDB_ADJ];              // byte offsets of the neighbours in a p row
-        unsigned w_kbeg[GDB_WPT], w_kend[GDB_WPT];      // row of the column in G2's row index
-        float diag[GDB_WPT][8];
-        gv_t xv[GDB_WPT][8], rv[GDB_WPT][8], apv[GDB_WPT][8];
+        float diag[GDB_WPT][GDB_RPW];
+        gv_t xv[GDB_WPT][GDB_RPW], rv[GDB_WPT][GDB_RPW], apv[GDB_WPT][GDB_RPW];
         float rho[GV_N];
 #pragma unroll
         for (int k = 0; k < GV_N; ++k) rho[k] = 0.f;
         {
 #pragma unroll
             for (int s = 0; s < GDB_WPT; ++s) {
-                const int col = (int)(threadIdx.x & 31) + 32 * s;
-                const bool live = col < n2 && w_row0 < n1;
-                const int i2 = live ? col : 0;
-                w_col[s] = live ? col : n2;
+                const int pos = GDB_POS(s);
+                const bool live = GDB_LIVE(s);
+                const int i2 = live ? (int)(g2.lanemap[pos] & 0xffffu) : 0;
                 const unsigned kbeg = g2.rowptr[i2], kend = g2.rowptr[i2 + 1];
-                w_woff[s] = (unsigned)(i2 * wd) * 4u;
+                w_deg[s] = live ? kend - kbeg : 0u;
+                w_woff[s] = (unsigned)(pos * wd) * 4u;
 #pragma unroll
                 for (int k = 0; k < GDB_ADJ; ++k)
-                    w_xoff[s][k] = (kbeg + k < kend) ? (g2.rowadj[kbeg + k] & 0xffffu) * (unsigned)sizeof(gv_t) : 0u;
-                w_kbeg[s] = kbeg;
-                w_kend[s] = kend;
+                    w_xoff[s][k] =
+                        (kbeg + k < kend) ? (g2.lanemap[g2.rowadj[kbeg + k] & 0xffffu] >> 16) * (unsigned)sizeof(gv_t) : 0u;
                 const node_t &u2 = g2.node[i2];
                 const float d2 = g2.degree[i2] * Q2;
 #if GDB_GRADIENT
                 const float p2 = P.p_start(u2);
 #endif
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
+                for (int r = 0; r < GDB_RPW; ++r) {
                     const int i1 = w_row0 + r;
                     diag[s][r] = 1.f;
                     xv[s][r] = gv_make(0.f, 0.f);
@@ -317,7 +377,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #endif
                         const gv_t z = gv_scale(__fdividef(1.0f, d), ri);
                         rv[s][r] = ri;
-                        pbuf[i1 * n2 + (int)i2] = z;
+                        pbuf[i1 * n2 + pos] = z;
 #pragma unroll
                         for (int k = 0; k < GV_N; ++k) rho[k] = fmaf(gv_get(ri, k), gv_get(z, k), rho[k]);
                     }
@@ -333,8 +393,8 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll
         for (int k = 0; k < GV_N; ++k) active[k] = rho[k] != 0.f;
         int iters = 0;  // summed over the systems that were still active
-        const unsigned char *Wb = reinterpret_cast<const unsigned char *>(W);
-        const unsigned char *pb = reinterpret_cast<const unsigned char *>(pbuf);
+        const unsigned W_sa = (unsigned)__cvta_generic_to_shared(W);     // shared-window addresses
+        const unsigned p_sa = (unsigned)__cvta_generic_to_shared(pbuf);
         const unsigned prow_bytes = (unsigned)n2 * (unsigned)sizeof(gv_t);
         for (int it = 0; it < N; ++it) {
             bool any = false;
@@ -349,7 +409,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll
             for (int k = 0; k < GV_N; ++k) pAp[k] = 0.f;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
+            for (int r = 0; r < GDB_RPW; ++r) {
                 const int i1 = w_row0 + r;
                 if (i1 < w_row1) {  // warp-uniform
                     gv_t acc[GDB_WPT];
@@ -357,27 +417,36 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
                     for (int s = 0; s < GDB_WPT; ++s) acc[s] = gv_make(0.f, 0.f);
                     const unsigned k1end = g1.rowptr[i1 + 1];
                     for (unsigned k1 = g1.rowptr[i1]; k1 < k1end; ++k1) {  // warp-uniform trip count
-                        const unsigned char *Wrow = Wb + k1 * (unsigned)(wstride * 4);
-                        const unsigned char *prow = pb + (g1.rowadj[k1] & 0xffffu) * prow_bytes;
+                        const unsigned Wrow = W_sa + k1 * (unsigned)(wstride * 4);
+                        const unsigned prow = p_sa + (g1.rowadj[k1] & 0xffffu) * prow_bytes;
 #pragma unroll
                         for (int s = 0; s < GDB_WPT; ++s) {
-                            if (w_col[s] < n2) {
-                                const float4 w4 = *reinterpret_cast<const float4 *>(Wrow + w_woff[s]);
-                                acc[s] = gv_fma(w4.x, *reinterpret_cast<const gv_t *>(prow + w_xoff[s][0]), acc[s]);
-                                acc[s] = gv_fma(w4.y, *reinterpret_cast<const gv_t *>(prow + w_xoff[s][1]), acc[s]);
-                                acc[s] = gv_fma(w4.z, *reinterpret_cast<const gv_t *>(prow + w_xoff[s][2]), acc[s]);
-                                acc[s] = gv_fma(w4.w, *reinterpret_cast<const gv_t *>(prow + w_xoff[s][3]), acc[s]);
-                                for (unsigned k = w_kbeg[s] + GDB_ADJ; k < w_kend[s]; ++k) {  // degree > GDB_ADJ
-                                    const float w = *reinterpret_cast<const float *>(Wrow + w_woff[s] + (k - w_kbeg[s]) * 4u);
-                                    acc[s] = gv_fma(w, *reinterpret_cast<const gv_t *>(prow + (g2.rowadj[k] & 0xffffu) * (unsigned)sizeof(gv_t)), acc[s]);
+                            // slot k is predicated on degree > k: idle lanes and the (high)
+                            // lanes of low-degree columns issue no shared-memory request
+                            const unsigned deg = w_deg[s];
+                            const float4 w4 = gdb_lds_f4(Wrow + w_woff[s], GDB_SLOT_ON(0u));
+                            const gv_t p0 = gdb_lds_gv(prow + w_xoff[s][0], GDB_SLOT_ON(0u));
+                            const gv_t p1 = gdb_lds_gv(prow + w_xoff[s][1], GDB_SLOT_ON(1u));
+                            const gv_t p2 = gdb_lds_gv(prow + w_xoff[s][2], GDB_SLOT_ON(2u));
+                            const gv_t p3 = gdb_lds_gv(prow + w_xoff[s][3], GDB_SLOT_ON(3u));
+                            acc[s] = gv_fma(w4.x, p0, acc[s]);
+                            acc[s] = gv_fma(w4.y, p1, acc[s]);
+                            acc[s] = gv_fma(w4.z, p2, acc[s]);
+                            acc[s] = gv_fma(w4.w, p3, acc[s]);
+                            if (deg > (unsigned)GDB_ADJ) {  // rare: the remaining neighbours from the row index
+                                const unsigned kbeg = g2.rowptr[g2.lanemap[GDB_POS(s)] & 0xffffu];
+                                for (unsigned k = GDB_ADJ; k < deg; ++k) {
+                                    const float w = W[k1 * (unsigned)wstride + (w_woff[s] >> 2) + k];
+                                    const unsigned j2 = g2.lanemap[g2.rowadj[kbeg + k] & 0xffffu] >> 16;
+                                    acc[s] = gv_fma(w, pbuf[(g1.rowadj[k1] & 0xffffu) * (unsigned)n2 + j2], acc[s]);
                                 }
                             }
                         }
                     }
 #pragma unroll
                     for (int s = 0; s < GDB_WPT; ++s) {
-                        if (w_col[s] < n2) {
-                            const gv_t pv = pbuf[i1 * n2 + w_col[s]];
+                        if (GDB_LIVE(s)) {
+                            const gv_t pv = pbuf[i1 * n2 + GDB_POS(s)];
                             const gv_t av = gv_fma2(gv_make(diag[s][r], diag[s][r]), pv, gv_neg(acc[s]));
                             apv[s][r] = av;
 #pragma unroll
@@ -400,10 +469,9 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll
             for (int s = 0; s < GDB_WPT; ++s) {
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
+                for (int r = 0; r < GDB_RPW; ++r) {
                     const int i1 = w_row0 + r;
-                    if (i1 < w_row1 && w_col[s] < n2) {
-                        xv[s][r] = gv_fma2(al, pbuf[i1 * n2 + w_col[s]], xv[s][r]);
+                    if (i1 < w_row1 && GDB_LIVE(s)) {
                         const gv_t ri = gv_fma2(gv_neg(al), apv[s][r], rv[s][r]);
                         rv[s][r] = ri;
                         const float dinv = __fdividef(1.0f, diag[s][r]);
@@ -429,11 +497,14 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll
             for (int s = 0; s < GDB_WPT; ++s) {
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
+                for (int r = 0; r < GDB_RPW; ++r) {
                     const int i1 = w_row0 + r;
-                    if (i1 < w_row1 && w_col[s] < n2) {
-                        gv_t *pp = pbuf + i1 * n2 + w_col[s];
-                        *pp = gv_fma2(be, *pp, gv_scale(__fdividef(1.0f, diag[s][r]), rv[s][r]));
+                    if (i1 < w_row1 && GDB_LIVE(s)) {
+                        // x += alpha p rides on the read of p that the update of p needs anyway
+                        gv_t *pp = pbuf + i1 * n2 + GDB_POS(s);
+                        const gv_t pv = *pp;
+                        xv[s][r] = gv_fma2(al, pv, xv[s][r]);
+                        *pp = gv_fma2(be, pv, gv_scale(__fdividef(1.0f, diag[s][r]), rv[s][r]));
                     }
                 }
             }
@@ -458,9 +529,9 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll
         for (int s = 0; s < GDB_WPT; ++s) {
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
+            for (int r = 0; r < GDB_RPW; ++r) {
                 const int i1 = w_row0 + r;
-                if (i1 < w_row1 && w_col[s] < n2) xs[i1 * n2 + w_col[s]] = xv[s][r];
+                if (i1 < w_row1 && GDB_LIVE(s)) xs[i1 * n2 + (int)(g2.lanemap[GDB_POS(s)] & 0xffffu)] = xv[s][r];
             }
         }
         gdb_group_sync();
@@ -511,12 +582,12 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             for (int m = 0; m < NACC; ++m) acc[m] = 0.f;
 #pragma unroll
             for (int s = 0; s < GDB_WPT; ++s) {
-                const node_t &u2 = g2.node[w_col[s] < n2 ? w_col[s] : 0];
+                const node_t &u2 = g2.node[GDB_LIVE(s) ? (g2.lanemap[GDB_POS(s)] & 0xffffu) : 0u];
                 const float p2 = P.p_start(u2);
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
+                for (int r = 0; r < GDB_RPW; ++r) {
                     const int i1 = w_row0 + r;
-                    if (i1 < w_row1 && w_col[s] < n2) {
+                    if (i1 < w_row1 && GDB_LIVE(s)) {
                         const node_t &u1 = g1.node[i1];
                         const float p1 = P.p_start(u1);
                         const float xi = gv_get(xv[s][r], 0);
@@ -654,3 +725,5 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #endif
     }
 }
+#undef GDB_POS
+#undef GDB_LIVE

@@ -390,19 +390,25 @@ class B200Backend(Backend):
 
     # -- programs ----------------------------------------------------------
     def _pick_block(self, sizes, eval_gradient=False):
-        """(threads per pair, workers per thread).  The small-pair kernel
-        needs block >= 32 * (tile rows) and 32 * workers >= nodes of the
-        largest graph; larger sets run the general kernel, sized by N = n^2."""
+        """(threads per pair, workers per thread, rows per warp).  The
+        small-pair kernel needs rows_per_warp * warps >= nodes and 32 *
+        workers >= nodes of the largest graph; larger sets run the general
+        kernel, sized by N = n^2."""
         n = int(np.max(sizes))
         max_wpt = 1 if eval_gradient else 2
         if self.block_size:
-            return int(self.block_size), min(max_wpt, max(1, -(-n // 32)))
-        # small-pair kernel: one warp per 8-row tile of G1, lanes x workers per
+            warps = int(self.block_size) // 32
+            return (int(self.block_size), min(max_wpt, max(1, -(-n // 32))),
+                    min(8, max(1, -(-n // max(1, warps)))))
+        # small-pair kernel: rows of G1 dealt to the warps, lanes x workers per
         # thread over the columns of G2
         if n <= 32 * max_wpt and n <= 256:
-            return max(64, 32 * -(-n // 8)), -(-n // 32)
+            # ~6 rows per warp: 4 warps for 24-node molecules (block sweep in
+            # DESIGN.md section 10: more, lighter warps hide the shared-memory latency)
+            warps = max(2, -(-n // 6))
+            return 32 * warps, -(-n // 32), -(-n // warps)
         N = n * n
-        return (128 if N <= 16384 else 256), 1
+        return (128 if N <= 16384 else 256), 1, 8
 
     @staticmethod
     def _desc(nl, el, weighted, node_kernel, edge_kernel, p, traits, block,
@@ -423,13 +429,14 @@ class B200Backend(Backend):
         d.nodal = native.NODAL_CODES[traits.nodal]
         d.lmin = int(traits.lmin)
         d.eval_gradient = int(traits.eval_gradient is True)
-        block, wpt = block if isinstance(block, tuple) else (block, 1)
+        block, wpt, rpw = (tuple(block) + (1, 8)[len(block) - 1:]) if isinstance(block, tuple) else (block, 1, 8)
         d.block_size = int(block)
         d.workers_per_thread = int(wpt)
+        d.rows_per_warp = int(rpw)
         d.extra_options = ' '.join(extra).encode() if extra else None
         keep = (fn, fe, fp)
         key = (nl.key, el.key, weighted, fn.key, fe.key, fp.key,
-               tuple(traits), block, wpt, tuple(extra))
+               tuple(traits), block, wpt, rpw, tuple(extra))
         return d, keep, key
 
     def program(self, gs, node_kernel, edge_kernel, p, traits):
@@ -543,14 +550,18 @@ def preset_sources():
     presets = {
         'c1_unlabeled': ('C1', (Constant(1.0), Constant(1.0)),
                          T(symmetric=True), (64, 1)),
-        'c2_molecular': ('C2', mol, T(symmetric=True), (96, 1)),
-        'c2_molecular_diag': ('C2', mol, T(diagonal=True), (96, 1)),
+        'c2_molecular': ('C2', mol, T(symmetric=True), (128, 1, 6)),
+        'c2_molecular_diag': ('C2', mol, T(diagonal=True), (128, 1, 6)),
         'c3_molecular_grad': ('C2', mol, T(symmetric=True,
-                                           eval_gradient=True), (96, 1)),
-        'c3_tile_grad': ('C2', mol, T(eval_gradient=True), (96, 1)),
+                                           eval_gradient=True), (128, 1, 6)),
+        'c3_tile_grad': ('C2', mol, T(eval_gradient=True), (128, 1, 6)),
+        'c3_grad_b96': ('C2', mol, T(symmetric=True, eval_gradient=True),
+                        (96, 1, 8)),
+        'c3_grad_b192': ('C2', mol, T(symmetric=True, eval_gradient=True),
+                         (192, 1, 4)),
         'c4_convolution': ('C4', conv, T(symmetric=True), (256, 1)),
-        'c5_offdiag': ('C2', mol, T(), (96, 1)),
-        'c2_nodal': ('C2', mol, T(symmetric=True, nodal=True), (96, 1)),
+        'c5_offdiag': ('C2', mol, T(), (128, 1, 6)),
+        'c2_nodal': ('C2', mol, T(symmetric=True, nodal=True), (128, 1, 6)),
         'c2_wpt2': ('C2', mol, T(symmetric=True), (128, 2)),
     }
     out = {}

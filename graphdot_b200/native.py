@@ -50,6 +50,7 @@ class ProgramDesc(C.Structure):
                 ('nodal', C.c_int32), ('lmin', C.c_int32),
                 ('eval_gradient', C.c_int32), ('block_size', C.c_int32),
                 ('workers_per_thread', C.c_int32),
+                ('rows_per_warp', C.c_int32),
                 ('extra_options', C.c_char_p)]
 
 

@@ -101,6 +101,10 @@ typedef struct gdb_program_desc {
                                 columns (nodes of the second graph); it is used
                                 when block_size >= 32 * tile rows and
                                 32 * workers_per_thread >= nodes             */
+    int32_t rows_per_warp;   /* small-pair kernel: rows of the first graph
+                                per warp, 1..8; 0 = 8.  Sizes the register
+                                arrays; the kernel is used when
+                                rows_per_warp * block_size / 32 >= nodes    */
     const char *extra_options; /* extra NVRTC options, space separated     */
 } gdb_program_desc;
 

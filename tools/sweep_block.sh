@@ -1,0 +1,10 @@
+# usage (GPU box): bash tools/sweep_block.sh  -- A/B sweep of the small-kernel launch shape
+run() { tag=$1; shift; python bench.py --steps 3 --warmup 3 --e2e-steps 1 --no-cpu-baseline --no-reference-gpu "$@" > gpurun_out/sw_$tag.json 2> gpurun_out/sw_$tag.err; python -c "
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(sys.argv[2], d['value'], d['roofline']['kernel'])
+" gpurun_out/sw_$tag.json $tag; }
+run default
+run nopred --nvrtc-extra=-DGDB_PRED_SLOTS=0
+run m5 --nvrtc-extra=-DGDB_SMALL_MINB=5
+run m5_nopred "--nvrtc-extra=-DGDB_SMALL_MINB=5 -DGDB_PRED_SLOTS=0"
+run noswap --nvrtc-extra=-DGDB_NO_ROLE_SWAP
