@@ -648,7 +648,9 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
         const uint64_t nrhs = p->eval_gradient ? 2 : 1;
         const uint64_t wmax = (uint64_t)gs->max_nnz[0] * gs->max_ell;  // W[k1][column slots]
         // two blob staging buffers (double-buffered TMA prefetch) + W + one vector
-        const uint64_t small_need = 2 * graphs_need + wmax * 4 + nrhs * maxNpad * 4;
+        // + the step table (two addresses per element of G1)
+        const uint64_t small_need =
+            2 * graphs_need + (((uint64_t)gs->max_nnz[0] * 8 + 15) & ~15ull) + wmax * 4 + nrhs * maxNpad * 4;
         const uint64_t small_cap = std::min<uint64_t>(cap, (uint64_t)c->prop.sharedMemPerBlockOptin - p->small_static_smem);
         // one warp per tile row of G1, lanes (x workers per thread) over the columns of G2
         const bool mapped = (uint64_t)gs->max_node[0] <= (uint64_t)p->rpw * (uint64_t)(block / 32) &&

@@ -49,12 +49,12 @@
 #endif
 #define GDB_ADJ 4  // neighbours of a column kept in registers
 #ifndef GDB_PRED_SLOTS
-#define GDB_PRED_SLOTS 1  // 0: gather all GDB_ADJ slots of every live column (A-B hook)
+#define GDB_PRED_SLOTS 0  // 1: predicate the gather of slot k on degree > k (A-B hook)
 #endif
 #if GDB_PRED_SLOTS
 #define GDB_SLOT_ON(k) (deg > (k))
 #else
-#define GDB_SLOT_ON(k) (GDB_LIVE(s))
+#define GDB_SLOT_ON(k) true
 #endif
 #ifndef GDB_TMA_STAGE
 #define GDB_TMA_STAGE 1  // 0: synchronous uint4 staging (tuning / A-B hook)
@@ -151,11 +151,11 @@ __device__ __forceinline__ void gdb_divmod(unsigned a, unsigned d, float inv_d, 
     }
 }
 
-// Predicated shared-memory loads by 32-bit shared-window address.  A lane whose
-// predicate is off issues no request (the wavefront count of a gather follows
-// the ACTIVE lanes) and gets zeros.  Written in PTX so that the compiler keeps
-// the five loads of a matvec step back to back instead of branching around
-// each one.
+// Shared-memory loads by 32-bit shared-window address (no generic-address
+// arithmetic, always LDS).  With GDB_PRED_SLOTS a lane whose predicate is off
+// issues no request (the wavefront count of a gather follows the ACTIVE lanes)
+// and gets zeros.
+#if GDB_PRED_SLOTS
 __device__ __forceinline__ gv_t gdb_lds_gv(unsigned addr, bool on) {
 #if GDB_GRADIENT
     float x = 0.f, y = 0.f;
@@ -174,6 +174,29 @@ __device__ __forceinline__ float4 gdb_lds_f4(unsigned addr, bool on) {
     asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q ld.shared.v4.f32 {%0, %1, %2, %3}, [%4]; }"
                  : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
                  : "r"(addr), "r"((unsigned)on));
+    return v;
+}
+#else
+__device__ __forceinline__ gv_t gdb_lds_gv(unsigned addr, bool) {
+#if GDB_GRADIENT
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+#else
+    float x;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(addr));
+    return x;
+#endif
+}
+__device__ __forceinline__ float4 gdb_lds_f4(unsigned addr, bool) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+#endif
+__device__ __forceinline__ uint2 gdb_lds_u2(unsigned addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
 
@@ -300,8 +323,18 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         // constant stride.
         const int wd = (int)((h2->max_degree + 3u) & ~3u);
         const int wstride = n2 * wd;  // floats per W row (multiple of 4)
-        float *W = reinterpret_cast<float *>(gdb_smem_work + used);
+        // step table: for every element k1 of G1 (row order) the shared-window byte
+        // addresses of its W row and of the p row of its neighbour, one 64-bit
+        // broadcast load per matvec step
+        uint2 *ktab = reinterpret_cast<uint2 *>(gdb_smem_work + used);
+        float *W = reinterpret_cast<float *>(gdb_smem_work + used + (((unsigned)nnz1 * 8u + 15u) & ~15u));
         gv_t *pbuf = reinterpret_cast<gv_t *>(W + nnz1 * wstride);
+        const unsigned W_sa = (unsigned)__cvta_generic_to_shared(W);  // shared-window addresses
+        const unsigned p_sa = (unsigned)__cvta_generic_to_shared(pbuf);
+        const unsigned ktab_sa = (unsigned)__cvta_generic_to_shared(ktab);
+        for (int k1 = threadIdx.x; k1 < nnz1; k1 += GDB_BLOCK)
+            ktab[k1] = make_uint2(W_sa + (unsigned)k1 * (unsigned)(wstride * 4),
+                                  p_sa + (g1.rowadj[k1] & 0xffffu) * ((unsigned)n2 * (unsigned)sizeof(gv_t)));
 
         // ---- W = w1 w2 kE(e1, e2), once per pair: zero fill, then one balanced pass
         //      over the nnz1 x nnz2 real element pairs (both in row order) ------------
@@ -348,7 +381,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
                 const int i2 = live ? (int)(g2.lanemap[pos] & 0xffffu) : 0;
                 const unsigned kbeg = g2.rowptr[i2], kend = g2.rowptr[i2 + 1];
                 w_deg[s] = live ? kend - kbeg : 0u;
-                w_woff[s] = (unsigned)(pos * wd) * 4u;
+                w_woff[s] = live ? (unsigned)(pos * wd) * 4u : 0u;
 #pragma unroll
                 for (int k = 0; k < GDB_ADJ; ++k)
                     w_xoff[s][k] =
@@ -393,9 +426,6 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll
         for (int k = 0; k < GV_N; ++k) active[k] = rho[k] != 0.f;
         int iters = 0;  // summed over the systems that were still active
-        const unsigned W_sa = (unsigned)__cvta_generic_to_shared(W);     // shared-window addresses
-        const unsigned p_sa = (unsigned)__cvta_generic_to_shared(pbuf);
-        const unsigned prow_bytes = (unsigned)n2 * (unsigned)sizeof(gv_t);
         for (int it = 0; it < N; ++it) {
             bool any = false;
 #pragma unroll
@@ -415,30 +445,43 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
                     gv_t acc[GDB_WPT];
 #pragma unroll
                     for (int s = 0; s < GDB_WPT; ++s) acc[s] = gv_make(0.f, 0.f);
-                    const unsigned k1end = g1.rowptr[i1 + 1];
-                    for (unsigned k1 = g1.rowptr[i1]; k1 < k1end; ++k1) {  // warp-uniform trip count
-                        const unsigned Wrow = W_sa + k1 * (unsigned)(wstride * 4);
-                        const unsigned prow = p_sa + (g1.rowadj[k1] & 0xffffu) * prow_bytes;
+                    const unsigned k1beg = g1.rowptr[i1], k1end = g1.rowptr[i1 + 1];
+#if !defined(GDB_K1_UNROLL)
+#pragma unroll 1  // the body is replicated per row already: keep the code in the instruction cache
+#endif
+                    for (unsigned k1 = k1beg; k1 < k1end; ++k1) {  // warp-uniform trip count
+                        const uint2 step = gdb_lds_u2(ktab_sa + k1 * 8u);  // (W row, p row)
 #pragma unroll
                         for (int s = 0; s < GDB_WPT; ++s) {
-                            // slot k is predicated on degree > k: idle lanes and the (high)
-                            // lanes of low-degree columns issue no shared-memory request
+                            // All lanes load: the missing slots of a column hold W = 0 and
+                            // point at position 0 of the p row, idle lanes read column 0.
+                            // With GDB_PRED_SLOTS slot k is predicated on degree > k instead.
+#if GDB_PRED_SLOTS
                             const unsigned deg = w_deg[s];
-                            const float4 w4 = gdb_lds_f4(Wrow + w_woff[s], GDB_SLOT_ON(0u));
-                            const gv_t p0 = gdb_lds_gv(prow + w_xoff[s][0], GDB_SLOT_ON(0u));
-                            const gv_t p1 = gdb_lds_gv(prow + w_xoff[s][1], GDB_SLOT_ON(1u));
-                            const gv_t p2 = gdb_lds_gv(prow + w_xoff[s][2], GDB_SLOT_ON(2u));
-                            const gv_t p3 = gdb_lds_gv(prow + w_xoff[s][3], GDB_SLOT_ON(3u));
+#endif
+                            const float4 w4 = gdb_lds_f4(step.x + w_woff[s], GDB_SLOT_ON(0u));
+                            const gv_t p0 = gdb_lds_gv(step.y + w_xoff[s][0], GDB_SLOT_ON(0u));
+                            const gv_t p1 = gdb_lds_gv(step.y + w_xoff[s][1], GDB_SLOT_ON(1u));
+                            const gv_t p2 = gdb_lds_gv(step.y + w_xoff[s][2], GDB_SLOT_ON(2u));
+                            const gv_t p3 = gdb_lds_gv(step.y + w_xoff[s][3], GDB_SLOT_ON(3u));
                             acc[s] = gv_fma(w4.x, p0, acc[s]);
                             acc[s] = gv_fma(w4.y, p1, acc[s]);
                             acc[s] = gv_fma(w4.z, p2, acc[s]);
                             acc[s] = gv_fma(w4.w, p3, acc[s]);
-                            if (deg > (unsigned)GDB_ADJ) {  // rare: the remaining neighbours from the row index
-                                const unsigned kbeg = g2.rowptr[g2.lanemap[GDB_POS(s)] & 0xffffu];
-                                for (unsigned k = GDB_ADJ; k < deg; ++k) {
-                                    const float w = W[k1 * (unsigned)wstride + (w_woff[s] >> 2) + k];
-                                    const unsigned j2 = g2.lanemap[g2.rowadj[kbeg + k] & 0xffffu] >> 16;
-                                    acc[s] = gv_fma(w, pbuf[(g1.rowadj[k1] & 0xffffu) * (unsigned)n2 + j2], acc[s]);
+                        }
+                    }
+                    if (wd > GDB_ADJ) {  // rare, uniform per pair: columns with more than GDB_ADJ neighbours
+                        for (unsigned k1 = k1beg; k1 < k1end; ++k1) {
+                            const unsigned j1 = g1.rowadj[k1] & 0xffffu;
+#pragma unroll
+                            for (int s = 0; s < GDB_WPT; ++s) {
+                                if (w_deg[s] > (unsigned)GDB_ADJ) {
+                                    const unsigned kbeg = g2.rowptr[g2.lanemap[GDB_POS(s)] & 0xffffu];
+                                    for (unsigned k = GDB_ADJ; k < w_deg[s]; ++k) {
+                                        const float w = W[k1 * (unsigned)wstride + (w_woff[s] >> 2) + k];
+                                        const unsigned j2 = g2.lanemap[g2.rowadj[kbeg + k] & 0xffffu] >> 16;
+                                        acc[s] = gv_fma(w, pbuf[j1 * (unsigned)n2 + j2], acc[s]);
+                                    }
                                 }
                             }
                         }

@@ -4,7 +4,9 @@ import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(sys.argv[2], d['value'], d['roofline']['kernel'])
 " gpurun_out/sw_$tag.json $tag; }
 run default
-run nopred --nvrtc-extra=-DGDB_PRED_SLOTS=0
-run m5 --nvrtc-extra=-DGDB_SMALL_MINB=5
-run m5_nopred "--nvrtc-extra=-DGDB_SMALL_MINB=5 -DGDB_PRED_SLOTS=0"
-run noswap --nvrtc-extra=-DGDB_NO_ROLE_SWAP
+run unroll --nvrtc-extra=-DGDB_K1_UNROLL
+run pred --nvrtc-extra=-DGDB_PRED_SLOTS=1
+run m6 --nvrtc-extra=-DGDB_SMALL_MINB=6
+run m4 --nvrtc-extra=-DGDB_SMALL_MINB=4
+run b160_m4 --block-size 160 --nvrtc-extra=-DGDB_SMALL_MINB=4
+run b192_m3 --block-size 192 --nvrtc-extra=-DGDB_SMALL_MINB=3
