@@ -275,6 +275,7 @@ def run_gpu(args, rank, world, local_rank):
     G = make_config_graphs('C2', n)
     backend = B200Backend(device=local_rank,
                           block_size=args.block_size or None,
+                          slots_per_lane=args.slots_per_lane or None,
                           nvrtc_extra=args.nvrtc_extra.split())
     kernel = make_config_kernel('C3', backend=backend)
     stream = torch.cuda.current_stream()
@@ -453,6 +454,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--tile-rows', type=int, default=64)
     ap.add_argument('--block-size', type=int, default=0)
+    ap.add_argument('--slots-per-lane', type=int, default=0)
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-reference-gpu', action='store_true')

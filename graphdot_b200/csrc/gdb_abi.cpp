@@ -224,7 +224,7 @@ struct gdb_program_s {
     std::string source, log;
     gdb_program_info info{};
     uint32_t theta_size[3] = {};
-    int eval_gradient = 0, nodal = 0, wpt = 1, rpw = 8;
+    int eval_gradient = 0, nodal = 0, wpt = 1, rpw = 8, adj = 4;
     int refcount = 1;
 };
 
@@ -250,6 +250,7 @@ static int pick_block(const gdb_program_desc *d) {
 static int pick_wpt(const gdb_program_desc *d) { return d->workers_per_thread <= 0 ? 1 : d->workers_per_thread; }
 
 static int pick_rpw(const gdb_program_desc *d) { return d->rows_per_warp <= 0 ? 8 : d->rows_per_warp; }
+static int pick_adj(const gdb_program_desc *d) { return d->slots_per_lane <= 0 ? 4 : d->slots_per_lane; }
 
 static int render(const gdb_program_desc *d, std::string &src) {
     if (!d || !d->node_decl || !d->edge_decl || !d->node_kernel.expr || !d->edge_kernel.expr || !d->p_start.expr)
@@ -259,6 +260,7 @@ static int render(const gdb_program_desc *d, std::string &src) {
     if (d->nodal < 0 || d->nodal > 2 || d->lmin < 0 || d->lmin > 1) return gdb_fail(GDB_ERR_INVALID, "invalid traits");
     if (pick_wpt(d) > 4) return gdb_fail(GDB_ERR_INVALID, "workers_per_thread must be 1..4");
     if (pick_rpw(d) > 8) return gdb_fail(GDB_ERR_INVALID, "rows_per_warp must be 1..8");
+    if (pick_adj(d) != 2 && pick_adj(d) != 4) return gdb_fail(GDB_ERR_INVALID, "slots_per_lane must be 2 or 4");
     std::ostringstream o;
     o << gdb_embedded_prelude << "\n";
     o << "// ---- generated splice ----\n";
@@ -266,17 +268,19 @@ static int render(const gdb_program_desc *d, std::string &src) {
     o << "#define GDB_MIN_BLOCKS " << std::max(1, std::min(16, 1024 / block)) << "\n";
     {
         // small-pair kernel: the per-thread state is rows_per_warp x (x, r, Ap, diag)
-        // [float2 with gradients] + ~50 registers of indices and loop state.  With
-        // at most 6 rows per warp 96 registers leave ptxas room to keep the five
-        // loads of a matvec step in flight together, so ask for 640 threads per SM
-        // instead of 512.  Measured on the C3 workload (pairs/s): block 96 / 8 rows /
-        // 128 regs 12.4 M; 128 / 6 / 80 regs 15.7 M; 128 / 6 / 96 regs 16.7 M -- the
-        // kernel is latency bound, more and lighter warps win.
-        const int threads = (pick_wpt(d) == 1 && pick_rpw(d) <= 6) ? 640 : 512;
+        // [float2 with gradients] + ~45 registers of indices and loop state.  The
+        // kernel is bound by instruction issue and latency, so more and lighter warps
+        // win: with at most 6 rows per warp ask ptxas for 768 (2 slots per lane) or
+        // 640 (4 slots) threads per SM instead of 512.  Measured on the C3 workload
+        // (M pairs/s): block 96 / 8 rows / 128 regs 12.4; 128 / 6 / 96 regs 16.4;
+        // 128 / 6 / 80 regs 16.9; 72 regs (spills in the CG loop) 11.6.
+        int threads = 512;
+        if (pick_wpt(d) == 1 && pick_rpw(d) <= 6) threads = pick_adj(d) == 2 ? 768 : 640;
         o << "#define GDB_MIN_BLOCKS_SMALL " << std::max(1, threads / block) << "\n";
     }
     o << "#define GDB_WPT " << pick_wpt(d) << "\n";
     o << "#define GDB_RPW " << pick_rpw(d) << "\n";
+    o << "#define GDB_ADJ " << pick_adj(d) << "\n";
     o << "#define GDB_WEIGHTED " << (d->weighted ? 1 : 0) << "\n";
     o << "#define GDB_DIAGONAL " << (d->diagonal ? 1 : 0) << "\n";
     o << "#define GDB_SYMMETRIC " << (d->symmetric ? 1 : 0) << "\n";
@@ -387,6 +391,7 @@ extern "C" int gdb_program_create(gdb_context_t c, const gdb_program_desc *d, gd
     p->nodal = d->nodal;
     p->wpt = pick_wpt(d);
     p->rpw = pick_rpw(d);
+    p->adj = pick_adj(d);
     p->theta_size[0] = d->node_kernel.theta_size;
     p->theta_size[1] = d->edge_kernel.theta_size;
     p->theta_size[2] = d->p_start.theta_size;
@@ -459,7 +464,10 @@ struct gdb_graphset_s {
     uint32_t max_blob[2] = {0, 0};  // two largest blobs
     uint32_t max_node[2] = {0, 0};  // two largest node counts
     uint32_t max_nnz[2] = {0, 0};   // two largest element counts
-    uint32_t max_ell = 0;           // largest n_node * pad4(max_degree): floats per W row
+    // small-pair kernel: most neighbour slots of one graph left without a helper lane,
+    // for [slots per lane 2, 4][workers per thread 1..4] (mirrors the lane tables of
+    // mlgk_small.cuh)
+    uint32_t max_ovf[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     uint32_t max_idx[2] = {0, 0};   // two largest (row index + edge elements) byte counts
     bool index16 = true;            // every graph carries a valid 16-bit row index
 };
@@ -528,8 +536,24 @@ extern "C" int gdb_graphset_create(gdb_context_t c, const gdb_layout *L, uint32_
         top2(gs->max_blob, (uint32_t)blob_bytes[k]);
         top2(gs->max_node, (uint32_t)h->n_node);
         top2(gs->max_nnz, (uint32_t)h->nnz);
-        gs->max_ell = std::max<uint32_t>(gs->max_ell, (uint32_t)h->n_node * ((h->max_degree + 3u) & ~3u));
         if (!(h->flags & 2u)) gs->index16 = false;
+        {
+            const uint32_t *rowptr = reinterpret_cast<const uint32_t *>(dst + h->off_rowptr);
+            const uint32_t *lanemap = reinterpret_cast<const uint32_t *>(dst + h->off_lanemap);
+            for (int a = 0; a < 2; ++a)
+                for (int w = 0; w < 4; ++w) {
+                    const uint32_t adj = a ? 4u : 2u, VL = 32u * (w + 1);
+                    uint32_t next = (uint32_t)h->n_node, ovf = 0;
+                    for (int32_t pos = 0; pos < h->n_node; ++pos) {  // nodes by decreasing degree
+                        const uint32_t c = lanemap[pos] & 0xffffu, deg = rowptr[c + 1] - rowptr[c];
+                        const uint32_t want = deg > adj ? (deg - 1u) / adj : 0u;
+                        const uint32_t got = next >= VL ? 0u : std::min(want, VL - next);
+                        next += want;
+                        if (deg > adj * (1u + got)) ovf += deg - adj * (1u + got);
+                    }
+                    gs->max_ovf[a][w] = std::max(gs->max_ovf[a][w], ovf);
+                }
+        }
         top2(gs->max_idx, (uint32_t)(((h->n_node + 1) * 4u + 15u) & ~15u) +
                               (uint32_t)((h->nnz * 4u + 15u) & ~15u) + (uint32_t)(h->off_emeta - h->off_edge));
         off += blob_bytes[k];
@@ -646,11 +670,16 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     CUfunction fn = p->fn;
     {
         const uint64_t nrhs = p->eval_gradient ? 2 : 1;
-        const uint64_t wmax = (uint64_t)gs->max_nnz[0] * gs->max_ell;  // W[k1][column slots]
-        // two blob staging buffers (double-buffered TMA prefetch) + W + one vector
-        // + the step table (two addresses per element of G1)
-        const uint64_t small_need =
-            2 * graphs_need + (((uint64_t)gs->max_nnz[0] * 8 + 15) & ~15ull) + wmax * 4 + nrhs * maxNpad * 4;
+        // work area of mlgk_solve_small (same layout, from the maxima of the graph set):
+        // step table | lane tables (vown, vhelp, vovf, wslot, vinfo) | p | W[k1][lanes' slots + overflow]
+        const uint64_t pad4nnz = ((uint64_t)gs->max_nnz[0] + 3) & ~3ull;
+        const uint64_t wrow = ((32ull * p->wpt * p->adj + 3) & ~3ull) +
+                              (((uint64_t)gs->max_ovf[p->adj == 4][std::min(p->wpt, 4) - 1] + 3) & ~3ull);
+        const uint64_t wmax = (uint64_t)gs->max_nnz[0] * wrow;
+        const uint64_t tables = 32ull * p->wpt + 2 * (((uint64_t)gs->max_node[0] + 3) & ~3ull) + pad4nnz + 4;
+        // two blob staging buffers (double-buffered TMA prefetch) + the work area
+        const uint64_t small_need = 2 * graphs_need + (((uint64_t)gs->max_nnz[0] * 8 + 15) & ~15ull) + tables * 4 +
+                                    nrhs * maxNpad * 4 + std::max(nrhs * maxNpad, wmax) * 4;  // p; W (W p aliases it)
         const uint64_t small_cap = std::min<uint64_t>(cap, (uint64_t)c->prop.sharedMemPerBlockOptin - p->small_static_smem);
         // one warp per tile row of G1, lanes (x workers per thread) over the columns of G2
         const bool mapped = (uint64_t)gs->max_node[0] <= (uint64_t)p->rpw * (uint64_t)(block / 32) &&

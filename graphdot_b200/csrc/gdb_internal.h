@@ -13,9 +13,9 @@ struct gdb_graph_hdr_host {
     uint32_t off_edge, off_pool, blob_bytes, flags;
     uint32_t off_emeta, off_rowptr, off_rowadj, off_tileelem;
     uint32_t max_degree;   // largest number of stored elements in a row
-    uint32_t off_ellslot;  // u32[nnz]: CSR position -> slot position(row) * pad4(max_degree) + k
+    uint32_t off_ellslot;  // u32[nnz] "rowpos": CSR position -> row | (index within the row << 16)
     uint32_t off_lanemap;  // u32[n_node]: [p] & 0xffff = node at degree-sorted position p, [i] >> 16 = position of node i
-    uint32_t reserved;
+    uint32_t vcols;        // virtual columns: sum ceil(deg / 2) | sum ceil(deg / 4) << 16 (each >= 1 per node)
 };
 static_assert(sizeof(gdb_graph_hdr_host) == GDB_HDR_BYTES, "header layout");
 

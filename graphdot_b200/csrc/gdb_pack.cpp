@@ -196,15 +196,13 @@ extern "C" int gdb_graph_pack(const gdb_layout *L, const gdb_graph_src *g, void 
         for (uint32_t i = 0; i <= g->n_node; ++i) rowptr[i] = fill[i];
         {
             // lane map of the small-pair kernel: nodes in order of decreasing degree
-            // (stable), so that the lanes that own a 2nd, 3rd, 4th ... neighbour slot
-            // are the LOW lanes of a warp and the gathers of the higher slots touch
-            // one half-warp only.  lanemap[p] & 0xffff = node at position p,
-            // lanemap[i] >> 16 = position of node i; ellslot[k] = slot of CSR
-            // element k in a W row laid out by position.
-            uint32_t *ellslot = reinterpret_cast<uint32_t *>(base + s.off_ellslot);
+            // (stable).  lanemap[p] & 0xffff = node at position p, lanemap[i] >> 16 =
+            // position of node i.  rowpos[k] = row | (index within the row << 16) of
+            // CSR element k.  vcols = number of virtual columns (chunks of 2 / of 4
+            // neighbour slots) the kernel needs lanes for.
+            uint32_t *rowpos = reinterpret_cast<uint32_t *>(base + s.off_ellslot);
             uint32_t *lanemap = reinterpret_cast<uint32_t *>(base + s.off_lanemap);
             h->off_lanemap = (uint32_t)s.off_lanemap;
-            const uint32_t wd = (max_degree + 3u) & ~3u;
             std::vector<uint32_t> order(g->n_node);
             for (uint32_t i = 0; i < g->n_node; ++i) order[i] = i;
             std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
@@ -212,9 +210,14 @@ extern "C" int gdb_graph_pack(const gdb_layout *L, const gdb_graph_src *g, void 
             });
             for (uint32_t pos = 0; pos < g->n_node; ++pos) lanemap[pos] = order[pos];
             for (uint32_t pos = 0; pos < g->n_node; ++pos) lanemap[order[pos]] |= pos << 16;
-            for (uint32_t i = 0; i < g->n_node; ++i)
-                for (uint32_t k = rowptr[i]; k < rowptr[i + 1]; ++k)
-                    ellslot[k] = (lanemap[i] >> 16) * wd + (k - rowptr[i]);
+            uint32_t nv2 = 0, nv4 = 0;
+            for (uint32_t i = 0; i < g->n_node; ++i) {
+                const uint32_t deg = rowptr[i + 1] - rowptr[i];
+                nv2 += std::max(1u, (deg + 1u) / 2u);
+                nv4 += std::max(1u, (deg + 3u) / 4u);
+                for (uint32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) rowpos[k] = i | ((k - rowptr[i]) << 16);
+            }
+            h->vcols = std::min(nv2, 0xffffu) | (std::min(nv4, 0xffffu) << 16);
         }
         // nz is sorted by (tile row, tile col, row, col): filling in this order
         // leaves every row's neighbours sorted by column

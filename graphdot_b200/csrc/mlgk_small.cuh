@@ -47,14 +47,11 @@
 #ifndef GDB_WPT
 #define GDB_WPT 1
 #endif
-#define GDB_ADJ 4  // neighbours of a column kept in registers
-#ifndef GDB_PRED_SLOTS
-#define GDB_PRED_SLOTS 0  // 1: predicate the gather of slot k on degree > k (A-B hook)
+#ifndef GDB_ADJ
+#define GDB_ADJ 4  // neighbour slots per (virtual) lane: 2 or 4
 #endif
-#if GDB_PRED_SLOTS
-#define GDB_SLOT_ON(k) (deg > (k))
-#else
-#define GDB_SLOT_ON(k) true
+#ifndef GDB_ROLL_ROWS
+#define GDB_ROLL_ROWS 0  // 1: matvec rolled over the rows, W p handed over through shared memory
 #endif
 #ifndef GDB_TMA_STAGE
 #define GDB_TMA_STAGE 1  // 0: synchronous uint4 staging (tuning / A-B hook)
@@ -72,6 +69,7 @@ __device__ __forceinline__ gv_t gv_fma(float a, gv_t b, gv_t c) { return make_fl
 __device__ __forceinline__ gv_t gv_fma2(gv_t a, gv_t b, gv_t c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 __device__ __forceinline__ gv_t gv_scale(float a, gv_t b) { return make_float2(a * b.x, a * b.y); }
 __device__ __forceinline__ gv_t gv_neg(gv_t a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ gv_t gv_add(gv_t a, gv_t b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float gv_get(gv_t a, int k) { return k ? a.y : a.x; }
 #else
 typedef float gv_t;
@@ -81,6 +79,7 @@ __device__ __forceinline__ gv_t gv_fma(float a, gv_t b, gv_t c) { return fmaf(a,
 __device__ __forceinline__ gv_t gv_fma2(gv_t a, gv_t b, gv_t c) { return fmaf(a, b, c); }
 __device__ __forceinline__ gv_t gv_scale(float a, gv_t b) { return a * b; }
 __device__ __forceinline__ gv_t gv_neg(gv_t a) { return -a; }
+__device__ __forceinline__ gv_t gv_add(gv_t a, gv_t b) { return a + b; }
 __device__ __forceinline__ float gv_get(gv_t a, int) { return a; }
 #endif
 
@@ -152,32 +151,8 @@ __device__ __forceinline__ void gdb_divmod(unsigned a, unsigned d, float inv_d, 
 }
 
 // Shared-memory loads by 32-bit shared-window address (no generic-address
-// arithmetic, always LDS).  With GDB_PRED_SLOTS a lane whose predicate is off
-// issues no request (the wavefront count of a gather follows the ACTIVE lanes)
-// and gets zeros.
-#if GDB_PRED_SLOTS
-__device__ __forceinline__ gv_t gdb_lds_gv(unsigned addr, bool on) {
-#if GDB_GRADIENT
-    float x = 0.f, y = 0.f;
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %3, 0; @q ld.shared.v2.f32 {%0, %1}, [%2]; }"
-                 : "+f"(x), "+f"(y)
-                 : "r"(addr), "r"((unsigned)on));
-    return make_float2(x, y);
-#else
-    float x = 0.f;
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q ld.shared.f32 %0, [%1]; }" : "+f"(x) : "r"(addr), "r"((unsigned)on));
-    return x;
-#endif
-}
-__device__ __forceinline__ float4 gdb_lds_f4(unsigned addr, bool on) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q ld.shared.v4.f32 {%0, %1, %2, %3}, [%4]; }"
-                 : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
-                 : "r"(addr), "r"((unsigned)on));
-    return v;
-}
-#else
-__device__ __forceinline__ gv_t gdb_lds_gv(unsigned addr, bool) {
+// arithmetic, always LDS).
+__device__ __forceinline__ gv_t gdb_lds_gv(unsigned addr) {
 #if GDB_GRADIENT
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
@@ -188,23 +163,64 @@ __device__ __forceinline__ gv_t gdb_lds_gv(unsigned addr, bool) {
     return x;
 #endif
 }
-__device__ __forceinline__ float4 gdb_lds_f4(unsigned addr, bool) {
+__device__ __forceinline__ float2 gdb_lds_f2(unsigned addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 gdb_lds_f4(unsigned addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
-#endif
 __device__ __forceinline__ uint2 gdb_lds_u2(unsigned addr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
+}
+// value held by virtual lane `src` (= lane + 32 * slot) of this warp
+template<int WPT> __device__ __forceinline__ gv_t gdb_shfl_vlane(const gv_t (&acc)[WPT], unsigned src) {
+    gv_t out;
+#pragma unroll
+    for (int q = 0; q < WPT; ++q) {
+#if GDB_GRADIENT
+        const gv_t t = make_float2(__shfl_sync(0xffffffffu, acc[q].x, (int)(src & 31u)),
+                                   __shfl_sync(0xffffffffu, acc[q].y, (int)(src & 31u)));
+#else
+        const gv_t t = __shfl_sync(0xffffffffu, acc[q], (int)(src & 31u));
+#endif
+        if (q == 0 || (src >> 5) == (unsigned)q) out = t;
+    }
+    return out;
+}
+
+// Slots of a column that found no helper lane (the warp ran out of lanes): the
+// owner walks them through the row index.  Out of line on purpose -- rare, and
+// the caller is replicated per row.
+__device__ __noinline__ gv_t gdb_small_overflow(const unsigned *rowadj1, const unsigned *rowptr2, const unsigned *rowadj2,
+                                                const unsigned *lanemap2, const unsigned *vovf, const float *W,
+                                                const gv_t *pbuf,
+                                                unsigned k1beg, unsigned k1end, unsigned wstride, unsigned ovf0, unsigned n2,
+                                                unsigned pos, unsigned t0) {
+    gv_t acc = gv_make(0.f, 0.f);
+    const unsigned col = lanemap2[pos] & 0xffffu;
+    const unsigned kbeg = rowptr2[col], deg = rowptr2[col + 1] - kbeg;
+    for (unsigned k1 = k1beg; k1 < k1end; ++k1) {
+        const unsigned j1 = rowadj1[k1] & 0xffffu;
+        for (unsigned t = t0; t < deg; ++t) {
+            const float w = W[k1 * wstride + ovf0 + vovf[col] + (t - t0)];
+            const unsigned j2 = lanemap2[rowadj2[kbeg + t] & 0xffffu] >> 16;
+            acc = gv_fma(w, pbuf[j1 * n2 + j2], acc);
+        }
+    }
+    return acc;
 }
 
 struct gdb_small_graph {
     const float *degree;
     const node_t *node;
     const edge_t *edge;
-    const unsigned *emeta, *rowptr, *rowadj, *ellslot, *lanemap;
+    const unsigned *emeta, *rowptr, *rowadj, *rowpos, *lanemap;
     int n, nnz, n_tile;
 };
 
@@ -217,7 +233,7 @@ __device__ __forceinline__ gdb_small_graph gdb_small_view(const unsigned char *b
     v.emeta = reinterpret_cast<const unsigned *>(base + h->off_emeta);
     v.rowptr = reinterpret_cast<const unsigned *>(base + h->off_rowptr);
     v.rowadj = reinterpret_cast<const unsigned *>(base + h->off_rowadj);
-    v.ellslot = reinterpret_cast<const unsigned *>(base + h->off_ellslot);
+    v.rowpos = reinterpret_cast<const unsigned *>(base + h->off_ellslot);
     v.lanemap = reinterpret_cast<const unsigned *>(base + h->off_lanemap);
     v.n = h->n_node;
     v.nnz = h->nnz;
@@ -299,42 +315,219 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             if (threadIdx.x == 0) prefetch(0);  // claims the next job only
         }
 #endif
-        const unsigned used = 0;
         unsigned char *const gdb_smem_work = work;
+        // ---- roles.  K and its Jacobian are symmetric in the two graphs, so the roles
+        //      are chosen per pair: the columns (lanes) go to the graph whose virtual
+        //      columns fit the lanes, then to the larger one (better lane utilisation,
+        //      fewer rows per warp).  The output position still follows (ja, jb). --------
+#if GDB_ADJ == 2
+#define GDB_VCOLS(h) ((h)->vcols & 0xffffu)
+#else
+#define GDB_VCOLS(h) ((h)->vcols >> 16)
+#endif
+        constexpr int VL = 32 * GDB_WPT;  // virtual lanes of a warp
 #if GDB_NODAL == 0 && !defined(GDB_NO_ROLE_SWAP)
-        // K and its Jacobian are symmetric in the two graphs, so the roles are chosen
-        // per pair: the LARGER graph provides the columns (lanes: better lane
-        // utilisation), the smaller one the rows (fewer rows per warp).  The output
-        // position still follows (ja, jb).
-        const bool swap_roles = reinterpret_cast<const gdb_graph_hdr *>(base1)->n_node >
-                                reinterpret_cast<const gdb_graph_hdr *>(base2)->n_node;
+        bool swap_roles;
+        {
+            const gdb_graph_hdr *ha = reinterpret_cast<const gdb_graph_hdr *>(base1);
+            const gdb_graph_hdr *hb = reinterpret_cast<const gdb_graph_hdr *>(base2);
+            const int sa = ha->n_node + (GDB_VCOLS(ha) <= (unsigned)VL ? 65536 : 0);
+            const int sb = hb->n_node + (GDB_VCOLS(hb) <= (unsigned)VL ? 65536 : 0);
+            swap_roles = sa > sb;
+        }
         const gdb_small_graph g1 = gdb_small_view(swap_roles ? base2 : base1);
         const gdb_small_graph g2 = gdb_small_view(swap_roles ? base1 : base2);
-        const gdb_graph_hdr *h2 = reinterpret_cast<const gdb_graph_hdr *>(swap_roles ? base1 : base2);
 #else
         const gdb_small_graph g1 = gdb_small_view(base1), g2 = gdb_small_view(base2);
-        const gdb_graph_hdr *h2 = reinterpret_cast<const gdb_graph_hdr *>(base2);
 #endif
         const int n1 = g1.n, n2 = g2.n, N = n1 * n2, nnz1 = g1.nnz, nnz2 = g2.nnz;
-        // W is indexed [k1][pos2 * wd + k]: k1 = position of the G1 element in row
-        // (CSR) order, (pos2, k) = k-th neighbour of the column at lane position pos2, padded with
-        // zeros to wd = 4 * ceil(max degree / 4) slots per column.  A worker's
-        // four slots are one aligned 128-bit load, and W rows are visited with a
-        // constant stride.
-        const int wd = (int)((h2->max_degree + 3u) & ~3u);
-        const int wstride = n2 * wd;  // floats per W row (multiple of 4)
-        // step table: for every element k1 of G1 (row order) the shared-window byte
-        // addresses of its W row and of the p row of its neighbour, one 64-bit
-        // broadcast load per matvec step
-        uint2 *ktab = reinterpret_cast<uint2 *>(gdb_smem_work + used);
-        float *W = reinterpret_cast<float *>(gdb_smem_work + used + (((unsigned)nnz1 * 8u + 15u) & ~15u));
-        gv_t *pbuf = reinterpret_cast<gv_t *>(W + nnz1 * wstride);
+
+        // ---- work area: [step table | lane tables | p | W p | W] -----------------------
+        //  ktab[k1]  (W row, p row) shared-window addresses of element k1 of G1 (row order):
+        //            one 64-bit broadcast load per matvec step
+        //  vown[v]   virtual lane v -> column | chunk << 16   (chunk = GDB_ADJ neighbour slots)
+        //  vhelp[c]  column c -> first helper lane | helpers << 16
+        //  vovf[c]   column c -> index of its first overflow slot (slots without a lane)
+        //  wslot[k2] element k2 of G2 (row order) -> float index of its W entry in a W row
+        //  vinfo     {lanes in use, most helpers of a column, overflow slots}
+        uint2 *ktab = reinterpret_cast<uint2 *>(gdb_smem_work);
+        unsigned *vown = reinterpret_cast<unsigned *>(gdb_smem_work + (((unsigned)nnz1 * 8u + 15u) & ~15u));
+        unsigned *vhelp = vown + VL;
+        unsigned *vovf = vhelp + ((n2 + 3) & ~3);
+        unsigned *wslot = vovf + ((n2 + 3) & ~3);
+        unsigned *vinfo = wslot + ((nnz2 + 3) & ~3);
+        gv_t *pbuf = reinterpret_cast<gv_t *>(vinfo + 4);
+#if GDB_ROLL_ROWS
+        gv_t *wpbuf = pbuf + ((N + 3) & ~3);  // W p of the current iteration (hand-off to the row registers)
+        float *W = reinterpret_cast<float *>(wpbuf + ((N + 3) & ~3));
+#else
+        float *W = reinterpret_cast<float *>(pbuf + ((N + 3) & ~3));
+        gv_t *wpbuf = reinterpret_cast<gv_t *>(W);  // setup hand-off only: W is filled after it
+#endif
         const unsigned W_sa = (unsigned)__cvta_generic_to_shared(W);  // shared-window addresses
         const unsigned p_sa = (unsigned)__cvta_generic_to_shared(pbuf);
         const unsigned ktab_sa = (unsigned)__cvta_generic_to_shared(ktab);
+        const int lane = (int)(threadIdx.x & 31);
+
+        // ---- lane tables (warp 0).  Lane position pos < n2 owns the column lanemap[pos]
+        //      of G2 (degree-sorted) and its first GDB_ADJ neighbour slots.  A column
+        //      with more neighbours gets HELPER lanes (n2, n2 + 1, ...: the lanes a warp
+        //      would otherwise idle), one per further chunk of GDB_ADJ slots, highest
+        //      degree first; what is left when the lanes run out (rare) is the overflow
+        //      that the owner walks through the row index. ------------------------------
+        if (threadIdx.x < 32) {
+            unsigned next = (unsigned)n2, most = 0u, ovf = 0u;
+            for (int p0 = 0; p0 < n2; p0 += 32) {
+                const int pos = p0 + lane;
+                const bool live = pos < n2;
+                const unsigned col = live ? (g2.lanemap[pos] & 0xffffu) : 0u;
+                const unsigned deg = live ? g2.rowptr[col + 1] - g2.rowptr[col] : 0u;
+                const unsigned want = deg > (unsigned)GDB_ADJ ? (deg - 1u) / (unsigned)GDB_ADJ : 0u;
+                unsigned incl = want;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const unsigned start = next + incl - want;
+                const unsigned got = start >= (unsigned)VL ? 0u : min(want, (unsigned)VL - start);
+                const unsigned covered = (unsigned)GDB_ADJ * (1u + got);
+                const unsigned left = deg > covered ? deg - covered : 0u;  // slots without a lane
+                unsigned lincl = left;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, lincl, o);
+                    if (lane >= o) lincl += t;
+                }
+                if (live) {
+                    vown[pos] = col;
+                    vhelp[col] = min(start, 0xffffu) | (got << 16);
+                    vovf[col] = ovf + lincl - left;
+                    for (unsigned j = 0; j < got; ++j) vown[start + j] = col | ((j + 1u) << 16);
+                }
+                next += __shfl_sync(0xffffffffu, incl, 31);
+                ovf += __shfl_sync(0xffffffffu, lincl, 31);
+                most = max(most, got);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {  // ovf is uniform already
+                most = max(most, __shfl_xor_sync(0xffffffffu, most, o));
+            }
+            if (lane == 0) {
+                vinfo[0] = min(next, (unsigned)VL);
+                vinfo[1] = most;
+                vinfo[2] = ovf;
+            }
+        }
+
+        // ---- per-worker setup: diagonal, rhs, CG start ---------------------------------
+        const float Q = 1.0f / (1.0f - F.q), Q2 = Q * Q;
+        // rows of G1 are dealt to ALL warps of the CTA in equal blocks of at most GDB_RPW
+        // (balanced: 20 rows on 4 warps = 5 + 5 + 5 + 5), so every loop over the elements
+        // of a row is warp-uniform
+        const int w_rows = (n1 + GDB_WARPS - 1) / GDB_WARPS;
+        const int w_row0 = min((int)(threadIdx.x >> 5) * w_rows, n1);
+        const int w_row1 = min(w_row0 + w_rows, n1);  // one past this warp's last row
+        // p and W are laid out by lane position, the graph data by node
+#define GDB_POS(s) (lane + 32 * (s))
+#define GDB_LIVE(s) (GDB_POS(s) < n2)
+        // The heavy per-element work (node kernel, Jacobians, the matvec) runs in
+        // ROLLED loops over the rows and hands its results to / from the row registers
+        // through shared memory: the register arrays need compile-time indices, but
+        // unrolling the heavy bodies GDB_RPW times overflows the instruction cache
+        // (measured: stall_no_instruction 0.2 -> 2.4 per issue at 6800 SASS instructions).
+        float diag[GDB_WPT][GDB_RPW];
+        gv_t xv[GDB_WPT][GDB_RPW], rv[GDB_WPT][GDB_RPW], apv[GDB_WPT][GDB_RPW];
+        float rho[GV_N];
+#pragma unroll
+        for (int k = 0; k < GV_N; ++k) rho[k] = 0.f;
+#pragma unroll
+        for (int s = 0; s < GDB_WPT; ++s) {
+            const int pos = GDB_POS(s);
+            if (GDB_LIVE(s)) {
+                const int i2 = (int)(g2.lanemap[pos] & 0xffffu);
+                const node_t &u2 = g2.node[i2];
+                const float d2 = g2.degree[i2] * Q2;
+#if GDB_GRADIENT
+                const float p2 = P.p_start(u2);
+#endif
+#pragma unroll 1
+                for (int i1 = w_row0; i1 < w_row1; ++i1) {
+                    const node_t &u1 = g1.node[i1];
+                    const float dx = g1.degree[i1] * d2;
+                    // diagonal Dx / Vx in the first float of p, rhs in the W p slot
+                    pbuf[i1 * n2 + pos] = gv_make(__fdividef(dx, P.node_kernel(u1, u2)), 0.f);
+#if GDB_GRADIENT
+                    wpbuf[i1 * n2 + pos] = gv_make(dx, P.p_start(u1) * p2);
+#else
+                    wpbuf[i1 * n2 + pos] = gv_make(dx, 0.f);
+#endif
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < GDB_RPW; ++r) {
+                const int i1 = w_row0 + r;
+                diag[s][r] = 1.f;
+                xv[s][r] = gv_make(0.f, 0.f);
+                rv[s][r] = gv_make(0.f, 0.f);
+                apv[s][r] = gv_make(0.f, 0.f);
+                if (GDB_LIVE(s) && i1 < w_row1) {
+                    const float d = gv_get(pbuf[i1 * n2 + pos], 0);
+                    const gv_t ri = wpbuf[i1 * n2 + pos];
+                    const gv_t z = gv_scale(__fdividef(1.0f, d), ri);
+                    diag[s][r] = d;
+                    rv[s][r] = ri;
+                    pbuf[i1 * n2 + pos] = z;
+#pragma unroll
+                    for (int k = 0; k < GV_N; ++k) rho[k] = fmaf(gv_get(ri, k), gv_get(z, k), rho[k]);
+                }
+            }
+        }
+        gdb_group_sum_n(rho, s_red, flip);  // barrier: the lane tables are visible
+
+        // ---- virtual lanes of this thread, W layout ------------------------------------
+        // W is indexed [k1][v * GDB_ADJ + k]: k1 = element of G1 in row order, (v, k) =
+        // k-th slot of virtual lane v, zero where a chunk has fewer neighbours; the
+        // overflow elements (if any) follow at [ovf0 + ...].  A lane's slots are one
+        // aligned 64/128-bit load, and W rows are visited with a constant stride.
+        const unsigned nvl = vinfo[0], w_most = vinfo[1];
+        const bool w_ovf = vinfo[2] != 0u;
+        const unsigned ovf0 = (nvl * (unsigned)GDB_ADJ + 3u) & ~3u;
+        const int wstride = (int)(ovf0 + ((vinfo[2] + 3u) & ~3u));  // floats per W row
+        unsigned w_woff[GDB_WPT];           // byte offset of the lane's slots in a W row
+        unsigned w_xoff[GDB_WPT][GDB_ADJ];  // byte offsets of the neighbours in a p row
+        unsigned w_help[GDB_WPT];           // owners: first helper lane | helpers << 16
+#pragma unroll
+        for (int s = 0; s < GDB_WPT; ++s) {
+            const unsigned v = (unsigned)GDB_POS(s);
+            const bool used = v < nvl;
+            const unsigned own = used ? vown[v] : 0u;
+            const unsigned col = own & 0xffffu, chunk = own >> 16;
+            const unsigned kbeg = g2.rowptr[col] + chunk * (unsigned)GDB_ADJ;
+            const unsigned kend = used ? min(g2.rowptr[col + 1], kbeg + (unsigned)GDB_ADJ) : kbeg;
+            w_woff[s] = used ? v * (unsigned)(GDB_ADJ * 4) : 0u;
+#pragma unroll
+            for (int k = 0; k < GDB_ADJ; ++k)
+                w_xoff[s][k] =
+                    (kbeg + k < kend) ? (g2.lanemap[g2.rowadj[kbeg + k] & 0xffffu] >> 16) * (unsigned)sizeof(gv_t) : 0u;
+            w_help[s] = (GDB_LIVE(s) && chunk == 0u) ? vhelp[col] : 0u;
+        }
         for (int k1 = threadIdx.x; k1 < nnz1; k1 += GDB_BLOCK)
             ktab[k1] = make_uint2(W_sa + (unsigned)k1 * (unsigned)(wstride * 4),
                                   p_sa + (g1.rowadj[k1] & 0xffffu) * ((unsigned)n2 * (unsigned)sizeof(gv_t)));
+        for (int k2 = threadIdx.x; k2 < nnz2; k2 += GDB_BLOCK) {
+            const unsigned rp = g2.rowpos[k2], col = rp & 0xffffu, t = rp >> 16;
+            const unsigned chunk = t / (unsigned)GDB_ADJ, slot = t % (unsigned)GDB_ADJ;
+            const unsigned hv = vhelp[col];
+            unsigned at;
+            if (chunk == 0u)
+                at = (g2.lanemap[col] >> 16) * (unsigned)GDB_ADJ + slot;
+            else if (chunk - 1u < (hv >> 16))
+                at = ((hv & 0xffffu) + chunk - 1u) * (unsigned)GDB_ADJ + slot;
+            else
+                at = ovf0 + vovf[col] + (t - (unsigned)GDB_ADJ * (1u + (hv >> 16)));
+            wslot[k2] = at;
+        }
 
         // ---- W = w1 w2 kE(e1, e2), once per pair: zero fill, then one balanced pass
         //      over the nnz1 x nnz2 real element pairs (both in row order) ------------
@@ -346,79 +539,11 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             for (unsigned idx = threadIdx.x; idx < (unsigned)(nnz1 * nnz2); idx += GDB_BLOCK) {
                 unsigned k1, k2;
                 gdb_divmod(idx, (unsigned)nnz2, inv, k1, k2);
-                W[k1 * wstride + g2.ellslot[k2]] =
+                W[k1 * wstride + wslot[k2]] =
                     gdb_edge_value(P, g1.edge[g1.rowadj[k1] >> 16], g2.edge[g2.rowadj[k2] >> 16]);
             }
         }
-
-        // ---- per-worker setup: adjacency of column i2, diagonal, rhs, CG start ------
-        const float Q = 1.0f / (1.0f - F.q), Q2 = Q * Q;
-        // worker mapping: warp = tile row T1 of G1, lane (+ 32 s) = column i2 of G2,
-        // so every loop over the elements of a row is warp-uniform
-        // rows of G1 are dealt to ALL warps of the CTA in equal blocks of at most 8
-        // (balanced: 20 rows on 3 warps = 7 + 7 + 6; 16 rows = 6 + 6 + 4, not 8 + 8 + 0)
-        const int w_rows = (n1 + GDB_WARPS - 1) / GDB_WARPS;
-        const int w_row0 = min((int)(threadIdx.x >> 5) * w_rows, n1);
-        const int w_row1 = min(w_row0 + w_rows, n1);  // one past this warp's last row
-        // lane position pos = lane + 32 s owns column lanemap[pos] of G2; p and W are laid
-        // out by position, the graph data by node
-        const int lane = (int)(threadIdx.x & 31);
-#define GDB_POS(s) (lane + 32 * (s))
-#define GDB_LIVE(s) (GDB_POS(s) < n2)
-        unsigned w_deg[GDB_WPT];                        // degree of the column; 0 also for idle slots
-        unsigned w_woff[GDB_WPT];                       // byte offset of the column's slots in a W row
-        unsigned w_xoff[GDB_WPT][GDB_ADJ];              // byte offsets of the neighbours in a p row
-        float diag[GDB_WPT][GDB_RPW];
-        gv_t xv[GDB_WPT][GDB_RPW], rv[GDB_WPT][GDB_RPW], apv[GDB_WPT][GDB_RPW];
-        float rho[GV_N];
-#pragma unroll
-        for (int k = 0; k < GV_N; ++k) rho[k] = 0.f;
-        {
-#pragma unroll
-            for (int s = 0; s < GDB_WPT; ++s) {
-                const int pos = GDB_POS(s);
-                const bool live = GDB_LIVE(s);
-                const int i2 = live ? (int)(g2.lanemap[pos] & 0xffffu) : 0;
-                const unsigned kbeg = g2.rowptr[i2], kend = g2.rowptr[i2 + 1];
-                w_deg[s] = live ? kend - kbeg : 0u;
-                w_woff[s] = live ? (unsigned)(pos * wd) * 4u : 0u;
-#pragma unroll
-                for (int k = 0; k < GDB_ADJ; ++k)
-                    w_xoff[s][k] =
-                        (kbeg + k < kend) ? (g2.lanemap[g2.rowadj[kbeg + k] & 0xffffu] >> 16) * (unsigned)sizeof(gv_t) : 0u;
-                const node_t &u2 = g2.node[i2];
-                const float d2 = g2.degree[i2] * Q2;
-#if GDB_GRADIENT
-                const float p2 = P.p_start(u2);
-#endif
-#pragma unroll
-                for (int r = 0; r < GDB_RPW; ++r) {
-                    const int i1 = w_row0 + r;
-                    diag[s][r] = 1.f;
-                    xv[s][r] = gv_make(0.f, 0.f);
-                    rv[s][r] = gv_make(0.f, 0.f);
-                    apv[s][r] = gv_make(0.f, 0.f);
-                    if (live && i1 < w_row1) {
-                        const node_t &u1 = g1.node[i1];
-                        const float dx = g1.degree[i1] * d2;
-                        const float d = __fdividef(dx, P.node_kernel(u1, u2));
-                        diag[s][r] = d;
-#if GDB_GRADIENT
-                        const gv_t ri = gv_make(dx, P.p_start(u1) * p2);
-#else
-                        const gv_t ri = gv_make(dx, 0.f);
-#endif
-                        const gv_t z = gv_scale(__fdividef(1.0f, d), ri);
-                        rv[s][r] = ri;
-                        pbuf[i1 * n2 + pos] = z;
-#pragma unroll
-                        for (int k = 0; k < GV_N; ++k) rho[k] = fmaf(gv_get(ri, k), gv_get(z, k), rho[k]);
-                    }
-                }
-            }
-        }
-        gdb_group_sum_n(rho, s_red, flip);
-        gdb_group_sync();  // W and p complete
+        gdb_group_sync();  // W, the step table and p complete
 
         // ---- Jacobi-PCG, both systems at once ---------------------------------------
         const float thresh = F.ftol * (float)N;
@@ -434,63 +559,92 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll
             for (int k = 0; k < GV_N; ++k) iters += active[k] ? 1 : 0;
 
-            // matvec: A p = diag p - W p for the 8 elements of every worker
+            // matvec: W p of every owned element, one row of G1 at a time
+            auto row_wp = [&](int i1, gv_t (&acc)[GDB_WPT]) {
+#pragma unroll
+                for (int s = 0; s < GDB_WPT; ++s) acc[s] = gv_make(0.f, 0.f);
+                const unsigned k1beg = g1.rowptr[i1], k1end = g1.rowptr[i1 + 1];
+#if !defined(GDB_K1_UNROLL)
+#pragma unroll 1  // the body is replicated per row already: keep the code in the instruction cache
+#endif
+                for (unsigned k1 = k1beg; k1 < k1end; ++k1) {  // warp-uniform trip count
+                    const uint2 step = gdb_lds_u2(ktab_sa + k1 * 8u);  // (W row, p row)
+#pragma unroll
+                    for (int s = 0; s < GDB_WPT; ++s) {
+                        // All lanes load: empty slots hold W = 0 and point at position 0
+                        // of the p row, unused lanes read lane 0's slots.
+#if GDB_ADJ == 2
+                        const float2 w2 = gdb_lds_f2(step.x + w_woff[s]);
+                        const gv_t p0 = gdb_lds_gv(step.y + w_xoff[s][0]);
+                        const gv_t p1 = gdb_lds_gv(step.y + w_xoff[s][1]);
+                        acc[s] = gv_fma(w2.x, p0, acc[s]);
+                        acc[s] = gv_fma(w2.y, p1, acc[s]);
+#else
+                        const float4 w4 = gdb_lds_f4(step.x + w_woff[s]);
+                        const gv_t p0 = gdb_lds_gv(step.y + w_xoff[s][0]);
+                        const gv_t p1 = gdb_lds_gv(step.y + w_xoff[s][1]);
+                        const gv_t p2 = gdb_lds_gv(step.y + w_xoff[s][2]);
+                        const gv_t p3 = gdb_lds_gv(step.y + w_xoff[s][3]);
+                        acc[s] = gv_fma(w4.x, p0, acc[s]);
+                        acc[s] = gv_fma(w4.y, p1, acc[s]);
+                        acc[s] = gv_fma(w4.z, p2, acc[s]);
+                        acc[s] = gv_fma(w4.w, p3, acc[s]);
+#endif
+                    }
+                }
+                if (w_ovf) {  // rare, uniform per pair: slots that found no helper lane
+#pragma unroll
+                    for (int s = 0; s < GDB_WPT; ++s)
+                        if (GDB_LIVE(s))
+                            acc[s] = gv_add(acc[s], gdb_small_overflow(g1.rowadj, g2.rowptr, g2.rowadj, g2.lanemap, vovf, W, pbuf, k1beg,
+                                                                       k1end, (unsigned)wstride, ovf0, (unsigned)n2,
+                                                                       (unsigned)GDB_POS(s),
+                                                                       (1u + (w_help[s] >> 16)) * (unsigned)GDB_ADJ));
+                }
+                // helpers hand their partial sums to the owning lane (fixed order)
+#pragma unroll 1
+                for (unsigned h = 0; h < w_most; ++h) {  // uniform per pair; 0 when no column has helpers
+#pragma unroll
+                    for (int s = 0; s < GDB_WPT; ++s) {
+                        const unsigned src = (w_help[s] & 0xffffu) + h;
+                        const gv_t t = gdb_shfl_vlane(acc, src);
+                        if (h < (w_help[s] >> 16)) acc[s] = gv_add(acc[s], t);
+                    }
+                }
+            };
             float pAp[GV_N];
 #pragma unroll
             for (int k = 0; k < GV_N; ++k) pAp[k] = 0.f;
+#if GDB_ROLL_ROWS
+            // rolled over the rows (small code); W p reaches the row registers through wpbuf
+#pragma unroll 1
+            for (int i1 = w_row0; i1 < w_row1; ++i1) {
+                gv_t acc[GDB_WPT];
+                row_wp(i1, acc);
+#pragma unroll
+                for (int s = 0; s < GDB_WPT; ++s)
+                    if (GDB_LIVE(s)) wpbuf[i1 * n2 + GDB_POS(s)] = acc[s];
+            }
+#endif
+            // A p = diag p - W p and p . A p on the row registers
 #pragma unroll
             for (int r = 0; r < GDB_RPW; ++r) {
                 const int i1 = w_row0 + r;
                 if (i1 < w_row1) {  // warp-uniform
+#if !GDB_ROLL_ROWS
                     gv_t acc[GDB_WPT];
-#pragma unroll
-                    for (int s = 0; s < GDB_WPT; ++s) acc[s] = gv_make(0.f, 0.f);
-                    const unsigned k1beg = g1.rowptr[i1], k1end = g1.rowptr[i1 + 1];
-#if !defined(GDB_K1_UNROLL)
-#pragma unroll 1  // the body is replicated per row already: keep the code in the instruction cache
+                    row_wp(i1, acc);
 #endif
-                    for (unsigned k1 = k1beg; k1 < k1end; ++k1) {  // warp-uniform trip count
-                        const uint2 step = gdb_lds_u2(ktab_sa + k1 * 8u);  // (W row, p row)
-#pragma unroll
-                        for (int s = 0; s < GDB_WPT; ++s) {
-                            // All lanes load: the missing slots of a column hold W = 0 and
-                            // point at position 0 of the p row, idle lanes read column 0.
-                            // With GDB_PRED_SLOTS slot k is predicated on degree > k instead.
-#if GDB_PRED_SLOTS
-                            const unsigned deg = w_deg[s];
-#endif
-                            const float4 w4 = gdb_lds_f4(step.x + w_woff[s], GDB_SLOT_ON(0u));
-                            const gv_t p0 = gdb_lds_gv(step.y + w_xoff[s][0], GDB_SLOT_ON(0u));
-                            const gv_t p1 = gdb_lds_gv(step.y + w_xoff[s][1], GDB_SLOT_ON(1u));
-                            const gv_t p2 = gdb_lds_gv(step.y + w_xoff[s][2], GDB_SLOT_ON(2u));
-                            const gv_t p3 = gdb_lds_gv(step.y + w_xoff[s][3], GDB_SLOT_ON(3u));
-                            acc[s] = gv_fma(w4.x, p0, acc[s]);
-                            acc[s] = gv_fma(w4.y, p1, acc[s]);
-                            acc[s] = gv_fma(w4.z, p2, acc[s]);
-                            acc[s] = gv_fma(w4.w, p3, acc[s]);
-                        }
-                    }
-                    if (wd > GDB_ADJ) {  // rare, uniform per pair: columns with more than GDB_ADJ neighbours
-                        for (unsigned k1 = k1beg; k1 < k1end; ++k1) {
-                            const unsigned j1 = g1.rowadj[k1] & 0xffffu;
-#pragma unroll
-                            for (int s = 0; s < GDB_WPT; ++s) {
-                                if (w_deg[s] > (unsigned)GDB_ADJ) {
-                                    const unsigned kbeg = g2.rowptr[g2.lanemap[GDB_POS(s)] & 0xffffu];
-                                    for (unsigned k = GDB_ADJ; k < w_deg[s]; ++k) {
-                                        const float w = W[k1 * (unsigned)wstride + (w_woff[s] >> 2) + k];
-                                        const unsigned j2 = g2.lanemap[g2.rowadj[kbeg + k] & 0xffffu] >> 16;
-                                        acc[s] = gv_fma(w, pbuf[j1 * (unsigned)n2 + j2], acc[s]);
-                                    }
-                                }
-                            }
-                        }
-                    }
 #pragma unroll
                     for (int s = 0; s < GDB_WPT; ++s) {
                         if (GDB_LIVE(s)) {
+#if GDB_ROLL_ROWS
+                            const gv_t wp = wpbuf[i1 * n2 + GDB_POS(s)];
+#else
+                            const gv_t wp = acc[s];
+#endif
                             const gv_t pv = pbuf[i1 * n2 + GDB_POS(s)];
-                            const gv_t av = gv_fma2(gv_make(diag[s][r], diag[s][r]), pv, gv_neg(acc[s]));
+                            const gv_t av = gv_fma2(gv_make(diag[s][r], diag[s][r]), pv, gv_neg(wp));
                             apv[s][r] = av;
 #pragma unroll
                             for (int k = 0; k < GV_N; ++k) pAp[k] = fmaf(gv_get(pv, k), gv_get(av, k), pAp[k]);
@@ -565,9 +719,9 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         (void)plane;
         (void)I2;
 
-#if GDB_NODAL != 0 || (GDB_GRADIENT && GDB_NE > 0)
-        // publish x (both systems) in shared memory: the nodal epilogues and the
-        // edge-Jacobian pass read elements owned by other threads
+        // publish x (both systems) in shared memory, indexed by node: the epilogues run
+        // rolled loops, and the nodal outputs and the edge-Jacobian pass read elements
+        // owned by other threads
         gv_t *xs = pbuf;
 #pragma unroll
         for (int s = 0; s < GDB_WPT; ++s) {
@@ -578,7 +732,6 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             }
         }
         gdb_group_sync();
-#endif
 
         // ---- epilogue: starting probabilities, Gram entry ----------------------------
 #if GDB_NODAL == 2
@@ -617,7 +770,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         }
 #else
         // graph level: K = sum xs p1 p2; with gradients also the node-side Jacobian
-        // terms, all from the registers of the owning worker
+        // terms, every worker over its own elements (rolled over the rows)
         {
             constexpr int NACC = 1 + (GDB_GRADIENT ? GDB_NP + 1 + GDB_NV : 0);
             float acc[NACC];
@@ -625,15 +778,19 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             for (int m = 0; m < NACC; ++m) acc[m] = 0.f;
 #pragma unroll
             for (int s = 0; s < GDB_WPT; ++s) {
-                const node_t &u2 = g2.node[GDB_LIVE(s) ? (g2.lanemap[GDB_POS(s)] & 0xffffu) : 0u];
-                const float p2 = P.p_start(u2);
-#pragma unroll
-                for (int r = 0; r < GDB_RPW; ++r) {
-                    const int i1 = w_row0 + r;
-                    if (i1 < w_row1 && GDB_LIVE(s)) {
+                if (GDB_LIVE(s)) {
+                    const int i2 = (int)(g2.lanemap[GDB_POS(s)] & 0xffffu);
+                    const node_t &u2 = g2.node[i2];
+                    const float p2 = P.p_start(u2);
+#if GDB_GRADIENT
+                    const float d2 = g2.degree[i2] * Q2;
+#endif
+#pragma unroll 1
+                    for (int i1 = w_row0; i1 < w_row1; ++i1) {
                         const node_t &u1 = g1.node[i1];
                         const float p1 = P.p_start(u1);
-                        const float xi = gv_get(xv[s][r], 0);
+                        const gv_t xy = xs[i1 * n2 + i2];
+                        const float xi = gv_get(xy, 0);
                         float xsft = xi;
 #if GDB_LMIN == 1 || GDB_GRADIENT
                         const float v = P.node_kernel(u1, u2);
@@ -646,16 +803,16 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
                         // dK/dp_m  = sum (dp1 p2 + p1 dp2) xs
                         // dK/dq    = sum y (2Q Dx) (1 - x / Vx)
                         // dK/dtv_m = sum y x Dx / Vx^2 dVx  [- p1 p2 dVx if lmin]
-                        const float yi = gv_get(xv[s][r], 1);
-                        const float dx = diag[s][r] * v;
+                        const float yi = gv_get(xy, 1);
+                        const float dx = g1.degree[i1] * d2;
 #if GDB_NP > 0
                         {
-                            float d1[GDB_NP], d2[GDB_NP];
+                            float d1[GDB_NP], dd2[GDB_NP];
                             P.p_start.jacobian(u1, d1);
-                            P.p_start.jacobian(u2, d2);
+                            P.p_start.jacobian(u2, dd2);
 #pragma unroll
                             for (int m = 0; m < GDB_NP; ++m)
-                                acc[1 + m] = fmaf(fmaf(d1[m], p2, p1 * d2[m]), xsft, acc[1 + m]);
+                                acc[1 + m] = fmaf(fmaf(d1[m], p2, p1 * dd2[m]), xsft, acc[1 + m]);
                         }
 #endif
                         acc[1 + GDB_NP] += 2.f * Q * dx * yi * (1.f - __fdividef(xi, v));
@@ -770,3 +927,4 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 }
 #undef GDB_POS
 #undef GDB_LIVE
+#undef GDB_VCOLS

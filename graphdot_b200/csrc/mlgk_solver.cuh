@@ -56,7 +56,7 @@ struct gdb_graph_hdr {
     unsigned off_degree, off_node, off_octile, off_tilerow;
     unsigned off_edge, off_pool, blob_bytes, flags;
     unsigned off_emeta, off_rowptr, off_rowadj, off_tileelem;
-    unsigned max_degree, off_ellslot, off_lanemap, reserved;
+    unsigned max_degree, off_ellslot, off_lanemap, vcols;
 };
 
 struct gdb_octile {

@@ -221,6 +221,10 @@ class GraphSet:
             C.byref(self.handle)))
         self.n = n
         self.sizes = np.array([p.n_node for p in packed])
+        # stored elements per node (header word 2 = nnz): picks the number of
+        # neighbour slots per lane of the small-pair kernel
+        nnz = sum(int(p.blob[:16].view(np.int32)[2]) for p in packed)
+        self.mean_degree = nnz / max(1, int(self.sizes.sum()))
 
     @property
     def nbytes(self):
@@ -277,10 +281,11 @@ class B200Backend(Backend):
         return native.pinned_empty(size, dtype)
 
     def __init__(self, device=0, block_size=None, nvrtc_extra=(),
-                 graphset_cache=4):
+                 graphset_cache=4, slots_per_lane=None):
         self.uuid = uuid.uuid4()
         self.device = device
         self.block_size = block_size
+        self.slots_per_lane = slots_per_lane   # 2 / 4 / None = by mean degree
         self.nvrtc_extra = list(nvrtc_extra)
         self._context = None
         self._programs = {}
@@ -389,26 +394,31 @@ class B200Backend(Backend):
         return gs
 
     # -- programs ----------------------------------------------------------
-    def _pick_block(self, sizes, eval_gradient=False):
-        """(threads per pair, workers per thread, rows per warp).  The
-        small-pair kernel needs rows_per_warp * warps >= nodes and 32 *
-        workers >= nodes of the largest graph; larger sets run the general
-        kernel, sized by N = n^2."""
+    def _pick_block(self, sizes, eval_gradient=False, mean_degree=None):
+        """(threads per pair, workers per thread, rows per warp, neighbour
+        slots per lane).  The small-pair kernel needs rows_per_warp * warps >=
+        nodes and 32 * workers >= nodes of the largest graph; larger sets run
+        the general kernel, sized by N = n^2."""
         n = int(np.max(sizes))
         max_wpt = 1 if eval_gradient else 2
+        # sparse (molecular) graphs: 2 slots per lane, columns of degree 3+
+        # borrow the idle lanes; denser graphs: 4 slots
+        adj = 2 if (mean_degree is not None and mean_degree <= 3.0) else 4
+        if self.slots_per_lane:
+            adj = int(self.slots_per_lane)
         if self.block_size:
             warps = int(self.block_size) // 32
             return (int(self.block_size), min(max_wpt, max(1, -(-n // 32))),
-                    min(8, max(1, -(-n // max(1, warps)))))
+                    min(8, max(1, -(-n // max(1, warps)))), adj)
         # small-pair kernel: rows of G1 dealt to the warps, lanes x workers per
         # thread over the columns of G2
         if n <= 32 * max_wpt and n <= 256:
             # ~6 rows per warp: 4 warps for 24-node molecules (block sweep in
             # DESIGN.md section 10: more, lighter warps hide the shared-memory latency)
             warps = max(2, -(-n // 6))
-            return 32 * warps, -(-n // 32), -(-n // warps)
+            return 32 * warps, -(-n // 32), -(-n // warps), adj
         N = n * n
-        return (128 if N <= 16384 else 256), 1, 8
+        return (128 if N <= 16384 else 256), 1, 8, adj
 
     @staticmethod
     def _desc(nl, el, weighted, node_kernel, edge_kernel, p, traits, block,
@@ -429,21 +439,23 @@ class B200Backend(Backend):
         d.nodal = native.NODAL_CODES[traits.nodal]
         d.lmin = int(traits.lmin)
         d.eval_gradient = int(traits.eval_gradient is True)
-        block, wpt, rpw = (tuple(block) + (1, 8)[len(block) - 1:]) if isinstance(block, tuple) else (block, 1, 8)
+        block, wpt, rpw, adj = (tuple(block) + (1, 8, 4)[len(block) - 1:]) if isinstance(block, tuple) else (block, 1, 8, 4)
         d.block_size = int(block)
         d.workers_per_thread = int(wpt)
         d.rows_per_warp = int(rpw)
+        d.slots_per_lane = int(adj)
         d.extra_options = ' '.join(extra).encode() if extra else None
         keep = (fn, fe, fp)
         key = (nl.key, el.key, weighted, fn.key, fe.key, fp.key,
-               tuple(traits), block, wpt, rpw, tuple(extra))
+               tuple(traits), block, wpt, rpw, adj, tuple(extra))
         return d, keep, key
 
     def program(self, gs, node_kernel, edge_kernel, p, traits):
         if traits.lmin not in (0, 1):
             raise ValueError(f'lmin must be 0 or 1, got {traits.lmin}')
         nl, el, weighted = gs.layouts
-        block = self._pick_block(gs.sizes, traits.eval_gradient is True)
+        block = self._pick_block(gs.sizes, traits.eval_gradient is True,
+                                 gs.mean_degree)
         d, keep, key = self._desc(nl, el, weighted, node_kernel, edge_kernel,
                                   p, traits, block, self.nvrtc_extra)
         prog = self._programs.get(key)
@@ -550,18 +562,18 @@ def preset_sources():
     presets = {
         'c1_unlabeled': ('C1', (Constant(1.0), Constant(1.0)),
                          T(symmetric=True), (64, 1)),
-        'c2_molecular': ('C2', mol, T(symmetric=True), (128, 1, 6)),
-        'c2_molecular_diag': ('C2', mol, T(diagonal=True), (128, 1, 6)),
+        'c2_molecular': ('C2', mol, T(symmetric=True), (128, 1, 6, 2)),
+        'c2_molecular_diag': ('C2', mol, T(diagonal=True), (128, 1, 6, 2)),
         'c3_molecular_grad': ('C2', mol, T(symmetric=True,
-                                           eval_gradient=True), (128, 1, 6)),
-        'c3_tile_grad': ('C2', mol, T(eval_gradient=True), (128, 1, 6)),
+                                           eval_gradient=True), (128, 1, 6, 2)),
+        'c3_tile_grad': ('C2', mol, T(eval_gradient=True), (128, 1, 6, 2)),
         'c3_grad_b96': ('C2', mol, T(symmetric=True, eval_gradient=True),
                         (96, 1, 8)),
         'c3_grad_b192': ('C2', mol, T(symmetric=True, eval_gradient=True),
                          (192, 1, 4)),
         'c4_convolution': ('C4', conv, T(symmetric=True), (256, 1)),
-        'c5_offdiag': ('C2', mol, T(), (128, 1, 6)),
-        'c2_nodal': ('C2', mol, T(symmetric=True, nodal=True), (128, 1, 6)),
+        'c5_offdiag': ('C2', mol, T(), (128, 1, 6, 2)),
+        'c2_nodal': ('C2', mol, T(symmetric=True, nodal=True), (128, 1, 6, 2)),
         'c2_wpt2': ('C2', mol, T(symmetric=True), (128, 2)),
     }
     out = {}

@@ -51,6 +51,7 @@ class ProgramDesc(C.Structure):
                 ('eval_gradient', C.c_int32), ('block_size', C.c_int32),
                 ('workers_per_thread', C.c_int32),
                 ('rows_per_warp', C.c_int32),
+                ('slots_per_lane', C.c_int32),
                 ('extra_options', C.c_char_p)]
 
 

@@ -75,6 +75,30 @@ def random_molecule(rng, n):
     return Graph(nodes, edf, title=f'mol{n}')
 
 
+def random_labeled_graph(rng, n, p_edge):
+    """Connected G(n, p) graph with the molecular attribute set (test helper:
+    arbitrary degrees exercise the helper-lane and overflow paths of the
+    small-pair kernel)."""
+    edges = {(int(rng.integers(v)), v) for v in range(1, n)}
+    for u in range(n):
+        for v in range(u + 1, n):
+            if rng.random() < p_edge:
+                edges.add((u, v))
+    e = np.array(sorted(edges), dtype=np.uint32)
+    m = len(e)
+    nodes = _frame({
+        '!i': np.arange(n, dtype=np.uint32),
+        'element': rng.choice(np.array([1, 6, 7, 8], dtype=np.int8), n),
+        'x': rng.uniform(0, 1, n).astype(np.float32),
+    })
+    edf = _frame({
+        '!i': e[:, 0], '!j': e[:, 1],
+        '!w': rng.uniform(0.5, 1.0, m).astype(np.float32),
+        'length': rng.uniform(1.0, 1.6, m).astype(np.float32),
+    })
+    return Graph(nodes, edf, title=f'gnp{n}')
+
+
 def newman_watts_strogatz(rng, n, k=4, p=0.05, n_feat=8):
     edges = set()
     for j in range(1, k // 2 + 1):

@@ -105,6 +105,10 @@ typedef struct gdb_program_desc {
                                 per warp, 1..8; 0 = 8.  Sizes the register
                                 arrays; the kernel is used when
                                 rows_per_warp * block_size / 32 >= nodes    */
+    int32_t slots_per_lane;  /* small-pair kernel: neighbour slots of a
+                                column that one lane gathers per step, 2 or
+                                4; 0 = 4.  Columns of higher degree borrow
+                                the idle lanes of the warp as helpers       */
     const char *extra_options; /* extra NVRTC options, space separated     */
 } gdb_program_desc;
 

@@ -552,3 +552,33 @@ def test_labeled_ragged_pairs_vs_oracle(backend):
     for k in range(dK.shape[2]):
         assert np.abs(dK[:, :, k] - dKo[:, :, k]).max() \
             < GRAD_RTOL * np.abs(dKo[:, :, k]).max()
+
+
+@pytest.mark.parametrize('slots', [2, 4])
+@pytest.mark.parametrize('p_edge', [0.1, 0.35, 0.8])
+def test_helper_lanes_and_overflow_vs_oracle(slots, p_edge):
+    """Columns with more neighbours than one lane gathers borrow helper lanes;
+    when the lanes run out the owner walks the rest (overflow).  Sparse to
+    nearly complete labeled graphs, both slot widths, value and Jacobian."""
+    from graphdot_b200.synthetic import random_labeled_graph
+    rng = np.random.default_rng(int(100 * p_edge) + slots)
+    sizes = {0.1: (3, 8, 13, 21, 24, 30), 0.35: (3, 8, 11, 13, 15, 17),
+             0.8: (3, 5, 6, 9, 11, 12)}[p_edge]    # W must fit in shared memory
+    G = [random_labeled_graph(rng, n, p_edge) for n in sizes]
+    be = B200Backend(slots_per_lane=slots)
+    kernel = make_config_kernel('C2', backend=be, q=0.2)
+    K, dK = kernel(G, eval_gradient=True)
+    assert be.last['small_kernel']
+    Ko, dKo = oracle.gram(G, knode=kernel.node_kernel,
+                          kedge=kernel.edge_kernel, q=0.2, eval_gradient=True)
+    assert np.allclose(K, Ko, rtol=GRAM_RTOL)
+    dKo = dKo[:, :, kernel.active_theta_mask]
+    for k in range(dK.shape[2]):
+        assert np.abs(dK[:, :, k] - dKo[:, :, k]).max() \
+            < GRAD_RTOL * np.abs(dKo[:, :, k]).max()
+    # without Jacobian (two workers per thread for n > 32 is exercised by C1)
+    assert np.allclose(kernel(G), Ko, rtol=GRAM_RTOL)
+    Kn = kernel(G[:3], nodal=True)
+    Kno = oracle.gram(G[:3], knode=kernel.node_kernel,
+                      kedge=kernel.edge_kernel, q=0.2, nodal=True)
+    assert np.allclose(Kn, Kno, rtol=GRAM_RTOL, atol=1e-7)

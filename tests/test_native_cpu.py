@@ -111,7 +111,7 @@ def test_octile_packer_roundtrip():
 
 
 def test_row_index_sections_of_the_blob():
-    """elem_meta / row_ptr / row_adj / tile_elem / ell_slot / lane_map are consistent with
+    """elem_meta / row_ptr / row_adj / tile_elem / row_pos / lane_map are consistent with
     the octile-ordered element array (the small-pair kernel indexes through
     them instead of decoding bit masks)."""
     be = B200Backend()
@@ -120,13 +120,13 @@ def test_row_index_sections_of_the_blob():
         hdr = np.frombuffer(blob[:80], dtype=np.uint32)
         n, n_oct, nnz, n_tile = hdr[:4].astype(int)
         off = {k: int(v) for k, v in zip(
-            ('emeta', 'rowptr', 'rowadj', 'tileelem', 'maxdeg', 'ellslot',
-             'lanemap'), hdr[12:19])}
+            ('emeta', 'rowptr', 'rowadj', 'tileelem', 'maxdeg', 'rowpos',
+             'lanemap', 'vcols'), hdr[12:20])}
         u32 = lambda o, c: np.frombuffer(blob[o:o + 4 * c], dtype=np.uint32)
         emeta, rowptr = u32(off['emeta'], nnz), u32(off['rowptr'], n + 1)
         rowadj, tileelem = u32(off['rowadj'], nnz), u32(off['tileelem'],
                                                         n_tile + 1)
-        ellslot = u32(off['ellslot'], nnz)
+        rowpos = u32(off['rowpos'], nnz)
         lanemap = u32(off['lanemap'], n)
         rows, cols = emeta & 0xffff, emeta >> 16
         ei, ej = np.asarray(g.edges['!i']), np.asarray(g.edges['!j'])
@@ -136,7 +136,9 @@ def test_row_index_sections_of_the_blob():
         assert rowptr[0] == 0 and rowptr[-1] == nnz
         deg = np.diff(rowptr.astype(int))
         assert off['maxdeg'] == deg.max()
-        wd = (int(deg.max()) + 3) // 4 * 4
+        # lanes the small-pair kernel wants: chunks of 2 / of 4 neighbour slots
+        assert off['vcols'] & 0xffff == np.maximum(1, (deg + 1) // 2).sum()
+        assert off['vcols'] >> 16 == np.maximum(1, (deg + 3) // 4).sum()
         # lane map: nodes by decreasing degree (stable) and its inverse
         order, pos = lanemap & 0xffff, lanemap >> 16
         assert np.array_equal(order, np.argsort(-deg, kind='stable'))
@@ -147,8 +149,8 @@ def test_row_index_sections_of_the_blob():
             assert np.all(rows[elem] == i)                 # elements of row i
             assert np.array_equal(cols[elem], adj & 0xffff)
             assert np.all(np.diff((adj & 0xffff).astype(int)) > 0)
-            assert np.array_equal(ellslot[rowptr[i]:rowptr[i + 1]],
-                                  pos[i] * wd + np.arange(deg[i]))
+            assert np.array_equal(rowpos[rowptr[i]:rowptr[i + 1]],
+                                  i | (np.arange(deg[i]) << 16))
         for t in range(n_tile):
             sel = rows[tileelem[t]:tileelem[t + 1]]
             assert np.all(sel // 8 == t)

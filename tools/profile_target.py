@@ -21,12 +21,14 @@ ap.add_argument('--n-graphs', type=int, default=2000)
 ap.add_argument('--rows', type=int, default=64)
 ap.add_argument('--launches', type=int, default=6)
 ap.add_argument('--block-size', type=int, default=0)
+ap.add_argument('--slots-per-lane', type=int, default=0)
 ap.add_argument('--no-grad', action='store_true')
 ap.add_argument('--nvrtc-extra', default='')
 args = ap.parse_args()
 
 G = make_config_graphs(args.config, args.n_graphs)
 be = B200Backend(block_size=args.block_size or None,
+                 slots_per_lane=args.slots_per_lane or None,
                  nvrtc_extra=args.nvrtc_extra.split())
 kernel = make_config_kernel(args.config, backend=be)
 w = GramTileWorker(kernel, G, be, eval_gradient=not args.no_grad,

@@ -4,9 +4,9 @@ import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(sys.argv[2], d['value'], d['roofline']['kernel'])
 " gpurun_out/sw_$tag.json $tag; }
 run default
-run unroll --nvrtc-extra=-DGDB_K1_UNROLL
-run pred --nvrtc-extra=-DGDB_PRED_SLOTS=1
 run m6 --nvrtc-extra=-DGDB_SMALL_MINB=6
-run m4 --nvrtc-extra=-DGDB_SMALL_MINB=4
+run m7 --nvrtc-extra=-DGDB_SMALL_MINB=7
+run adj4 --slots-per-lane 4
+run adj4_m6 --slots-per-lane 4 --nvrtc-extra=-DGDB_SMALL_MINB=6
 run b160_m4 --block-size 160 --nvrtc-extra=-DGDB_SMALL_MINB=4
-run b192_m3 --block-size 192 --nvrtc-extra=-DGDB_SMALL_MINB=3
+run b160_m5 --block-size 160 --nvrtc-extra=-DGDB_SMALL_MINB=5
