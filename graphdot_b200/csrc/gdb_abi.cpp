@@ -270,12 +270,11 @@ static int render(const gdb_program_desc *d, std::string &src) {
         // small-pair kernel: the per-thread state is rows_per_warp x (x, r, Ap, diag)
         // [float2 with gradients] + ~45 registers of indices and loop state.  The
         // kernel is bound by instruction issue and latency, so more and lighter warps
-        // win: with at most 6 rows per warp ask ptxas for 768 (2 slots per lane) or
-        // 640 (4 slots) threads per SM instead of 512.  Measured on the C3 workload
-        // (M pairs/s): block 96 / 8 rows / 128 regs 12.4; 128 / 6 / 96 regs 16.4;
-        // 128 / 6 / 80 regs 16.9; 72 regs (spills in the CG loop) 11.6.
-        int threads = 512;
-        if (pick_wpt(d) == 1 && pick_rpw(d) <= 6) threads = pick_adj(d) == 2 ? 768 : 640;
+        // win: with at most 6 rows per warp ask ptxas for 640 threads per SM (96
+        // registers, no spills) instead of 512.  Measured on the C3 workload
+        // (M pairs/s): block 96 / 8 rows / 128 regs 12.4; 128 / 6 / 96 regs 17.6;
+        // 128 / 6 / 80 regs (A p spilled) 17.6; 72 regs 11.6.
+        const int threads = (pick_wpt(d) == 1 && pick_rpw(d) <= 6) ? 640 : 512;
         o << "#define GDB_MIN_BLOCKS_SMALL " << std::max(1, threads / block) << "\n";
     }
     o << "#define GDB_WPT " << pick_wpt(d) << "\n";

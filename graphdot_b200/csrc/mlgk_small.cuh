@@ -114,16 +114,38 @@ __device__ __forceinline__ void gdb_mbar_wait(unsigned long long *bar, unsigned 
 }
 
 // Group sum of K <= 4 values at once (one barrier); fixed summation order.
+// Within a warp the K sums share one butterfly: at the first steps every lane
+// passes on half of its values and keeps the other half (6 shuffles for K = 4
+// instead of 20); lane 8 k ends up with the warp total of value k (K = 4), lane
+// 16 k (K = 2).
 template<int K> __device__ __forceinline__ void gdb_group_sum_n(float (&v)[K], float *red, int &flip) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) v[k] = gdb_warp_sum(v[k]);
+    static_assert(K == 1 || K == 2 || K == 4, "gdb_group_sum_n: K must be 1, 2 or 4");
+    const unsigned lane = threadIdx.x & 31u;
+    float keep;
+    if constexpr (K == 4) {
+        const bool hi = lane & 16u;
+        float ka = hi ? v[2] : v[0], kb = hi ? v[3] : v[1];
+        ka += __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[2], 16);
+        kb += __shfl_xor_sync(0xffffffffu, hi ? v[1] : v[3], 16);
+        const bool hi8 = lane & 8u;
+        keep = (hi8 ? kb : ka) + __shfl_xor_sync(0xffffffffu, hi8 ? ka : kb, 8);
+        keep += __shfl_xor_sync(0xffffffffu, keep, 4);
+        keep += __shfl_xor_sync(0xffffffffu, keep, 2);
+        keep += __shfl_xor_sync(0xffffffffu, keep, 1);
+    } else if constexpr (K == 2) {
+        const bool hi = lane & 16u;
+        keep = (hi ? v[K - 1] : v[0]) + __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[K - 1], 16);
+        keep += __shfl_xor_sync(0xffffffffu, keep, 8);
+        keep += __shfl_xor_sync(0xffffffffu, keep, 4);
+        keep += __shfl_xor_sync(0xffffffffu, keep, 2);
+        keep += __shfl_xor_sync(0xffffffffu, keep, 1);
+    } else {
+        keep = gdb_warp_sum(v[0]);
+    }
 #if GDB_BLOCK > 32
     float *buf = red + flip * (GDB_WARPS * 4);
     flip ^= 1;
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) buf[(threadIdx.x >> 5) * 4 + k] = v[k];
-    }
+    if ((lane & (32u / K - 1u)) == 0u) buf[(threadIdx.x >> 5) * 4 + lane / (32u / K)] = keep;
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -133,6 +155,8 @@ template<int K> __device__ __forceinline__ void gdb_group_sum_n(float (&v)[K], f
         v[k] = t;
     }
 #else
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = __shfl_sync(0xffffffffu, keep, k * (32 / K));
     __syncwarp();  // orders the lanes' shared-memory accesses like the barrier above
 #endif
 }
@@ -428,6 +452,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         const int w_rows = (n1 + GDB_WARPS - 1) / GDB_WARPS;
         const int w_row0 = min((int)(threadIdx.x >> 5) * w_rows, n1);
         const int w_row1 = min(w_row0 + w_rows, n1);  // one past this warp's last row
+        const int w_nrow = w_row1 - w_row0;
         // p and W are laid out by lane position, the graph data by node
 #define GDB_POS(s) (lane + 32 * (s))
 #define GDB_LIVE(s) (GDB_POS(s) < n2)
@@ -667,17 +692,15 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             for (int s = 0; s < GDB_WPT; ++s) {
 #pragma unroll
                 for (int r = 0; r < GDB_RPW; ++r) {
-                    const int i1 = w_row0 + r;
-                    if (i1 < w_row1 && GDB_LIVE(s)) {
-                        const gv_t ri = gv_fma2(gv_neg(al), apv[s][r], rv[s][r]);
-                        rv[s][r] = ri;
-                        const float dinv = __fdividef(1.0f, diag[s][r]);
+                    // straight-line code: rows / lanes without an element hold r = A p = 0, diag = 1
+                    const gv_t ri = gv_fma2(gv_neg(al), apv[s][r], rv[s][r]);
+                    rv[s][r] = ri;
+                    const float dinv = __fdividef(1.0f, diag[s][r]);
 #pragma unroll
-                        for (int k = 0; k < GV_N; ++k) {
-                            const float rk = gv_get(ri, k);
-                            sums[2 * k] = fmaf(rk, rk, sums[2 * k]);
-                            sums[2 * k + 1] = fmaf(rk * dinv, rk, sums[2 * k + 1]);
-                        }
+                    for (int k = 0; k < GV_N; ++k) {
+                        const float rk = gv_get(ri, k);
+                        sums[2 * k] = fmaf(rk, rk, sums[2 * k]);
+                        sums[2 * k + 1] = fmaf(rk * dinv, rk, sums[2 * k + 1]);
                     }
                 }
             }
@@ -695,14 +718,14 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             for (int s = 0; s < GDB_WPT; ++s) {
 #pragma unroll
                 for (int r = 0; r < GDB_RPW; ++r) {
-                    const int i1 = w_row0 + r;
-                    if (i1 < w_row1 && GDB_LIVE(s)) {
-                        // x += alpha p rides on the read of p that the update of p needs anyway
-                        gv_t *pp = pbuf + i1 * n2 + GDB_POS(s);
-                        const gv_t pv = *pp;
-                        xv[s][r] = gv_fma2(al, pv, xv[s][r]);
-                        *pp = gv_fma2(be, pv, gv_scale(__fdividef(1.0f, diag[s][r]), rv[s][r]));
-                    }
+                    // x += alpha p rides on the read of p that the update of p needs anyway;
+                    // only the two memory operations are predicated
+                    const bool own = r < w_nrow && GDB_LIVE(s);
+                    gv_t *pp = pbuf + (w_row0 + r) * n2 + GDB_POS(s);
+                    const gv_t pv = own ? *pp : gv_make(0.f, 0.f);
+                    xv[s][r] = gv_fma2(al, pv, xv[s][r]);
+                    const gv_t pn = gv_fma2(be, pv, gv_scale(__fdividef(1.0f, diag[s][r]), rv[s][r]));
+                    if (own) *pp = pn;
                 }
             }
             gdb_group_sync();  // p complete before the next matvec

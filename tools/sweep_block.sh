@@ -4,9 +4,7 @@ import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(sys.argv[2], d['value'], d['roofline']['kernel'])
 " gpurun_out/sw_$tag.json $tag; }
 run default
-run m6 --nvrtc-extra=-DGDB_SMALL_MINB=6
-run m7 --nvrtc-extra=-DGDB_SMALL_MINB=7
+run m5 --nvrtc-extra=-DGDB_SMALL_MINB=5
+run default2
+run m5b --nvrtc-extra=-DGDB_SMALL_MINB=5
 run adj4 --slots-per-lane 4
-run adj4_m6 --slots-per-lane 4 --nvrtc-extra=-DGDB_SMALL_MINB=6
-run b160_m4 --block-size 160 --nvrtc-extra=-DGDB_SMALL_MINB=4
-run b160_m5 --block-size 160 --nvrtc-extra=-DGDB_SMALL_MINB=5
