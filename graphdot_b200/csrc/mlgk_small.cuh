@@ -197,6 +197,37 @@ __device__ __forceinline__ float4 gdb_lds_f4(unsigned addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+// predicated variants: a lane whose predicate is off issues no request; the load returns zeros
+__device__ __forceinline__ gv_t gdb_lds_gv_if(unsigned addr, bool on) {
+#if GDB_GRADIENT
+    float x = 0.f, y = 0.f;
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %3, 0; @q ld.shared.v2.f32 {%0, %1}, [%2]; }"
+                 : "+f"(x), "+f"(y)
+                 : "r"(addr), "r"((unsigned)on));
+    return make_float2(x, y);
+#else
+    float x = 0.f;
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q ld.shared.f32 %0, [%1]; }" : "+f"(x) : "r"(addr), "r"((unsigned)on));
+    return x;
+#endif
+}
+__device__ __forceinline__ void gdb_sts_gv_if(unsigned addr, gv_t v, bool on) {
+#if GDB_GRADIENT
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %3, 0; @q st.shared.v2.f32 [%0], {%1, %2}; }" ::"r"(addr), "f"(v.x), "f"(v.y),
+                 "r"((unsigned)on)
+                 : "memory");
+#else
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.f32 [%0], %1; }" ::"r"(addr), "f"(v), "r"((unsigned)on)
+                 : "memory");
+#endif
+}
+// An address the compiler must keep in a register: without this it re-derives
+// the shared-memory layout (~20 uniform instructions) at every single access.
+__device__ __forceinline__ unsigned gdb_opaque(unsigned x) {
+    unsigned y;
+    asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
 __device__ __forceinline__ uint2 gdb_lds_u2(unsigned addr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
@@ -390,7 +421,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #endif
         const unsigned W_sa = (unsigned)__cvta_generic_to_shared(W);  // shared-window addresses
         const unsigned p_sa = (unsigned)__cvta_generic_to_shared(pbuf);
-        const unsigned ktab_sa = (unsigned)__cvta_generic_to_shared(ktab);
+        const unsigned ktab_sa = gdb_opaque((unsigned)__cvta_generic_to_shared(ktab));
         const int lane = (int)(threadIdx.x & 31);
 
         // ---- lane tables (warp 0).  Lane position pos < n2 owns the column lanemap[pos]
@@ -456,6 +487,15 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         // p and W are laid out by lane position, the graph data by node
 #define GDB_POS(s) (lane + 32 * (s))
 #define GDB_LIVE(s) (GDB_POS(s) < n2)
+        // this thread's elements of p: row r of slot s at w_psa[s] + r * w_prow, valid for r < w_nown[s]
+        const unsigned w_prow = gdb_opaque((unsigned)n2 * (unsigned)sizeof(gv_t));
+        unsigned w_psa[GDB_WPT];
+        int w_nown[GDB_WPT];
+#pragma unroll
+        for (int s = 0; s < GDB_WPT; ++s) {
+            w_psa[s] = gdb_opaque(p_sa + (unsigned)(w_row0 * n2 + GDB_POS(s)) * (unsigned)sizeof(gv_t));
+            w_nown[s] = GDB_LIVE(s) ? w_nrow : 0;
+        }
         // The heavy per-element work (node kernel, Jacobians, the matvec) runs in
         // ROLLED loops over the rows and hands its results to / from the row registers
         // through shared memory: the register arrays need compile-time indices, but
@@ -571,18 +611,15 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         gdb_group_sync();  // W, the step table and p complete
 
         // ---- Jacobi-PCG, both systems at once ---------------------------------------
-        const float thresh = F.ftol * (float)N;
-        bool active[GV_N];
+        // stop when sqrt(r.r) < ftol N  <=>  r.r < (ftol N)^2; bit k of `active`: system k runs
+        const float thresh2 = (F.ftol * (float)N) * (F.ftol * (float)N);
+        unsigned active = 0u;
 #pragma unroll
-        for (int k = 0; k < GV_N; ++k) active[k] = rho[k] != 0.f;
+        for (int k = 0; k < GV_N; ++k) active |= (rho[k] != 0.f ? 1u : 0u) << k;
         int iters = 0;  // summed over the systems that were still active
         for (int it = 0; it < N; ++it) {
-            bool any = false;
-#pragma unroll
-            for (int k = 0; k < GV_N; ++k) any |= active[k];
-            if (!any) break;
-#pragma unroll
-            for (int k = 0; k < GV_N; ++k) iters += active[k] ? 1 : 0;
+            if (active == 0u) break;
+            iters += __popc(active);
 
             // matvec: W p of every owned element, one row of G1 at a time
             auto row_wp = [&](int i1, gv_t (&acc)[GDB_WPT]) {
@@ -627,13 +664,21 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
                                                                        (1u + (w_help[s] >> 16)) * (unsigned)GDB_ADJ));
                 }
                 // helpers hand their partial sums to the owning lane (fixed order)
-#pragma unroll 1
-                for (unsigned h = 0; h < w_most; ++h) {  // uniform per pair; 0 when no column has helpers
+                if (w_most == 1u) {  // uniform per pair: the common case of molecular graphs, no loop
 #pragma unroll
                     for (int s = 0; s < GDB_WPT; ++s) {
-                        const unsigned src = (w_help[s] & 0xffffu) + h;
-                        const gv_t t = gdb_shfl_vlane(acc, src);
-                        if (h < (w_help[s] >> 16)) acc[s] = gv_add(acc[s], t);
+                        const gv_t t = gdb_shfl_vlane(acc, w_help[s] & 0xffffu);
+                        if (w_help[s] >> 16) acc[s] = gv_add(acc[s], t);
+                    }
+                } else {
+#pragma unroll 1
+                    for (unsigned h = 0; h < w_most; ++h) {  // 0 trips when no column has helpers
+#pragma unroll
+                        for (int s = 0; s < GDB_WPT; ++s) {
+                            const unsigned src = (w_help[s] & 0xffffu) + h;
+                            const gv_t t = gdb_shfl_vlane(acc, src);
+                            if (h < (w_help[s] >> 16)) acc[s] = gv_add(acc[s], t);
+                        }
                     }
                 }
             };
@@ -662,18 +707,18 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #endif
 #pragma unroll
                     for (int s = 0; s < GDB_WPT; ++s) {
-                        if (GDB_LIVE(s)) {
+                        // no branch: lanes without an element (idle or helper lanes) get p = W p = 0
+                        const bool own = r < w_nown[s];
 #if GDB_ROLL_ROWS
-                            const gv_t wp = wpbuf[i1 * n2 + GDB_POS(s)];
+                        const gv_t wp = own ? wpbuf[i1 * n2 + GDB_POS(s)] : gv_make(0.f, 0.f);
 #else
-                            const gv_t wp = acc[s];
+                        const gv_t wp = own ? acc[s] : gv_make(0.f, 0.f);
 #endif
-                            const gv_t pv = pbuf[i1 * n2 + GDB_POS(s)];
-                            const gv_t av = gv_fma2(gv_make(diag[s][r], diag[s][r]), pv, gv_neg(wp));
-                            apv[s][r] = av;
+                        const gv_t pv = gdb_lds_gv_if(w_psa[s] + (unsigned)r * w_prow, own);
+                        const gv_t av = gv_fma2(gv_make(diag[s][r], diag[s][r]), pv, gv_neg(wp));
+                        apv[s][r] = av;
 #pragma unroll
-                            for (int k = 0; k < GV_N; ++k) pAp[k] = fmaf(gv_get(pv, k), gv_get(av, k), pAp[k]);
-                        }
+                        for (int k = 0; k < GV_N; ++k) pAp[k] = fmaf(gv_get(pv, k), gv_get(av, k), pAp[k]);
                     }
                 }
             }
@@ -681,8 +726,8 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             float alpha[GV_N];
 #pragma unroll
             for (int k = 0; k < GV_N; ++k) {
-                if (pAp[k] == 0.f) active[k] = false;
-                alpha[k] = active[k] ? __fdividef(rho[k], pAp[k]) : 0.f;
+                if (pAp[k] == 0.f) active &= ~(1u << k);
+                alpha[k] = (active >> k) & 1u ? __fdividef(rho[k], pAp[k]) : 0.f;
             }
             const gv_t al = gv_make(alpha[0], alpha[GV_N - 1]);
             float sums[2 * GV_N];
@@ -708,10 +753,11 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             float beta[GV_N];
 #pragma unroll
             for (int k = 0; k < GV_N; ++k) {
-                if (active[k] && sqrtf(sums[2 * k]) < thresh) active[k] = false;
-                beta[k] = active[k] ? __fdividef(sums[2 * k + 1], rho[k]) : 0.f;
-                if (active[k]) rho[k] = sums[2 * k + 1];
-                if (rho[k] == 0.f) active[k] = false;
+                if (sums[2 * k] < thresh2) active &= ~(1u << k);
+                const bool on = (active >> k) & 1u;
+                beta[k] = on ? __fdividef(sums[2 * k + 1], rho[k]) : 0.f;
+                rho[k] = on ? sums[2 * k + 1] : rho[k];
+                if (rho[k] == 0.f) active &= ~(1u << k);
             }
             const gv_t be = gv_make(beta[0], beta[GV_N - 1]);
 #pragma unroll
@@ -720,12 +766,11 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
                 for (int r = 0; r < GDB_RPW; ++r) {
                     // x += alpha p rides on the read of p that the update of p needs anyway;
                     // only the two memory operations are predicated
-                    const bool own = r < w_nrow && GDB_LIVE(s);
-                    gv_t *pp = pbuf + (w_row0 + r) * n2 + GDB_POS(s);
-                    const gv_t pv = own ? *pp : gv_make(0.f, 0.f);
+                    const bool own = r < w_nown[s];
+                    const unsigned pa = w_psa[s] + (unsigned)r * w_prow;
+                    const gv_t pv = gdb_lds_gv_if(pa, own);
                     xv[s][r] = gv_fma2(al, pv, xv[s][r]);
-                    const gv_t pn = gv_fma2(be, pv, gv_scale(__fdividef(1.0f, diag[s][r]), rv[s][r]));
-                    if (own) *pp = pn;
+                    gdb_sts_gv_if(pa, gv_fma2(be, pv, gv_scale(__fdividef(1.0f, diag[s][r]), rv[s][r])), own);
                 }
             }
             gdb_group_sync();  // p complete before the next matvec
