@@ -422,7 +422,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         const unsigned W_sa = (unsigned)__cvta_generic_to_shared(W);  // shared-window addresses
         const unsigned p_sa = (unsigned)__cvta_generic_to_shared(pbuf);
         const unsigned ktab_sa = gdb_opaque((unsigned)__cvta_generic_to_shared(ktab));
-        const int lane = (int)(threadIdx.x & 31);
+        const int lane = (int)gdb_opaque(threadIdx.x & 31u);  // kept in a register (S2R is slow)
 
         // ---- lane tables (warp 0).  Lane position pos < n2 owns the column lanemap[pos]
         //      of G2 (degree-sorted) and its first GDB_ADJ neighbour slots.  A column
@@ -494,7 +494,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll
         for (int s = 0; s < GDB_WPT; ++s) {
             w_psa[s] = gdb_opaque(p_sa + (unsigned)(w_row0 * n2 + GDB_POS(s)) * (unsigned)sizeof(gv_t));
-            w_nown[s] = GDB_LIVE(s) ? w_nrow : 0;
+            w_nown[s] = (int)gdb_opaque((unsigned)(GDB_LIVE(s) ? w_nrow : 0));
         }
         // The heavy per-element work (node kernel, Jacobians, the matvec) runs in
         // ROLLED loops over the rows and hands its results to / from the row registers
@@ -664,15 +664,16 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
                                                                        (1u + (w_help[s] >> 16)) * (unsigned)GDB_ADJ));
                 }
                 // helpers hand their partial sums to the owning lane (fixed order)
-                if (w_most == 1u) {  // uniform per pair: the common case of molecular graphs, no loop
+                // (the first exchange is unconditional -- lanes without a helper add nothing --
+                // so that the common case of molecular graphs, one helper at most, has no loop)
 #pragma unroll
-                    for (int s = 0; s < GDB_WPT; ++s) {
-                        const gv_t t = gdb_shfl_vlane(acc, w_help[s] & 0xffffu);
-                        if (w_help[s] >> 16) acc[s] = gv_add(acc[s], t);
-                    }
-                } else {
+                for (int s = 0; s < GDB_WPT; ++s) {
+                    const gv_t t = gdb_shfl_vlane(acc, w_help[s] & 0xffffu);
+                    if (w_help[s] >> 16) acc[s] = gv_add(acc[s], t);
+                }
+                if (w_most > 1u) {  // uniform per pair
 #pragma unroll 1
-                    for (unsigned h = 0; h < w_most; ++h) {  // 0 trips when no column has helpers
+                    for (unsigned h = 1; h < w_most; ++h) {
 #pragma unroll
                         for (int s = 0; s < GDB_WPT; ++s) {
                             const unsigned src = (w_help[s] & 0xffffu) + h;
