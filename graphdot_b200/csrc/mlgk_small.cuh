@@ -629,8 +629,9 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #if !defined(GDB_K1_UNROLL)
 #pragma unroll 1  // the body is replicated per row already: keep the code in the instruction cache
 #endif
-                for (unsigned k1 = k1beg; k1 < k1end; ++k1) {  // warp-uniform trip count
-                    const uint2 step = gdb_lds_u2(ktab_sa + k1 * 8u);  // (W row, p row)
+                const unsigned ka_end = ktab_sa + k1end * 8u;
+                for (unsigned ka = ktab_sa + k1beg * 8u; ka != ka_end; ka += 8u) {  // warp-uniform trip count
+                    const uint2 step = gdb_lds_u2(ka);  // (W row, p row)
 #pragma unroll
                     for (int s = 0; s < GDB_WPT; ++s) {
                         // All lanes load: empty slots hold W = 0 and point at position 0
@@ -708,12 +709,13 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #endif
 #pragma unroll
                     for (int s = 0; s < GDB_WPT; ++s) {
-                        // no branch: lanes without an element (idle or helper lanes) get p = W p = 0
+                        // no branch: lanes without an element (idle or helper lanes) get p = 0, and
+                        // whatever their A p is, the update of r below multiplies it by zero
                         const bool own = r < w_nown[s];
 #if GDB_ROLL_ROWS
                         const gv_t wp = own ? wpbuf[i1 * n2 + GDB_POS(s)] : gv_make(0.f, 0.f);
 #else
-                        const gv_t wp = own ? acc[s] : gv_make(0.f, 0.f);
+                        const gv_t wp = acc[s];
 #endif
                         const gv_t pv = gdb_lds_gv_if(w_psa[s] + (unsigned)r * w_prow, own);
                         const gv_t av = gv_fma2(gv_make(diag[s][r], diag[s][r]), pv, gv_neg(wp));
@@ -731,6 +733,9 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
                 alpha[k] = (active >> k) & 1u ? __fdividef(rho[k], pAp[k]) : 0.f;
             }
             const gv_t al = gv_make(alpha[0], alpha[GV_N - 1]);
+            gv_t nal[GDB_WPT];  // -alpha for the lanes that own elements
+#pragma unroll
+            for (int s = 0; s < GDB_WPT; ++s) nal[s] = w_nown[s] > 0 ? gv_neg(al) : gv_make(0.f, 0.f);
             float sums[2 * GV_N];
 #pragma unroll
             for (int k = 0; k < 2 * GV_N; ++k) sums[k] = 0.f;
@@ -738,8 +743,9 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             for (int s = 0; s < GDB_WPT; ++s) {
 #pragma unroll
                 for (int r = 0; r < GDB_RPW; ++r) {
-                    // straight-line code: rows / lanes without an element hold r = A p = 0, diag = 1
-                    const gv_t ri = gv_fma2(gv_neg(al), apv[s][r], rv[s][r]);
+                    // straight-line code: rows without an element hold r = A p = 0, diag = 1;
+                    // lanes without elements use alpha = 0
+                    const gv_t ri = gv_fma2(nal[s], apv[s][r], rv[s][r]);
                     rv[s][r] = ri;
                     const float dinv = __fdividef(1.0f, diag[s][r]);
 #pragma unroll
