@@ -4,7 +4,9 @@ import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(sys.argv[2], d['value'], d['roofline']['kernel'])
 " gpurun_out/sw_$tag.json $tag; }
 run default
-run m5 --nvrtc-extra=-DGDB_SMALL_MINB=5
-run default2
-run m5b --nvrtc-extra=-DGDB_SMALL_MINB=5
+run m6 --nvrtc-extra=-DGDB_SMALL_MINB=6
+run m4 --nvrtc-extra=-DGDB_SMALL_MINB=4
+run b160_m4 --block-size 160 --nvrtc-extra=-DGDB_SMALL_MINB=4
+run b96_m6 --block-size 96 --nvrtc-extra=-DGDB_SMALL_MINB=6
+run b96_m5 --block-size 96 --nvrtc-extra=-DGDB_SMALL_MINB=5
 run adj4 --slots-per-lane 4
