@@ -7,38 +7,48 @@
 // graphdot/cpp/marginalized_kernel.h:189-490 (compute), :492-804
 // (compute_duo) and :806-997 (derivative) for pairs in this regime.
 //
-// Design:
+// Design (measurements and the variants that lost: DESIGN.md sections 4.1, 10):
 //  * W = w1 w2 kE(e1, e2) is evaluated ONCE per pair for all nnz1 x nnz2
-//    element pairs (balanced, divergence-free) into shared memory, with one
-//    extra zero column so that padded adjacency slots need no predicate.  The
-//    reference re-evaluates the edge microkernel for every product in every CG
-//    iteration (marginalized_kernel.h:299-300, :346).
-//  * workers = (block of <= GDB_RPW rows of G1, dealt evenly to the warps) x
+//    element pairs (balanced, divergence-free) into shared memory, zero where a
+//    lane has fewer neighbours than slots, so that the matvec needs no
+//    predicates.  The reference re-evaluates the edge microkernel for every
+//    product in every CG iteration (marginalized_kernel.h:299-300, :346).
+//  * workers = (block of <= GDB_RPW rows of G1, dealt evenly to ALL warps) x
 //    (column of G2 = lane), one or a few per thread.  A worker owns the
 //    product-graph elements (its rows, its column): their x, r, A p and diagonal
 //    live in REGISTERS for the whole solve; only the search direction p, which
-//    neighbours gather, is in shared memory.  The first GDB_ADJ neighbours of
-//    the column are held in registers as byte offsets, so one matvec product is
-//        LDS.128 W[row + off], 4 x LDS p[row' + off'_k], FMA (x2 with gradients).
+//    neighbours gather, is in shared memory.
+//  * virtual lanes: lane position p < n2 owns the column lane_map[p] of G2 (the
+//    packer's degree-sorted order, gdb_pack.cpp) and its first GDB_ADJ neighbour
+//    slots, kept in registers as byte offsets; a column with more neighbours gets
+//    HELPER lanes (n2, n2 + 1, ...: the lanes a warp would otherwise idle), one
+//    per further chunk of GDB_ADJ slots, and receives their partial sums by one
+//    shuffle per row.  What finds no lane (rare) is a compact overflow region
+//    walked by the owner.  One matvec step is
+//        LDS.64 step table (W row, p row), LDS.64/128 W, GDB_ADJ x LDS p, FMAs.
 //    No atomics, fixed summation order => bit-reproducible.
-//  * lanes follow the packer's degree-sorted lane map (gdb_pack.cpp): lane l
-//    owns the node with the l-th largest degree, p and W are laid out by that
-//    position.  The gathers of neighbour slot k are predicated on degree > k,
-//    so slots 1..3 touch only the low lanes: one shared-memory wavefront
-//    instead of two per 64-bit gather for typical molecular graphs.
-//  * K and its Jacobian are symmetric in the two graphs, so per pair the
-//    larger graph provides the columns and the smaller one the rows.
+//  * K and its Jacobian are symmetric in the two graphs, so per pair the graph
+//    whose virtual columns fit the lanes (then the larger one) provides the
+//    columns and the other one the rows.
 //  * with gradients the value system (rhs Dx) and the adjoint system (rhs
 //    p1 (x) p2) are solved together on float2 data: one W load and one 64-bit
 //    load feed two FMAs.  Each system has its own CG scalars and convergence
 //    flag (the reference shares alpha/beta between the stacked systems,
 //    marginalized_kernel.h:721-772).
-//  * three barriers per CG iteration (two reductions + publish p); the dot
-//    products are warp-shuffle trees joined through a double-buffered
-//    shared-memory slot.
+//  * three barriers per CG iteration (two reductions + publish p); the K dot
+//    products of a reduction share one shuffle butterfly and are joined through
+//    a double-buffered shared-memory slot.
+//  * the next pair's blobs are prefetched by TMA bulk copies (cp.async.bulk +
+//    mbarrier, double buffered) while the current pair is solved.
+//  * the kernel is bound by instruction issue and shared-memory latency, and its
+//    CG loop must stay inside the instruction cache: heavy one-time code (node
+//    kernel, Jacobians) runs in rolled loops that talk to the row registers
+//    through shared memory, rare paths are out of line, and addresses that the
+//    compiler would re-derive at every access are pinned in registers.
 //
-// Extra macro from the generated header: GDB_WPT (workers per thread, so that
-// GDB_BLOCK * GDB_WPT >= max tile rows * max nodes of the graph set).
+// Macros from the generated header: GDB_BLOCK, GDB_WPT (workers per thread:
+// 32 * GDB_WPT >= nodes), GDB_RPW (rows per warp: GDB_RPW * warps >= nodes),
+// GDB_ADJ (neighbour slots per lane, 2 or 4), GDB_MIN_BLOCKS_SMALL.
 #pragma once
 
 #ifndef GDB_RPW

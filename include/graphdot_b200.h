@@ -142,12 +142,18 @@ void gdb_free(void *p);
  * Replaces OctileGraph (reference _octilegraph.py:11-189) and graph_t
  * (reference graphdot/cpp/graph.h:8-33).  A packed graph is ONE
  * position-independent, 16-byte aligned blob
- *   [header | degree f32[n] | node_t[n] | octile[n_oct] | tile_row u32[T+1]
- *    | edge_t[nnz] | variable-length feature pool]
+ *   [header 80 B | degree f32[n] | node_t[n] | octile[n_oct]
+ *    | tile_row u32[T+1] | edge_t[nnz]
+ *    | elem_meta u32[nnz] | row_ptr u32[n+1] | row_adj u32[nnz]
+ *    | tile_elem u32[T+1] | row_pos u32[nnz] | lane_map u32[n]
+ *    | variable-length feature pool]
  * with 8x8 octiles sorted by (tile row, tile column), a row-major 64-bit
  * non-zero mask per octile and compact row-major elements.  Degrees are the
  * sums of incident weights (self loops once), 0 replaced by 1 (reference
- * _octilegraph.py:113-139). */
+ * _octilegraph.py:113-139).  elem_meta .. lane_map are a pair-independent row
+ * index derived from the octiles at pack time (CSR over rows, degree-sorted
+ * lane map; layout in csrc/gdb_internal.h and DESIGN.md section 3), so that
+ * the solver kernels never decode bit masks in their hot loops. */
 typedef struct gdb_graph_src {
     uint32_t n_node;
     uint32_t n_edge;          /* undirected edges                          */
