@@ -597,8 +597,11 @@ extern "C" int gdb_graphset_destroy(gdb_graphset_t gs) {
 extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gdb_solve_args *a) {
     if (!c || !p || !gs || !a) return gdb_fail(GDB_ERR_INVALID, "gdb_solve: null argument");
     if (p->ctx != c || gs->ctx != c) return gdb_fail(GDB_ERR_INVALID, "program / graph set belong to another context");
-    if (!a->starts || !a->gramian) return gdb_fail(GDB_ERR_INVALID, "gdb_solve: starts and gramian are required");
-    if (p->eval_gradient && !a->gradient) return gdb_fail(GDB_ERR_INVALID, "program evaluates gradients: gradient buffer required");
+    if (!a->starts) return gdb_fail(GDB_ERR_INVALID, "gdb_solve: starts is required");
+    // host output buffers are only needed when the results are copied back
+    if (!a->keep_on_device && !a->gramian) return gdb_fail(GDB_ERR_INVALID, "gdb_solve: gramian buffer required");
+    if (!a->keep_on_device && p->eval_gradient && !a->gradient)
+        return gdb_fail(GDB_ERR_INVALID, "program evaluates gradients: gradient buffer required");
     if (p->eval_gradient && a->nJ != p->layout[7])
         return gdb_fail(GDB_ERR_INVALID, "nJ = %u but the program has %u hyper-parameters", a->nJ, p->layout[7]);
     uint64_t n_jobs = 0;

@@ -21,6 +21,12 @@ class Normalization:
                 return out
         return self._host_normalized(X, Y, eval_gradient, **options)
 
+    def device_gram(self, X, Y=None, eval_gradient=False, **options):
+        """Normalized Gram matrix (and Jacobian) as device-resident torch
+        tensors (see ``MarginalizedGraphKernel.device_gram``)."""
+        return self.kernel.device_gram(X, Y, eval_gradient=eval_gradient,
+                                       normalize=True, **options)
+
     def _host_normalized(self, X, Y=None, eval_gradient=False, **options):
         if eval_gradient is True:
             R, dR = self.kernel(X, Y, eval_gradient=True, **options)

@@ -524,7 +524,7 @@ class B200Backend(Backend):
                 for b in blobs]
         a.node_theta, a.edge_theta, a.p_theta = [
             C.cast(b, C.c_void_p) if b is not None else None for b in bufs]
-        a.gramian = gramian.ctypes.data
+        a.gramian = gramian.ctypes.data if gramian is not None else None
         a.gradient = gradient.ctypes.data if gradient is not None else None
         a.nX, a.nY, a.nJ = int(nX), int(nY), int(nJ)
         a.stream = stream
@@ -539,6 +539,35 @@ class B200Backend(Backend):
                          small_kernel=bool(a.used_small_kernel), grid=a.grid,
                          smem_bytes=a.smem_bytes)
         return a
+
+
+    def device_outputs(self, rows, cols, n_jac=0):
+        """The Gram matrix (and Jacobian) of the most recent solve as torch
+        CUDA tensors, copied device-to-device out of the engine's output
+        buffers (``keep_on_device=True`` solves leave them there): shapes
+        (rows, cols) and (rows, cols, n_jac), float32.  This is what lets a
+        caller such as the GPR training loop (reference
+        model/gaussian_process/gpr.py:259-296) keep the 4 (1 + nJ) bytes per
+        pair off the PCIe bus."""
+        import torch
+        g, d = C.c_void_p(), C.c_void_p()
+        native.check(native.load().gdb_last_outputs(self.context, C.byref(g),
+                                                    C.byref(d)))
+
+        class _View:      # engine memory through the CUDA array interface
+            def __init__(self, ptr, shape):
+                self.__cuda_array_interface__ = dict(
+                    shape=shape, typestr='<f4', data=(ptr, False), version=3,
+                    strides=None)
+
+        dev = torch.device('cuda', self.device)
+        # Fortran order [r + c rows (+ k rows cols)] = C order (k, c, r)
+        K = torch.as_tensor(_View(g.value, (cols, rows)), device=dev)
+        K = K.clone().t()
+        if not n_jac:
+            return K, None
+        dK = torch.as_tensor(_View(d.value, (n_jac, cols, rows)), device=dev)
+        return K, dK.clone().permute(2, 1, 0)
 
 
 # --------------------------------------------------------------------------

@@ -134,8 +134,20 @@ class MarginalizedGraphKernel:
         return self.__call__(X, Y, eval_gradient=eval_gradient, lmin=lmin,
                              timing=timing, _fused_normalization=True)
 
+    def device_gram(self, X, Y=None, eval_gradient=False, lmin=0,
+                    normalize=False):
+        """Graph-level Gram matrix (and Jacobian) as float32 torch CUDA
+        tensors that never visit the host -- for callers that continue on the
+        device, e.g. ``graphdot_b200.model.gaussian_process``.  ``normalize``
+        fuses K_ij / sqrt(K_ii K_jj) into the solve."""
+        if not hasattr(self.backend, 'device_outputs'):
+            raise NotImplementedError('back end has no device-resident outputs')
+        return self.__call__(X, Y, eval_gradient=eval_gradient, lmin=lmin,
+                             _fused_normalization=bool(normalize),
+                             _device=True)
+
     def __call__(self, X, Y=None, eval_gradient=False, nodal=False, lmin=0,
-                 timing=False, _fused_normalization=False):
+                 timing=False, _fused_normalization=False, _device=False):
         """Pairwise similarity matrix between the graphs in ``X`` (and ``Y``).
 
         Returns the (len(X), len(Y)) matrix -- node-by-node if ``nodal`` --
@@ -184,9 +196,12 @@ class MarginalizedGraphKernel:
             else:
                 starts[nx:] = np.arange(ny + 1)
             rows, cols = nx, ny
-        gramian = backend.empty(rows * cols, np.float32)
-        gradient = (backend.empty(self.n_dims * rows * cols, np.float32)
-                    if traits.eval_gradient is True else None)
+        if _device:     # results stay in the engine's device buffers
+            gramian = gradient = None
+        else:
+            gramian = backend.empty(rows * cols, np.float32)
+            gradient = (backend.empty(self.n_dims * rows * cols, np.float32)
+                        if traits.eval_gradient is True else None)
         timer.toc('creating output buffer')
 
         timer.tic('calling GPU kernel (overall)')
@@ -208,10 +223,22 @@ class MarginalizedGraphKernel:
                                 eval_gradient=eval_gradient),
                     timer, store_diag=True, keep_on_device=True)
             extra['normalize'] = True   # ... and scale the main solve
+        if _device:
+            extra['keep_on_device'] = True
         backend(graphs, self.node_kernel, self.edge_kernel, self.p, self.q,
                 self.eps, self.ftol, self.gtol, jobs, starts, gramian,
                 gradient, rows, cols, self.n_dims, traits, timer, **extra)
         timer.toc('calling GPU kernel (overall)')
+
+        if _device:
+            K, dK = backend.device_outputs(
+                rows, cols, self.n_dims if traits.eval_gradient is True else 0)
+            if dK is None:
+                return K
+            import torch
+            mask = torch.as_tensor(np.asarray(self.active_theta_mask),
+                                   device=dK.device)
+            return K, dK[:, :, mask]
 
         timer.tic('collecting result')
         gramian = gramian.reshape(rows, cols, order='F')
