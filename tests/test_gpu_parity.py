@@ -582,3 +582,27 @@ def test_helper_lanes_and_overflow_vs_oracle(slots, p_edge):
     Kno = oracle.gram(G[:3], knode=kernel.node_kernel,
                       kedge=kernel.edge_kernel, q=0.2, nodal=True)
     assert np.allclose(Kn, Kno, rtol=GRAM_RTOL, atol=1e-7)
+
+
+@pytest.mark.parametrize('lmin', [0, 1])
+def test_rectangular_blocks_with_role_choice_vs_oracle(backend, lmin):
+    """X x Y blocks whose pairs need both role assignments (the smaller graph
+    provides the rows): values, Jacobian and starting-probability Jacobian
+    against the oracle; K(X, Y) = K(Y, X)^T."""
+    from graphdot_b200.synthetic import random_molecule
+    rng = np.random.default_rng(23 + lmin)
+    X = [random_molecule(rng, n) for n in (24, 6, 17, 9)]
+    Y = [random_molecule(rng, n) for n in (8, 23, 16, 3, 12)]
+    kernel = make_config_kernel('C2', backend=backend, q=0.1)
+    K, dK = kernel(X, Y, eval_gradient=True, lmin=lmin)
+    Ko, dKo = oracle.gram(X, Y, knode=kernel.node_kernel,
+                          kedge=kernel.edge_kernel, q=0.1, lmin=lmin,
+                          eval_gradient=True)
+    assert np.allclose(K, Ko, rtol=GRAM_RTOL)
+    dKo = dKo[:, :, kernel.active_theta_mask]
+    for k in range(dK.shape[2]):
+        assert np.abs(dK[:, :, k] - dKo[:, :, k]).max() \
+            < GRAD_RTOL * np.abs(dKo[:, :, k]).max()
+    Kt, dKt = kernel(Y, X, eval_gradient=True, lmin=lmin)
+    assert np.allclose(Kt.T, K, rtol=2e-6)
+    assert np.allclose(np.swapaxes(dKt, 0, 1), dK, rtol=2e-5, atol=1e-6)
