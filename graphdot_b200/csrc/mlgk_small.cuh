@@ -604,18 +604,26 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             wslot[k2] = at;
         }
 
-        // ---- W = w1 w2 kE(e1, e2), once per pair: zero fill, then one balanced pass
-        //      over the nnz1 x nnz2 real element pairs (both in row order) ------------
+        // ---- W = w1 w2 kE(e1, e2), once per pair: zero fill, then one pass over the
+        //      nnz1 x nnz2 real element pairs.  The element-pair passes (here and the
+        //      edge Jacobian in the epilogue) split the CTA into groups of ep_gs
+        //      threads over the elements of G2 (the smallest power-of-two multiple of
+        //      32 that divides the block and covers nnz2), the groups share out G1. ---
+        unsigned ep_gs = 32u;
+        while (ep_gs < (unsigned)nnz2 && ep_gs * 2u <= (unsigned)GDB_BLOCK && (unsigned)GDB_BLOCK % (ep_gs * 2u) == 0u) ep_gs *= 2u;
+        const unsigned ep_ng = (unsigned)GDB_BLOCK / ep_gs, ep_grp = threadIdx.x / ep_gs, ep_lane = threadIdx.x % ep_gs;
         {
             float4 *W4 = reinterpret_cast<float4 *>(W);
             for (int idx = threadIdx.x; idx < (nnz1 * wstride) / 4; idx += GDB_BLOCK) W4[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
             gdb_group_sync();
-            const float inv = __frcp_rn((float)nnz2);
-            for (unsigned idx = threadIdx.x; idx < (unsigned)(nnz1 * nnz2); idx += GDB_BLOCK) {
-                unsigned k1, k2;
-                gdb_divmod(idx, (unsigned)nnz2, inv, k1, k2);
-                W[k1 * wstride + wslot[k2]] =
-                    gdb_edge_value(P, g1.edge[g1.rowadj[k1] >> 16], g2.edge[g2.rowadj[k2] >> 16]);
+            // a thread keeps ONE element of G2 (edge, slot) in registers and walks
+            // the elements of G1 that its group is dealt: no index arithmetic and
+            // one broadcast load per product
+            for (unsigned k2 = ep_lane; k2 < (unsigned)nnz2; k2 += ep_gs) {
+                const edge_t e2 = g2.edge[g2.rowadj[k2] >> 16];
+                float *Wk = W + wslot[k2];
+                for (unsigned k1 = ep_grp; k1 < (unsigned)nnz1; k1 += ep_ng)
+                    Wk[k1 * (unsigned)wstride] = gdb_edge_value(P, g1.edge[g1.rowadj[k1] >> 16], e2);
             }
         }
         gdb_group_sync();  // W, the step table and p complete
@@ -926,16 +934,15 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             float eacc[GDB_NE];
 #pragma unroll
             for (int m = 0; m < GDB_NE; ++m) eacc[m] = 0.f;
-            {
-                const float inv = __frcp_rn((float)nnz2);
-                for (unsigned idx = threadIdx.x; idx < (unsigned)(nnz1 * nnz2); idx += GDB_BLOCK) {
-                    unsigned e1, e2;
-                    gdb_divmod(idx, (unsigned)nnz2, inv, e1, e2);
-                    const unsigned m1 = g1.emeta[e1], m2 = g2.emeta[e2];
-                    const float yi = gv_get(xs[(m1 & 0xffffu) * n2 + (m2 & 0xffffu)], 1);
-                    float xj = gv_get(xs[(m1 >> 16) * n2 + (m2 >> 16)], 0);
+            for (unsigned e2 = ep_lane; e2 < (unsigned)nnz2; e2 += ep_gs) {  // element of G2 in registers
+                const unsigned m2 = g2.emeta[e2];
+                const edge_t b = g2.edge[e2];
+                const gv_t *xs_y = xs + (m2 & 0xffffu), *xs_x = xs + (m2 >> 16);
+                for (unsigned e1 = ep_grp; e1 < (unsigned)nnz1; e1 += ep_ng) {
+                    const unsigned m1 = g1.emeta[e1];
+                    const float yi = gv_get(xs_y[(m1 & 0xffffu) * n2], 1);
+                    float xj = gv_get(xs_x[(m1 >> 16) * n2], 0);
                     const edge_t &a = g1.edge[e1];
-                    const edge_t &b = g2.edge[e2];
 #if GDB_WEIGHTED
                     xj *= a.weight * b.weight;
 #endif
