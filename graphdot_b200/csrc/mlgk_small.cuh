@@ -567,6 +567,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         // aligned 64/128-bit load, and W rows are visited with a constant stride.
         const unsigned nvl = vinfo[0], w_most = vinfo[1];
         const bool w_ovf = vinfo[2] != 0u;
+        const bool w_rare = w_ovf || w_most > 1u;
         const unsigned ovf0 = (nvl * (unsigned)GDB_ADJ + 3u) & ~3u;
         const int wstride = (int)(ovf0 + ((vinfo[2] + 3u) & ~3u));  // floats per W row
         unsigned w_woff[GDB_WPT];           // byte offset of the lane's slots in a W row
@@ -673,24 +674,15 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #endif
                     }
                 }
-                if (w_ovf) {  // rare, uniform per pair: slots that found no helper lane
-#pragma unroll
-                    for (int s = 0; s < GDB_WPT; ++s)
-                        if (GDB_LIVE(s))
-                            acc[s] = gv_add(acc[s], gdb_small_overflow(g1.rowadj, g2.rowptr, g2.rowadj, g2.lanemap, vovf, W, pbuf, k1beg,
-                                                                       k1end, (unsigned)wstride, ovf0, (unsigned)n2,
-                                                                       (unsigned)GDB_POS(s),
-                                                                       (1u + (w_help[s] >> 16)) * (unsigned)GDB_ADJ));
-                }
-                // helpers hand their partial sums to the owning lane (fixed order)
-                // (the first exchange is unconditional -- lanes without a helper add nothing --
-                // so that the common case of molecular graphs, one helper at most, has no loop)
+                // helpers hand their partial sums to the owning lane (fixed order).  The first
+                // exchange is unconditional -- lanes without a helper add nothing -- so that the
+                // common case of molecular graphs (one helper at most, no overflow) is straight-line
 #pragma unroll
                 for (int s = 0; s < GDB_WPT; ++s) {
                     const gv_t t = gdb_shfl_vlane(acc, w_help[s] & 0xffffu);
                     if (w_help[s] >> 16) acc[s] = gv_add(acc[s], t);
                 }
-                if (w_most > 1u) {  // uniform per pair
+                if (w_rare) {  // uniform per pair: more helpers per column, or slots without a lane
 #pragma unroll 1
                     for (unsigned h = 1; h < w_most; ++h) {
 #pragma unroll
@@ -699,6 +691,15 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
                             const gv_t t = gdb_shfl_vlane(acc, src);
                             if (h < (w_help[s] >> 16)) acc[s] = gv_add(acc[s], t);
                         }
+                    }
+                    if (w_ovf) {
+#pragma unroll
+                        for (int s = 0; s < GDB_WPT; ++s)
+                            if (GDB_LIVE(s))
+                                acc[s] = gv_add(acc[s], gdb_small_overflow(g1.rowadj, g2.rowptr, g2.rowadj, g2.lanemap, vovf, W, pbuf,
+                                                                           k1beg, k1end, (unsigned)wstride, ovf0, (unsigned)n2,
+                                                                           (unsigned)GDB_POS(s),
+                                                                           (1u + (w_help[s] >> 16)) * (unsigned)GDB_ADJ));
                     }
                 }
             };
