@@ -673,14 +673,15 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     {
         const uint64_t nrhs = p->eval_gradient ? 2 : 1;
         // work area of mlgk_solve_small (same layout, from the maxima of the graph set):
-        // step table | lane tables (vown, vhelp, vovf, wslot, vinfo) | p | W[k1][lanes' slots + overflow]
+        // step table | row table | lane tables (vown, vhelp, vovf, wslot, vinfo) | p | W[k1][lanes' slots + overflow]
         const uint64_t pad4nnz = ((uint64_t)gs->max_nnz[0] + 3) & ~3ull;
         const uint64_t wrow = ((32ull * p->wpt * p->adj + 3) & ~3ull) +
                               (((uint64_t)gs->max_ovf[p->adj == 4][std::min(p->wpt, 4) - 1] + 3) & ~3ull);
         const uint64_t wmax = (uint64_t)gs->max_nnz[0] * wrow;
         const uint64_t tables = 32ull * p->wpt + 2 * (((uint64_t)gs->max_node[0] + 3) & ~3ull) + pad4nnz + 4;
         // two blob staging buffers (double-buffered TMA prefetch) + the work area
-        const uint64_t small_need = 2 * graphs_need + (((uint64_t)gs->max_nnz[0] * 8 + 15) & ~15ull) + tables * 4 +
+        const uint64_t small_need = 2 * graphs_need + (((uint64_t)gs->max_nnz[0] * 8 + 15) & ~15ull) +
+                                    (((uint64_t)gs->max_node[0] * 8 + 15) & ~15ull) + tables * 4 +
                                     nrhs * maxNpad * 4 + std::max(nrhs * maxNpad, wmax) * 4;  // p; W (W p aliases it)
         const uint64_t small_cap = std::min<uint64_t>(cap, (uint64_t)c->prop.sharedMemPerBlockOptin - p->small_static_smem);
         // one warp per tile row of G1, lanes (x workers per thread) over the columns of G2

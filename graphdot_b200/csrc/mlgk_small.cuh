@@ -408,6 +408,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         const int n1 = g1.n, n2 = g2.n, N = n1 * n2, nnz1 = g1.nnz, nnz2 = g2.nnz;
 
         // ---- work area: [step table | lane tables | p | W p | W] -----------------------
+        //  rtab[i1]  (first, one-past-last) step-table address of row i1 of G1
         //  ktab[k1]  (W row, p row) shared-window addresses of element k1 of G1 (row order):
         //            one 64-bit broadcast load per matvec step
         //  vown[v]   virtual lane v -> column | chunk << 16   (chunk = GDB_ADJ neighbour slots)
@@ -416,7 +417,8 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         //  wslot[k2] element k2 of G2 (row order) -> float index of its W entry in a W row
         //  vinfo     {lanes in use, most helpers of a column, overflow slots}
         uint2 *ktab = reinterpret_cast<uint2 *>(gdb_smem_work);
-        unsigned *vown = reinterpret_cast<unsigned *>(gdb_smem_work + (((unsigned)nnz1 * 8u + 15u) & ~15u));
+        uint2 *rtab = reinterpret_cast<uint2 *>(gdb_smem_work + (((unsigned)nnz1 * 8u + 15u) & ~15u));
+        unsigned *vown = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(rtab) + (((unsigned)n1 * 8u + 15u) & ~15u));
         unsigned *vhelp = vown + VL;
         unsigned *vovf = vhelp + ((n2 + 3) & ~3);
         unsigned *wslot = vovf + ((n2 + 3) & ~3);
@@ -499,6 +501,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #define GDB_LIVE(s) (GDB_POS(s) < n2)
         // this thread's elements of p: row r of slot s at w_psa[s] + r * w_prow, valid for r < w_nown[s]
         const unsigned w_prow = gdb_opaque((unsigned)n2 * (unsigned)sizeof(gv_t));
+        const unsigned w_rtsa = gdb_opaque((unsigned)__cvta_generic_to_shared(rtab) + (unsigned)w_row0 * 8u);
         unsigned w_psa[GDB_WPT];
         int w_nown[GDB_WPT];
 #pragma unroll
@@ -591,6 +594,8 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         for (int k1 = threadIdx.x; k1 < nnz1; k1 += GDB_BLOCK)
             ktab[k1] = make_uint2(W_sa + (unsigned)k1 * (unsigned)(wstride * 4),
                                   p_sa + (g1.rowadj[k1] & 0xffffu) * ((unsigned)n2 * (unsigned)sizeof(gv_t)));
+        for (int i1 = threadIdx.x; i1 < n1; i1 += GDB_BLOCK)
+            rtab[i1] = make_uint2(ktab_sa + g1.rowptr[i1] * 8u, ktab_sa + g1.rowptr[i1 + 1] * 8u);
         for (int k2 = threadIdx.x; k2 < nnz2; k2 += GDB_BLOCK) {
             const unsigned rp = g2.rowpos[k2], col = rp & 0xffffu, t = rp >> 16;
             const unsigned chunk = t / (unsigned)GDB_ADJ, slot = t % (unsigned)GDB_ADJ;
@@ -644,12 +649,11 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             auto row_wp = [&](int i1, gv_t (&acc)[GDB_WPT]) {
 #pragma unroll
                 for (int s = 0; s < GDB_WPT; ++s) acc[s] = gv_make(0.f, 0.f);
-                const unsigned k1beg = g1.rowptr[i1], k1end = g1.rowptr[i1 + 1];
+                const uint2 row = gdb_lds_u2(w_rtsa + (unsigned)(i1 - w_row0) * 8u);  // steps of this row
 #if !defined(GDB_K1_UNROLL)
 #pragma unroll 1  // the body is replicated per row already: keep the code in the instruction cache
 #endif
-                const unsigned ka_end = ktab_sa + k1end * 8u;
-                for (unsigned ka = ktab_sa + k1beg * 8u; ka != ka_end; ka += 8u) {  // warp-uniform trip count
+                for (unsigned ka = row.x; ka != row.y; ka += 8u) {  // warp-uniform trip count
                     const uint2 step = gdb_lds_u2(ka);  // (W row, p row)
 #pragma unroll
                     for (int s = 0; s < GDB_WPT; ++s) {
@@ -697,7 +701,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
                         for (int s = 0; s < GDB_WPT; ++s)
                             if (GDB_LIVE(s))
                                 acc[s] = gv_add(acc[s], gdb_small_overflow(g1.rowadj, g2.rowptr, g2.rowadj, g2.lanemap, vovf, W, pbuf,
-                                                                           k1beg, k1end, (unsigned)wstride, ovf0, (unsigned)n2,
+                                                                           g1.rowptr[i1], g1.rowptr[i1 + 1], (unsigned)wstride, ovf0, (unsigned)n2,
                                                                            (unsigned)GDB_POS(s),
                                                                            (1u + (w_help[s] >> 16)) * (unsigned)GDB_ADJ));
                     }
