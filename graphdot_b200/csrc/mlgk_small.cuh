@@ -60,6 +60,11 @@
 #ifndef GDB_ADJ
 #define GDB_ADJ 4  // neighbour slots per (virtual) lane: 2 or 4
 #endif
+#ifndef GDB_K1_UNROLL
+#define GDB_K1_UNROLL 1  // unroll factor of the element loop of a row (A-B hook)
+#endif
+#define GDB_PRAGMA_(x) _Pragma(#x)
+#define GDB_UNROLL(n) GDB_PRAGMA_(unroll n)
 #ifndef GDB_ROLL_ROWS
 #define GDB_ROLL_ROWS 0  // 1: matvec rolled over the rows, W p handed over through shared memory
 #endif
@@ -650,9 +655,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll
                 for (int s = 0; s < GDB_WPT; ++s) acc[s] = gv_make(0.f, 0.f);
                 const uint2 row = gdb_lds_u2(w_rtsa + (unsigned)(i1 - w_row0) * 8u);  // steps of this row
-#if !defined(GDB_K1_UNROLL)
-#pragma unroll 1  // the body is replicated per row already: keep the code in the instruction cache
-#endif
+                GDB_UNROLL(GDB_K1_UNROLL)  // the body is replicated per row already: keep the code in the instruction cache
                 for (unsigned ka = row.x; ka != row.y; ka += 8u) {  // warp-uniform trip count
                     const uint2 step = gdb_lds_u2(ka);  // (W row, p row)
 #pragma unroll
