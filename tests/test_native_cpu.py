@@ -244,6 +244,13 @@ def test_compile_errors_are_reported():
         nl, el, weighted, k.node_kernel, k.edge_kernel, Uniform(1.0),
         T(nodal=True, eval_gradient=True), (96, 5), ())
     assert lib.gdb_program_compile_only(C.byref(d), None) == -1   # wpt > 4
+    for shape, what in (((96, 1, 9), b'rows_per_warp'),
+                        ((96, 1, 6, 3), b'slots_per_lane')):
+        d, keep, _ = B200Backend._desc(
+            nl, el, weighted, k.node_kernel, k.edge_kernel, Uniform(1.0),
+            T(symmetric=True), shape, ())
+        assert lib.gdb_program_compile_only(C.byref(d), None) == -1
+        assert what in lib.gdb_last_error()
     d, keep, _ = B200Backend._desc(
         nl, el, weighted, k.node_kernel, k.edge_kernel, Uniform(1.0),
         T(nodal=True, eval_gradient=True), (96, 1), ())
@@ -273,3 +280,23 @@ def test_heterogeneous_graphs_raise_type_error():
     b = make_config_graphs('C1', 1)[0]
     with pytest.raises(TypeError):
         kernel([a, b])
+
+
+def test_launch_shape_follows_the_graph_set():
+    """_pick_block: ~6 rows per warp for the small-pair kernel, two neighbour
+    slots per lane for sparse (molecular) graphs and four for dense ones; the
+    shape macros reach the rendered source."""
+    be = B200Backend()
+    assert be._pick_block(np.array([16, 24]), True, 2.2) == (128, 1, 6, 2)
+    assert be._pick_block(np.array([10, 20]), False, 5.5) == (128, 1, 5, 4)
+    assert be._pick_block(np.array([40]), False, 2.0) == (224, 2, 6, 2)
+    assert be._pick_block(np.array([40]), True, 2.0)[0] in (128, 256)   # general kernel
+    assert B200Backend(block_size=96)._pick_block(
+        np.array([24]), True, 2.2) == (96, 1, 8, 2)
+    assert B200Backend(slots_per_lane=4)._pick_block(
+        np.array([24]), True, 2.2)[3] == 4
+    from graphdot_b200.kernel.marginalized._backend_b200 import preset_sources
+    src = preset_sources()['c3_molecular_grad']
+    for line in ('#define GDB_BLOCK 128', '#define GDB_RPW 6',
+                 '#define GDB_ADJ 2', '#define GDB_MIN_BLOCKS_SMALL 5'):
+        assert line in src
