@@ -421,6 +421,11 @@ def run_gpu(args, rank, world, local_rank):
             'peak_source': f'{info.sm_count} SMs x 128 lanes x 2 x '
                            f'{sm_mhz:.0f} MHz (measured sm_max_mhz)',
             'matvec_tflops': fl['matvec'] / world / kernel_s / 1e12,
+            # SURVEY 8(d) also asks for the MUFU ceiling of an edge kernel
+            # evaluated on the fly (one ex2 per product, 16 / clk / SM); this
+            # kernel caches the products per pair, so it may exceed it
+            'mufu_model_frac': (products / args.steps / world / kernel_s)
+            / (info.sm_count * 16 * sm_mhz * 1e6),
             'kernel_ms_per_step': kernel_ms / args.steps / world,
             'cg_iterations_per_pair': cg_it / args.steps / total_pairs,
             'kernel': (f'mlgk_solve_small block={pinfo.block_size} '
