@@ -279,11 +279,15 @@ def run_gpu(args, rank, world, local_rank):
                           nvrtc_extra=args.nvrtc_extra.split())
     kernel = make_config_kernel('C3', backend=backend)
     stream = torch.cuda.current_stream()
+    # row-block height: about 8 tiles per rank -- tall tiles amortise the tail
+    # of a launch (measured at N = 1: 32 / 64 / 128 / 256 rows = 20.2 / 20.9 /
+    # 21.5 / 21.7 M pairs/s), enough tiles keep the dynamic queue balanced
+    tile_rows = args.tile_rows or max(32, min(256, n // (8 * world)))
     worker = GramTileWorker(kernel, G, backend, eval_gradient=True,
-                            max_rows=args.tile_rows,
+                            max_rows=tile_rows,
                             stream=stream.cuda_stream)
     worker.diag(store=True)     # self-similarities for the fused normalization
-    tiles = row_tiles(n, args.tile_rows)
+    tiles = row_tiles(n, tile_rows)
     total_pairs = n * (n + 1) // 2
     assert sum(tile_pairs(a, b, n) for a, b in tiles) == total_pairs
     sizes = np.array([len(g.nodes) for g in G], float)
@@ -402,7 +406,9 @@ def run_gpu(args, rank, world, local_rank):
         'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': workload_config(world),
+        'data': 'synthetic',
+        'config': dict(workload_config(world), tile_rows=tile_rows,
+                       tiles_per_step=len(tiles)),
         'e2e': {'value': e2e_value, 'unit': UNIT,
                 'h2d_bytes_per_step': int(h2d / e2e_steps),
                 'd2h_bytes_per_step': int(d2h / e2e_steps),
@@ -457,7 +463,8 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--tile-rows', type=int, default=64)
+    ap.add_argument('--tile-rows', type=int, default=0,
+                    help='rows per tile launch; 0 = about 8 tiles per rank')
     ap.add_argument('--block-size', type=int, default=0)
     ap.add_argument('--slots-per-lane', type=int, default=0)
     ap.add_argument('--e2e-steps', type=int, default=2)
