@@ -125,3 +125,20 @@ def test_bounds_validation():
     with pytest.raises(ValueError):
         Composite('-', a=Constant(1.0))
     assert Normalize(Normalize(Constant(2.0))).name == 'Normalize'
+
+
+def test_jacobian_plane_selection_is_a_single_pass_equivalent():
+    """MarginalizedGraphKernel._active_planes == jacobian[:, :, mask].astype()
+    (values, dtype, Fortran layout) for full and partial masks."""
+    import numpy as np
+    from graphdot_b200.kernel.marginalized import MarginalizedGraphKernel
+    rng = np.random.default_rng(0)
+    raw = np.asfortranarray(rng.standard_normal((7, 5, 4)).astype(np.float32))
+    for mask in ([True] * 4, [True, False, True, True], [False] * 4):
+        for dtype in (np.float64, np.float32):
+            got = MarginalizedGraphKernel._active_planes(raw, mask, dtype)
+            want = raw[:, :, np.asarray(mask)].astype(dtype)
+            assert got.dtype == dtype and got.shape == want.shape
+            assert np.array_equal(got, want)
+            assert got.flags.f_contiguous or got.size == 0
+            assert got is not raw
