@@ -5,22 +5,33 @@ solves/sec, Gram + gradient).
     python bench.py --gpus N --steps K --warmup W            # this engine
     python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm
 
-Workload (``config.workload``): BASELINE config C3 = C2 with
-``eval_gradient=True`` -- the normalized Gram matrix AND its Jacobian over all
-5 hyper-parameters of the synthetic molecular set (KroneckerDelta(element) x
-SquareExponential(x) node kernel, SquareExponential(length) edge kernel,
-weighted bonds, q = 0.05).  At N = 1 this is the 2000-graph set of
-BASELINE.json (2 001 000 graph pairs per step).  At N > 1 the set grows to
-2000*sqrt(N) graphs so that every GPU keeps 2 001 000 pairs per step (weak
-scaling); the pairs are cut into row-block tiles that the ranks pull from one
-dynamic queue (a counter in the torch.distributed store) -- no collective on
-the data path.  A "step" is one pass over all pairs.
+Workloads (``config.workload``):
 
-``value``   pairs/s with graphs resident in HBM and outputs left on the
-            device (CUDA events on the launching stream, max over ranks).
-``e2e``     pairs/s through the tile worker with HOST buffers: every step
-            re-sends the packed graphs (pinned) host->device, copies every
-            Gram / Jacobian tile device->host and normalizes it on the host.
+* N = 1 -- BASELINE config C3 (= C2 + ``eval_gradient=True``): the normalized
+  Gram matrix AND its Jacobian over all 5 hyper-parameters of the 2000
+  synthetic molecules (2 001 000 graph pairs per step).
+* N > 1 -- BASELINE config C5 at its stated, FIXED size (strong scaling): the
+  10 000 x 10 000 off-diagonal block X x Y of the 20 000-molecule seed-5005
+  set, normalized Gram + Jacobian = 10^8 pairs per step.  The job rectangle
+  is cut into column tiles that the ranks pull from one dynamic queue (a
+  counter in the torch.distributed store); rank 0 packs the graphs once and
+  broadcasts the packed set; every rank copies its finished tiles straight
+  into ONE page-locked shared-memory host matrix, so rank 0 ends up holding
+  the assembled result with no collective on the data path.
+  (``--workload c5`` runs the same job on one GPU.)
+
+A "step" is one pass over all pairs.
+
+``value``   pairs/s with graphs resident in HBM and the complete result left in
+            device memory (CUDA events on the launching stream, max over ranks).
+``e2e``     pairs/s through the public call with HOST buffers.  N = 1:
+            ``Normalization(kernel)(G, eval_gradient=True)`` -- every step
+            re-sends the packed graphs (pinned) host->device and returns the
+            float64 Gram + Jacobian as numpy arrays.  N > 1: the tile worker;
+            every step re-sends the graphs and lands all tiles in the shared
+            host matrix.
+``parity``  after the timed loops, entries of the e2e result sampled at random
+            are compared with the float64 CPU oracle (oracle/mlgk_oracle.py).
 ``roofline`` achieved FP32 FLOP/s of the solver kernel (algorithmic flops of
             SURVEY.md 8(d) with the iteration counts the engine reports) against
             the FP32 pipe peak derived from the measured SM clock.
@@ -31,7 +42,6 @@ the data path.  A "step" is one pass over all pairs.
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -48,29 +58,41 @@ UNIT = 'pairs/s'
 # kernels (a transcendental counts 1), SURVEY.md 8(d)
 F_E, F_DE = 6, 3           # edge: w1*w2, sub, sq, scale, exp, mul | d/dls
 F_V, F_DV = 7, 6           # node: cmp, select, sub, sq, scale, exp, mul
+C5_NX = C5_NY = 10000
+N_CPU_SAMPLE = 96          # graphs whose pairs the CPU arm times
 
 
-def n_graphs_for(world):
-    return int(round(2000 * math.sqrt(world)))
+def pick_workload(args, world):
+    return (args.workload or ('c3' if world == 1 else 'c5')).lower()
+
+
+def workload_config(workload):
+    base = {
+        'node_kernel': 'TensorProduct(element=KroneckerDelta(0.5), '
+                       'x=SquareExponential(1.0))',
+        'edge_kernel': 'TensorProduct(length=SquareExponential(0.1))',
+        'q': 0.05, 'outputs': 'normalized Gram + Jacobian over all 5 '
+                              'hyper-parameters (p, q, h, l_node, l_edge)',
+        'l2': 'flushed between timed steps (256 MiB write)',
+    }
+    if workload == 'c3':
+        n = 2000
+        return dict(base, workload='C3 = C2 + eval_gradient: 2000 synthetic '
+                    'molecular graphs (16-24 nodes), symmetric normalized '
+                    'Gram + Jacobian', n_graphs=n,
+                    pairs_per_step=n * (n + 1) // 2)
+    return dict(base, workload='C5: 10000 x 10000 off-diagonal block X x Y of '
+                'the 20000-molecule seed-5005 set (16-24 nodes), fixed size '
+                '(strong scaling), normalized Gram + Jacobian',
+                n_graphs=C5_NX + C5_NY, pairs_per_step=C5_NX * C5_NY,
+                sharding='column tiles of the job rectangle from a dynamic '
+                         'queue, graphs replicated (packed once, broadcast)')
 
 
 # ---------------------------------------------------------------------------
-# CPU arm (oracle port), also the cpu_baseline of the GPU arm
+# CPU arm (oracle port), also the cpu_baseline of the GPU arm and the parity
+# checker
 # ---------------------------------------------------------------------------
-def _cpu_pair(args):
-    from graphdot_b200.synthetic import make_config_kernel
-    from oracle import mlgk_oracle as oracle
-    g1, g2 = args
-    k = _cpu_pair.kernel
-    if k is None:
-        k = _cpu_pair.kernel = make_config_kernel('C3', backend=_NoBackend())
-    return oracle.solve_pair(g1, g2, k.node_kernel, k.edge_kernel, k.q, k.p,
-                             eval_gradient=True)[1]
-
-
-_cpu_pair.kernel = None
-
-
 class _NoBackend:
     """Placeholder so the CPU arm can build the kernel object (for its
     hyper-parameters) without touching the CUDA library."""
@@ -83,43 +105,72 @@ class _NoBackend:
         return Dummy()
 
 
-def cpu_sample_rate(n_sample_graphs=16, repeats=1, pool=None):
-    """pairs/s of the oracle on the upper-triangle pairs of the first
-    ``n_sample_graphs`` C2 graphs, on all host cores."""
+def _cpu_kernel():
+    k = _cpu_kernel.kernel
+    if k is None:
+        from graphdot_b200.synthetic import make_config_kernel
+        k = _cpu_kernel.kernel = make_config_kernel('C3',
+                                                    backend=_NoBackend())
+    return k
+
+
+_cpu_kernel.kernel = None
+
+
+def _cpu_pair(args):
+    """(K, dK/dtheta) of one graph pair by the float64 oracle."""
+    from oracle import mlgk_oracle as oracle
+    g1, g2 = args
+    k = _cpu_kernel()
+    out = oracle.solve_pair(g1, g2, k.node_kernel, k.edge_kernel, k.q, k.p,
+                            eval_gradient=True)
+    return out[1], out[2]
+
+
+def _pool():
     import multiprocessing as mp
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
+    return mp.get_context('fork').Pool(os.cpu_count() or 1)
+
+
+def cpu_sample_pairs(workload):
+    """The bounded sample the CPU arm times: pairs among the first 96 graphs
+    of the workload's set (upper triangle for C3, X[:96] x Y[:48] for C5)."""
     from graphdot_b200.synthetic import make_config_graphs
-    G = make_config_graphs('C2', n_sample_graphs)
-    pairs = [(G[i], G[j]) for i in range(len(G)) for j in range(i, len(G))]
+    if workload == 'c3':
+        G = make_config_graphs('C2', N_CPU_SAMPLE)
+        return [(G[i], G[j]) for i in range(len(G))
+                for j in range(i, len(G))], \
+            (f'upper triangle of the first {N_CPU_SAMPLE} graphs of the C2 '
+             'set')
+    G = make_config_graphs('C5', N_CPU_SAMPLE + N_CPU_SAMPLE // 2)
+    X, Y = G[:N_CPU_SAMPLE], G[N_CPU_SAMPLE:]
+    return [(a, b) for a in X for b in Y], \
+        (f'{N_CPU_SAMPLE} x {N_CPU_SAMPLE // 2} block of the first '
+         f'{len(G)} graphs of the C5 set')
+
+
+def cpu_sample_rate(workload, pool, repeats=1):
+    pairs, what = cpu_sample_pairs(workload)
     cores = os.cpu_count() or 1
-    own = pool is None
-    if own:
-        pool = mp.get_context('fork').Pool(cores)
-    try:
-        pool.map(_cpu_pair, pairs[:cores])           # warm the workers
-        t0 = time.perf_counter()
-        for _ in range(repeats):
-            pool.map(_cpu_pair, pairs, chunksize=max(1, len(pairs) // (8 * cores)))
-        dt = (time.perf_counter() - t0) / repeats
-    finally:
-        if own:
-            pool.close()
-            pool.join()
-    return len(pairs) / dt, cores, len(pairs), dt
+    pool.map(_cpu_pair, pairs[:cores])           # warm the workers
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        pool.map(_cpu_pair, pairs, chunksize=max(1, len(pairs) // (8 * cores)))
+    dt = (time.perf_counter() - t0) / repeats
+    return len(pairs) / dt, cores, len(pairs), dt, what
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    os.environ.setdefault('OMP_NUM_THREADS', '1')
-    os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
-    import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    pool = mp.get_context('fork').Pool(cores)
-    n_sample = 96
+    workload = pick_workload(args, world)
+    pool = _pool()
     times = []
     try:
         for s in range(args.warmup + args.steps):
-            rate, cores, n_pairs, dt = cpu_sample_rate(n_sample, 1, pool)
+            rate, cores, n_pairs, dt, what = cpu_sample_rate(workload, pool)
             if s >= args.warmup:
                 times.append(dt)
     finally:
@@ -127,15 +178,17 @@ def run_reference(args, rank, world):
         pool.join()
     dt = float(np.mean(times))
     value = n_pairs / dt
-    sample = (f'{n_pairs} pairs per step: upper triangle of the first '
-              f'{n_sample} graphs of the C2 set, float64 dense Kronecker '
-              'solve + adjoint Jacobian')
+    sample = (f'{n_pairs} pairs per step ({what}), float64 dense Kronecker '
+              'solve + adjoint Jacobian (oracle/mlgk_oracle.py); the rate is '
+              'measured on this sample, not on the full pairs_per_step')
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'ms_per_step': dt * 1e3, 'higher_is_better': True,
+        'scaling': 'weak' if workload == 'c3' else 'strong',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(world),
+        'config': workload_config(workload),
+        'timed_pairs_per_step': n_pairs,
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores,
                          'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
@@ -144,19 +197,33 @@ def run_reference(args, rank, world):
     }))
 
 
-def workload_config(world):
-    n = n_graphs_for(world)
-    return {
-        'workload': 'C3 = C2 + eval_gradient: synthetic molecular graphs '
-                    '(16-24 nodes), normalized Gram + Jacobian over 5 '
-                    'hyper-parameters',
-        'n_graphs': n, 'pairs_per_step': n * (n + 1) // 2,
-        'node_kernel': 'TensorProduct(element=KroneckerDelta(0.5), '
-                       'x=SquareExponential(1.0))',
-        'edge_kernel': 'TensorProduct(length=SquareExponential(0.1))',
-        'q': 0.05, 'l2': 'flushed between timed steps (256 MiB write)',
-        'sharding': 'row-block tiles from a dynamic queue, replicated graphs',
-    }
+def check_parity(pool, G, pairs, K, dK, diag_cache=None):
+    """Compare sampled normalized entries K[r, c], dK[r, c, :] -- the pair
+    (graph a, graph b) listed as (r, c, a, b) -- with the float64 oracle:
+    raw pair solves + the quotient rule of reference kernel/fix.py:46-73."""
+    need = sorted({a for _, _, a, b in pairs} | {b for _, _, a, b in pairs})
+    selfs = dict(zip(need, pool.map(_cpu_pair, [(G[a], G[a]) for a in need],
+                                    chunksize=8)))
+    cross = pool.map(_cpu_pair, [(G[a], G[b]) for _, _, a, b in pairs],
+                     chunksize=8)
+    err_k = err_g = 0.0
+    scale_g = np.zeros(dK.shape[2])
+    diff_g = np.zeros(dK.shape[2])
+    for (r, c, a, b), (kab, dab) in zip(pairs, cross):
+        kaa, daa = selfs[a]
+        kbb, dbb = selfs[b]
+        kn = kab / np.sqrt(kaa * kbb)
+        dn = dab / np.sqrt(kaa * kbb) - 0.5 * kn * (daa / kaa + dbb / kbb)
+        err_k = max(err_k, abs(K[r, c] - kn) / abs(kn))
+        diff_g = np.maximum(diff_g, np.abs(dK[r, c, :] - dn))
+        scale_g = np.maximum(scale_g, np.abs(dn))
+    err_g = float(np.max(diff_g / scale_g))
+    return {'max_rel_gram': float(err_k), 'max_rel_grad': err_g,
+            'n': len(pairs), 'tolerance': {'gram': 1e-5, 'grad': 1e-4},
+            'ok': bool(err_k < 1e-5 and err_g < 1e-4),
+            'against': 'oracle/mlgk_oracle.py (float64 dense solve), '
+                       'gradient error per plane relative to the largest '
+                       'sampled entry of that plane'}
 
 
 # ---------------------------------------------------------------------------
@@ -232,28 +299,78 @@ def reference_gpu_rate(n, q):
         return {'unavailable': f'{type(e).__name__}: {e}'}
 
 
-def algorithmic_flops(stats, sum_N, sum_nnzx, nJ):
+def algorithmic_flops(products, vec_elems, sum_N, sum_nnzx, nJ):
     """FP32 flops of the solver per SURVEY.md 8(d): matvec
     W_mv = nnzx (2 + F_e) + 2N per application, plus 13 N per CG iteration,
     setup N (F_v + 4) per solve, and the Jacobian sweep."""
-    it_nnzx = stats['matvec_products']
-    it_N = stats['vector_elements']
-    matvec = it_nnzx * (2 + F_E) + 2 * it_N
-    cg = matvec + 13 * it_N
+    matvec = products * (2 + F_E) + 2 * vec_elems
+    cg = matvec + 13 * vec_elems
     setup = sum_N * (F_V + 4) * 2
     jac = sum_nnzx * (2 + F_E + F_DE) + sum_N * (F_DV + 8 + 2 * nJ)
     return {'matvec': matvec, 'total': cg + setup + jac}
 
 
+class SharedHostMatrix:
+    """ONE host copy of the (nx, ny) Gram and (nx, ny, nJ) Jacobian, Fortran
+    ordered float32, in a shared-memory file that every rank maps and
+    page-locks: ranks copy their tiles into it directly ("gathering Gram tiles
+    back to host" without a collective)."""
+
+    def __init__(self, tag, nx, ny, nJ, rank, barrier):
+        from graphdot_b200 import native
+        self.nbytes = nx * ny * (1 + nJ) * 4
+        d = '/dev/shm'
+        try:
+            st = os.statvfs(d)
+            if st.f_bavail * st.f_frsize < self.nbytes * 1.05:
+                d = '/tmp'
+        except OSError:
+            d = '/tmp'
+        self.path = os.path.join(d, f'gdb_result_{tag}.bin')
+        self.rank = rank
+        if rank == 0:
+            with open(self.path, 'wb') as f:
+                f.truncate(self.nbytes)
+        barrier()
+        self.mm = np.memmap(self.path, dtype=np.float32, mode='r+',
+                            shape=(nx * ny * (1 + nJ),))
+        self.addr = self.mm.ctypes.data
+        self.pinned = True
+        try:
+            native.check(native.load().gdb_host_register(self.addr,
+                                                         self.nbytes))
+        except native.NativeError:
+            self.pinned = False
+        self.K = self.mm[:nx * ny].reshape((nx, ny), order='F')
+        self.dK = self.mm[nx * ny:].reshape((nx, ny, nJ), order='F')
+        self.k_addr = self.addr
+        self.dk_addr = self.addr + nx * ny * 4
+        barrier()
+
+    def close(self, barrier):
+        from graphdot_b200 import native
+        if self.pinned:
+            native.load().gdb_host_unregister(self.addr)
+        self.K = self.dK = None
+        del self.mm
+        barrier()
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from graphdot_b200.kernel.marginalized._backend_b200 import B200Backend
+    from graphdot_b200.kernel.fix import Normalization
+    from graphdot_b200.kernel.marginalized._backend_b200 import (B200Backend,
+                                                                 PackedGraph)
     from graphdot_b200.kernel.marginalized._tiles import (GramTileWorker,
                                                           LocalTileQueue,
                                                           StoreTileQueue,
-                                                          row_tiles,
-                                                          tile_pairs)
+                                                          col_tiles)
     from graphdot_b200.synthetic import make_config_graphs, make_config_kernel
 
     # keep stdout clean for the single JSON line (NCCL prints its version there)
@@ -271,60 +388,167 @@ def run_gpu(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    n = n_graphs_for(world)
-    G = make_config_graphs('C2', n)
+    workload = pick_workload(args, world)
     backend = B200Backend(device=local_rank,
                           block_size=args.block_size or None,
                           slots_per_lane=args.slots_per_lane or None,
                           nvrtc_extra=args.nvrtc_extra.split())
     kernel = make_config_kernel('C3', backend=backend)
     stream = torch.cuda.current_stream()
-    # row-block height: about 8 tiles per rank -- tall tiles amortise the tail
-    # of a launch (measured at N = 1: 32 / 64 / 128 / 256 rows = 20.2 / 20.9 /
-    # 21.5 / 21.7 M pairs/s), enough tiles keep the dynamic queue balanced
-    tile_rows = args.tile_rows or max(32, min(256, n // (8 * world)))
-    worker = GramTileWorker(kernel, G, backend, eval_gradient=True,
-                            max_rows=tile_rows,
-                            stream=stream.cuda_stream)
-    worker.diag(store=True)     # self-similarities for the fused normalization
-    tiles = row_tiles(n, tile_rows)
-    total_pairs = n * (n + 1) // 2
-    assert sum(tile_pairs(a, b, n) for a, b in tiles) == total_pairs
-    sizes = np.array([len(g.nodes) for g in G], float)
-    nnz = np.array([2 * len(g.edges) for g in G], float)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
-    step_no = [0]
+    nJ = kernel.n_dims
+    launch = {}
+    first_call = {}
 
-    def tile_queue():
-        """Dynamic tile queue: a local counter (N=1) or an atomic counter in
-        the torch.distributed store shared by all ranks (N>1)."""
-        key = f'tiles{step_no[0]}'
-        step_no[0] += 1
-        if store is None:
-            return iter(LocalTileQueue(tiles))
-        return iter(StoreTileQueue(store, tiles, key))
+    if workload == 'c3':
+        # ---- one GPU, symmetric 2000-graph set through the public API ---------
+        n = 2000
+        G = make_config_graphs('C2', n)
+        total_pairs = n * (n + 1) // 2
+        t0 = time.perf_counter()
+        backend.pack_graphs(G)
+        first_call['pack_ms'] = (time.perf_counter() - t0) * 1e3
+        norm = Normalization(kernel)
+        sizes = np.array([len(g.nodes) for g in G], float)
+        nnz = np.array([2 * len(g.edges) for g in G], float)
+        # sums over the unique pairs (i <= j) of N = n_i n_j and nnz_i nnz_j
+        sum_N = (sizes.sum() ** 2 + (sizes ** 2).sum()) / 2
+        sum_nnzx = (nnz.sum() ** 2 + (nnz ** 2).sum()) / 2
+        result = {}
 
-    def step_device():
-        for i0, i1 in tile_queue():
-            worker.run_tile(i0, i1, keep_on_device=True, normalize=True)
+        def step_device():
+            # complete normalized Gram + Jacobian left in device memory
+            result['dev'] = norm.device_gram(G, eval_gradient=True)
 
-    def step_e2e():
-        # H2D of the packed graphs; self-similarities stay on the device
-        worker.diag(upload=True, store=True)
-        checksum = 0.0
-        for i0, i1 in tile_queue():
-            # normalized in the solver epilogue; D2H of the tile
-            Kn, dKn = worker.run_tile(i0, i1, normalize=True)
-            checksum += float(Kn[0, i0]) + float(dKn[0, i0, 1])
-        return checksum
+        def step_e2e():
+            backend.resend_graphs = True
+            try:
+                result['host'] = norm(G, eval_gradient=True)
+            finally:
+                backend.resend_graphs = False
+
+        launch.update(value_path='Normalization(kernel).device_gram(G, '
+                      'eval_gradient=True): 1 diagonal launch + 1 launch of '
+                      'all 2 001 000 pairs, result in torch CUDA tensors',
+                      e2e_path='Normalization(kernel)(G, eval_gradient=True)'
+                      ': graphs H2D, diagonal launch, 8 pipelined row-block '
+                      'launches, column blocks D2H + float64 collection '
+                      'overlapped with the next launch')
+
+        def sample_pairs(rng, k):
+            r = rng.integers(0, n, k)
+            c = rng.integers(0, n, k)
+            return [(int(a), int(b), int(a), int(b)) for a, b in zip(r, c)]
+
+        def host_result():
+            return result['host']
+
+        def cleanup():
+            pass
+    else:
+        # ---- C5: fixed 10k x 10k block, column tiles from a dynamic queue ------
+        nx, ny = C5_NX, C5_NY
+        total_pairs = nx * ny
+        G = None
+        payload = [None]
+        if rank == 0:
+            G = make_config_graphs('C5', nx + ny)
+            t0 = time.perf_counter()
+            packed = backend.pack_graphs(G)
+            first_call['pack_ms'] = (time.perf_counter() - t0) * 1e3
+            base = packed[0].blob.base
+            cuts = np.cumsum([0] + [p.blob.nbytes for p in packed])
+            same_buf = base is not None and all(p.blob.base is base
+                                                for p in packed)
+            buf = (np.asarray(base) if same_buf
+                   else np.concatenate([p.blob for p in packed]))
+            payload = [(buf.tobytes(), cuts, [p.n_node for p in packed],
+                        packed[0].key, B200Backend._layouts(G[0]))]
+        if world > 1:
+            t0 = time.perf_counter()
+            dist.broadcast_object_list(payload, src=0)
+            first_call['broadcast_ms'] = (time.perf_counter() - t0) * 1e3
+        raw, cuts, n_nodes, key, layouts = payload[0]
+        buf = np.frombuffer(raw, dtype=np.uint8)
+        packed = [PackedGraph(buf[a:b], nn, key)
+                  for a, b, nn in zip(cuts[:-1], cuts[1:], n_nodes)]
+        t0 = time.perf_counter()
+        gs = backend.graphset_from_packed(packed, layouts)
+        first_call['upload_ms'] = (time.perf_counter() - t0) * 1e3
+        worker = GramTileWorker(kernel, None, backend, eval_gradient=True,
+                                max_rows=0, stream=stream.cuda_stream, nx=nx,
+                                packed=gs)
+        tile_cols = args.tile_cols or max(16, ny // (8 * world))
+        tiles = col_tiles(ny, tile_cols)
+        # the complete result of this rank's tiles stays in device memory
+        Kd = torch.zeros((ny, nx), dtype=torch.float32, device='cuda')
+        dKd = torch.zeros((nJ, ny, nx), dtype=torch.float32, device='cuda')
+        dev = (Kd.data_ptr(), dKd.data_ptr())
+        shared = SharedHostMatrix(f'{os.environ.get("MASTER_PORT", "0")}_'
+                                  f'{os.getppid() if world > 1 else os.getpid()}',
+                                  nx, ny, nJ, rank, barrier)
+        host = (shared.k_addr, shared.dk_addr)
+        sizes_x = np.array(n_nodes[:nx], float)
+        sizes_y = np.array(n_nodes[nx:], float)
+        hdr = [p.blob[:16].view(np.int32) for p in packed]
+        nnz_all = np.array([h[2] for h in hdr], float)
+        sum_N = sizes_x.sum() * sizes_y.sum()
+        sum_nnzx = nnz_all[:nx].sum() * nnz_all[nx:].sum()
+        step_no = [0]
+
+        def tile_queue():
+            """Dynamic tile queue: a local counter (N=1) or an atomic counter
+            in the torch.distributed store shared by all ranks (N>1)."""
+            key = f'tiles{step_no[0]}'
+            step_no[0] += 1
+            if store is None:
+                return iter(LocalTileQueue(tiles))
+            return iter(StoreTileQueue(store, tiles, key))
+
+        def step_device():
+            for j0, j1 in tile_queue():
+                worker.run_cols(j0, j1, normalize=True, dev=dev)
+
+        def step_e2e():
+            # H2D of the packed graphs + self-similarities, then tiles whose
+            # copy-back into the shared host matrix overlaps the next tile
+            worker.diag(upload=True, store=True, fetch=False)
+            for j0, j1 in tile_queue():
+                worker.run_cols(j0, j1, normalize=True, dev=dev, host=host,
+                                async_=True)
+            backend.synchronize()
+
+        worker.diag(store=True, fetch=False)
+        launch.update(tile_cols=tile_cols, tiles_per_step=len(tiles),
+                      host_matrix=('shared memory, page-locked by every rank'
+                                   if shared.pinned else
+                                   'shared memory, NOT page-locked '
+                                   '(registration failed)'),
+                      host_matrix_path=shared.path,
+                      value_path='tile worker, result tiles left in a '
+                      'full-size device matrix per rank',
+                      e2e_path='tile worker: graphs H2D + diagonal launch, '
+                      'every tile copied asynchronously into the shared '
+                      'host matrix (copy overlaps the next tile)')
+
+        def sample_pairs(rng, k):
+            r = rng.integers(0, nx, k)
+            c = rng.integers(0, ny, k)
+            return [(int(a), int(b), int(a), int(nx + b))
+                    for a, b in zip(r, c)]
+
+        def host_result():
+            return shared.K, shared.dK
+
+        def cleanup():
+            shared.close(barrier)
 
     # ---- device-resident throughput -----------------------------------------
     for _ in range(args.warmup):
         barrier()
         step_device()
     sampler = ClockSampler(local_rank)
-    for k in worker.stats:
-        worker.stats[k] = 0
+    backend.reset_totals()
     ev = [(torch.cuda.Event(enable_timing=True),
            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -338,52 +562,67 @@ def run_gpu(args, rank, world, local_rank):
     barrier()
     clocks = sampler.stop()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    stats = dict(worker.stats)
+    stats = dict(backend.totals)
 
     # ---- end to end with host buffers ----------------------------------------
     for _ in range(max(1, args.warmup // 2)):
         barrier()
         step_e2e()
-    for k in worker.stats:
-        worker.stats[k] = 0
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    backend.reset_totals()
+    e2e_steps = args.e2e_steps or args.steps
     barrier()
     t0 = time.perf_counter()
     for s in range(e2e_steps):
         step_e2e()
-    torch.cuda.synchronize()
+        barrier()
     e2e_s = time.perf_counter() - t0
-    barrier()
-    e2e_stats = dict(worker.stats)
+    e2e_stats = dict(backend.totals)
 
     # ---- reduce over ranks ------------------------------------------------------
     vec = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device='cuda')
     sums = torch.tensor([stats['kernel_ms'], stats['cg_iterations'],
                          stats['matvec_products'], stats['vector_elements'],
                          stats['launches'], stats['pairs'],
-                         e2e_stats['h2d_bytes'], e2e_stats['d2h_bytes']],
+                         e2e_stats['h2d_bytes'], e2e_stats['d2h_bytes'],
+                         e2e_stats['launches']],
                         dtype=torch.float64, device='cuda')
+    per_rank = torch.zeros(world, dtype=torch.float64, device='cuda')
+    per_rank[rank] = stats['pairs']
     if world > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
     dev_ms, e2e_s = vec.tolist()
     (kernel_ms, cg_it, products, vec_elems, launches, pairs_done, h2d,
-     d2h) = sums.tolist()
-    assert int(pairs_done) == total_pairs * args.steps, (pairs_done,
-                                                         total_pairs)
+     d2h, e2e_launches) = sums.tolist()
+    n_diag = 2000 if workload == 'c3' else 0    # device_gram's diagonal solve
+    assert int(pairs_done) == (total_pairs + n_diag) * args.steps, (
+        pairs_done, total_pairs)
     if rank != 0:
+        cleanup()
         if world > 1:
             dist.destroy_process_group()
         return
 
+    # ---- parity of the assembled end-to-end result vs the CPU oracle ------------
+    pool = _pool()
+    try:
+        Kh, dKh = host_result()
+        if G is None:
+            G = make_config_graphs('C5', C5_NX + C5_NY)
+        pairs = sample_pairs(np.random.default_rng(12345), args.parity_samples)
+        parity = check_parity(pool, G, pairs, Kh, dKh)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_sample_rate(workload, pool)
+    finally:
+        pool.close()
+        pool.join()
+
     value = total_pairs * args.steps / (dev_ms * 1e-3)
     e2e_value = total_pairs * e2e_steps / e2e_s
-    # sums over the unique pairs (i <= j) of N = n_i n_j and nnz_i nnz_j
-    sum_N = (sizes.sum() ** 2 + (sizes ** 2).sum()) / 2
-    sum_nnzx = (nnz.sum() ** 2 + (nnz ** 2).sum()) / 2
-    fl = algorithmic_flops({'matvec_products': products / args.steps,
-                            'vector_elements': vec_elems / args.steps},
-                           sum_N, sum_nnzx, kernel.n_dims)
+    fl = algorithmic_flops(products / args.steps, vec_elems / args.steps,
+                           sum_N, sum_nnzx, nJ)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -394,36 +633,35 @@ def run_gpu(args, rank, world, local_rank):
     peak_tflops = info.sm_count * 128 * 2 * sm_mhz * 1e6 / 1e12
     kernel_s = kernel_ms * 1e-3 / args.steps / world   # avg per rank & step
     achieved = fl['total'] / world / kernel_s / 1e12
-    pinfo = backend.program_info(worker.prog)
     traffic = None      # DRAM bytes of one launch from the committed ncu capture
+    traffic_note = None
     try:
-        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))
-        traffic = tr['dram_bytes_per_launch']
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')))
+        traffic = tr[workload]['dram_bytes_per_launch']
+        traffic_note = tr[workload]['note']
     except (OSError, KeyError, ValueError):
         pass
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic',
-        'config': dict(workload_config(world), tile_rows=tile_rows,
-                       tiles_per_step=len(tiles)),
+        'scaling': 'weak' if workload == 'c3' else 'strong',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(workload),
+        'launch': launch,
         'e2e': {'value': e2e_value, 'unit': UNIT,
                 'h2d_bytes_per_step': int(h2d / e2e_steps),
                 'd2h_bytes_per_step': int(d2h / e2e_steps),
-                'steps': e2e_steps,
-                'note': 'tile worker with host buffers: graphs H2D, diagonal '
-                        'solve, normalized Gram+Jacobian tiles D2H'},
+                'steps': e2e_steps, 'ms_per_step': e2e_s / e2e_steps * 1e3,
+                'launches_per_step': e2e_launches / e2e_steps,
+                'first_call_ms': first_call},
+        'parity': parity,
         'gpu_launches': int(launches),
+        'pairs_per_rank': [int(x) for x in (per_rank / args.steps).tolist()],
         'roofline': {
             'bound': 'fp32', 'achieved': achieved, 'peak': peak_tflops,
             'unit': 'TFLOP/s', 'frac': achieved / peak_tflops,
-            'traffic': traffic,
-            'traffic_note': 'dram read+write bytes of ONE launch (row-block tile '
-                            'of 125 984 pairs) from profiles/r1_small_final_ncu_'
-                            'summary.md; the kernel is on-chip bound, the blobs '
-                            'stream in once',
+            'traffic': traffic, 'traffic_note': traffic_note,
             'peak_source': f'{info.sm_count} SMs x 128 lanes x 2 x '
                            f'{sm_mhz:.0f} MHz (measured sm_max_mhz)',
             'matvec_tflops': fl['matvec'] / world / kernel_s / 1e12,
@@ -434,23 +672,22 @@ def run_gpu(args, rank, world, local_rank):
             / (info.sm_count * 16 * sm_mhz * 1e6),
             'kernel_ms_per_step': kernel_ms / args.steps / world,
             'cg_iterations_per_pair': cg_it / args.steps / total_pairs,
-            'kernel': (f'mlgk_solve_small block={pinfo.block_size} '
-                       f'regs={pinfo.num_regs_small}'
-                       if backend.last.get('small_kernel') else
-                       f'mlgk_solve block={pinfo.block_size} '
-                       f'regs={pinfo.num_regs}'),
+            'kernel': ('mlgk_solve_small' if backend.last.get('small_kernel')
+                       else 'mlgk_solve') + f' grid={backend.last.get("grid")}'
+                      f' smem={backend.last.get("smem_bytes")}',
         },
         'clocks': clocks,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        rate, cores, n_pairs, dt = cpu_sample_rate(96)
+    if cpu is not None:
+        rate, cores, n_pairs, dt, what = cpu
         line['cpu_baseline'] = {
             'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': f'{n_pairs} pairs (upper triangle of the first 96 '
-                      f'graphs), {dt:.1f} s, float64 dense Kronecker solve + '
-                      'adjoint Jacobian (oracle/mlgk_oracle.py)'}
-    if world == 1 and not args.no_reference_gpu:
-        line['reference_gpu'] = reference_gpu_rate(n, kernel.q)
+            'sample': f'{n_pairs} pairs ({what}), {dt:.1f} s, float64 dense '
+                      'Kronecker solve + adjoint Jacobian '
+                      '(oracle/mlgk_oracle.py)'}
+    if world == 1 and workload == 'c3' and not args.no_reference_gpu:
+        line['reference_gpu'] = reference_gpu_rate(2000, kernel.q)
+    cleanup()
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + '\n').encode())
     if world > 1:
@@ -463,11 +700,15 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--tile-rows', type=int, default=0,
-                    help='rows per tile launch; 0 = about 8 tiles per rank')
+    ap.add_argument('--workload', default='', choices=['', 'c3', 'c5'],
+                    help='default: c3 on one GPU, c5 on several')
+    ap.add_argument('--tile-cols', type=int, default=0,
+                    help='C5: columns per tile; 0 = about 8 tiles per rank')
     ap.add_argument('--block-size', type=int, default=0)
     ap.add_argument('--slots-per-lane', type=int, default=0)
-    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--e2e-steps', type=int, default=0,
+                    help='0 = as many as --steps')
+    ap.add_argument('--parity-samples', type=int, default=1000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-reference-gpu', action='store_true')
     ap.add_argument('--nvrtc-extra', default='',

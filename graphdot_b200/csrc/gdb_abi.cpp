@@ -14,12 +14,15 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -83,7 +86,11 @@ struct gdb_context_s {
     int device = 0;
     cudaDeviceProp prop{};
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // device->host copies of finished column blocks
     cudaEvent_t ev[6] = {};
+    cudaEvent_t ev_copy = nullptr;        // last copy issued on copy_stream
+    std::vector<cudaEvent_t> tile_ev;     // per launch: kernel done, copy done
+    struct gdb_pool *pool = nullptr;      // host threads of the collection step
     // driver entry points
     CUresult (*cuModuleLoadData)(CUmodule *, const void *) = nullptr;
     CUresult (*cuModuleUnload)(CUmodule) = nullptr;
@@ -137,7 +144,10 @@ extern "C" int gdb_context_create(int device, gdb_context_t *out) {
         fprintf(stderr, "graphdot_b200: warning: device %s is sm_%d%d; kernels are built for sm_100a\n", c->prop.name,
                 c->prop.major, c->prop.minor);
     RT(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    RT(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) RT(cudaEventCreate(&e));
+    RT(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+    RT(cudaEventRecord(c->ev_copy, c->copy_stream));
     int rc;
     if ((rc = load_entry("cuModuleLoadData", c->cuModuleLoadData))) return rc;
     if ((rc = load_entry("cuModuleUnload", c->cuModuleUnload))) return rc;
@@ -149,8 +159,8 @@ extern "C" int gdb_context_create(int device, gdb_context_t *out) {
     if ((rc = load_entry("cuOccupancyMaxActiveBlocksPerMultiprocessor", c->cuOccupancyMaxActiveBlocksPerMultiprocessor)))
         return rc;
     if ((rc = load_entry("cuGetErrorString", c->cuGetErrorString))) return rc;
-    RT(cudaMalloc(&c->counters.ptr, 64));
-    c->counters.cap = 64;
+    RT(cudaMalloc(&c->counters.ptr, 4096));
+    c->counters.cap = 4096;
     *out = c;
     return GDB_OK;
 }
@@ -177,10 +187,13 @@ extern "C" int gdb_context_synchronize(gdb_context_t c) {
     if (!c) return gdb_fail(GDB_ERR_INVALID, "null context");
     RT(cudaSetDevice(c->device));
     RT(cudaStreamSynchronize(c->stream));
+    RT(cudaStreamSynchronize(c->copy_stream));
+    RT(cudaGetLastError());
     return GDB_OK;
 }
 
 extern "C" int gdb_program_destroy(gdb_program_t p);
+void gdb_pool_destroy(struct gdb_pool *p);
 
 extern "C" int gdb_context_destroy(gdb_context_t c) {
     if (!c) return GDB_OK;
@@ -194,7 +207,12 @@ extern "C" int gdb_context_destroy(gdb_context_t c) {
     for (DevBuf *b : {&c->jobs, &c->starts, &c->gram, &c->grad, &c->scratch, &c->counters, &c->norm_diag, &c->norm_ddiag})
         if (b->ptr) cudaFree(b->ptr);
     for (auto &e : c->ev) cudaEventDestroy(e);
+    for (auto &e : c->tile_ev) cudaEventDestroy(e);
+    cudaEventDestroy(c->ev_copy);
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
+    if (c->pool) gdb_pool_destroy(c->pool);
     delete c;
     return GDB_OK;
 }
@@ -211,6 +229,17 @@ extern "C" int gdb_host_free(void *p) {
     return GDB_OK;
 }
 
+extern "C" int gdb_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return gdb_fail(GDB_ERR_INVALID, "gdb_host_register: null argument");
+    RT(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return GDB_OK;
+}
+
+extern "C" int gdb_host_unregister(void *p) {
+    if (p) RT(cudaHostUnregister(p));
+    return GDB_OK;
+}
+
 // ---------------------------------------------------------------------------
 // program
 // ---------------------------------------------------------------------------
@@ -224,7 +253,7 @@ struct gdb_program_s {
     std::string source, log;
     gdb_program_info info{};
     uint32_t theta_size[3] = {};
-    int eval_gradient = 0, nodal = 0, wpt = 1, rpw = 8, adj = 4;
+    int eval_gradient = 0, nodal = 0, symmetric = 0, diagonal = 0, wpt = 1, rpw = 8, adj = 4;
     int refcount = 1;
 };
 
@@ -388,6 +417,8 @@ extern "C" int gdb_program_create(gdb_context_t c, const gdb_program_desc *d, gd
     p->log = log;
     p->eval_gradient = d->eval_gradient;
     p->nodal = d->nodal;
+    p->symmetric = d->symmetric ? 1 : 0;
+    p->diagonal = d->diagonal ? 1 : 0;
     p->wpt = pick_wpt(d);
     p->rpw = pick_rpw(d);
     p->adj = pick_adj(d);
@@ -489,8 +520,15 @@ extern "C" int gdb_graphset_create(gdb_context_t c, const gdb_layout *L, uint32_
         total += blob_bytes[k];
     }
     gs->bytes = total;
-    RT(cudaHostAlloc((void **)&gs->host, total, cudaHostAllocPortable));
-    RT(cudaMalloc((void **)&gs->dev, total));
+    {
+        cudaError_t e1 = cudaHostAlloc((void **)&gs->host, total, cudaHostAllocPortable);
+        cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc((void **)&gs->dev, total) : e1;
+        if (e2 != cudaSuccess) {
+            if (gs->host) cudaFreeHost(gs->host);
+            delete gs;
+            return gdb_fail(GDB_ERR_CUDA, "graph set of %llu bytes: %s", (unsigned long long)total, cudaGetErrorString(e2));
+        }
+    }
     gdb_graph_ref_host *table = reinterpret_cast<gdb_graph_ref_host *>(gs->host);
     uint64_t off = gs->table_bytes;
     for (uint32_t k = 0; k < n; ++k) {
@@ -592,62 +630,107 @@ extern "C" int gdb_graphset_destroy(gdb_graphset_t gs) {
 }
 
 // ---------------------------------------------------------------------------
+// host thread pool (collection of finished column blocks)
+// ---------------------------------------------------------------------------
+struct gdb_pool {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    std::function<void(size_t)> job;
+    size_t n_parts = 0, next = 0, done = 0;
+    uint64_t epoch = 0;
+    bool stop = false;
+
+    explicit gdb_pool(unsigned n) {
+        for (unsigned k = 0; k < n; ++k) workers.emplace_back([this] { loop(); });
+    }
+    ~gdb_pool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto &w : workers) w.join();
+    }
+    void loop() {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(mu);
+        while (true) {
+            cv.wait(lk, [&] { return stop || (epoch != seen && next < n_parts); });
+            if (stop) return;
+            while (next < n_parts) {
+                const size_t part = next++;
+                lk.unlock();
+                job(part);
+                lk.lock();
+                if (++done == n_parts) cv_done.notify_all();
+            }
+            seen = epoch;
+        }
+    }
+    // run f(0..n-1) on the workers and the calling thread; returns when all are done
+    void parallel_for(size_t n, std::function<void(size_t)> f) {
+        if (n == 0) return;
+        std::unique_lock<std::mutex> lk(mu);
+        job = std::move(f);
+        n_parts = n;
+        next = done = 0;
+        ++epoch;
+        cv.notify_all();
+        while (next < n_parts) {
+            const size_t part = next++;
+            lk.unlock();
+            job(part);
+            lk.lock();
+            ++done;
+        }
+        cv_done.wait(lk, [&] { return done == n_parts; });
+        n_parts = 0;
+    }
+};
+
+static gdb_pool *ctx_pool(gdb_context_t c) {
+    if (!c->pool) {
+        unsigned n = std::thread::hardware_concurrency();
+        if (const char *env = getenv("GDB_HOST_THREADS")) n = (unsigned)strtoul(env, nullptr, 10);
+        n = std::max(1u, std::min(n, 16u));
+        c->pool = new gdb_pool(n - 1);  // the calling thread takes part
+    }
+    return c->pool;
+}
+
+void gdb_pool_destroy(gdb_pool *p) { delete p; }
+
+// ---------------------------------------------------------------------------
 // solve
 // ---------------------------------------------------------------------------
-extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gdb_solve_args *a) {
-    if (!c || !p || !gs || !a) return gdb_fail(GDB_ERR_INVALID, "gdb_solve: null argument");
-    if (p->ctx != c || gs->ctx != c) return gdb_fail(GDB_ERR_INVALID, "program / graph set belong to another context");
-    if (!a->starts) return gdb_fail(GDB_ERR_INVALID, "gdb_solve: starts is required");
-    // host output buffers are only needed when the results are copied back
-    if (!a->keep_on_device && !a->gramian) return gdb_fail(GDB_ERR_INVALID, "gdb_solve: gramian buffer required");
-    if (!a->keep_on_device && p->eval_gradient && !a->gradient)
-        return gdb_fail(GDB_ERR_INVALID, "program evaluates gradients: gradient buffer required");
-    if (p->eval_gradient && a->nJ != p->layout[7])
-        return gdb_fail(GDB_ERR_INVALID, "nJ = %u but the program has %u hyper-parameters", a->nJ, p->layout[7]);
-    uint64_t n_jobs = 0;
-    if (a->job_mode == GDB_JOBS_LIST) {
-        if (!a->jobs && a->n_jobs) return gdb_fail(GDB_ERR_INVALID, "job list missing");
-        n_jobs = a->n_jobs;
-        for (uint64_t k = 0; k < 2 * n_jobs; ++k)
-            if (a->jobs[k] >= gs->n) return gdb_fail(GDB_ERR_INVALID, "job %llu references graph %u of %u", (unsigned long long)(k / 2), a->jobs[k], gs->n);
-    } else if (a->job_mode == GDB_JOBS_RECT) {
-        if (a->i1 > gs->n || a->j1 > gs->n || a->i0 > a->i1 || a->j0 > a->j1) return gdb_fail(GDB_ERR_INVALID, "job rectangle out of range");
-        n_jobs = (uint64_t)(a->i1 - a->i0) * (a->j1 - a->j0);
-    } else if (a->job_mode == GDB_JOBS_TRIU) {
-        if (a->i1 > gs->n || a->j1 > gs->n || a->i0 > a->i1 || a->i1 > a->j1) return gdb_fail(GDB_ERR_INVALID, "job triangle out of range");
-        const uint64_t rows = a->i1 - a->i0, m = a->j1 - a->i0;
-        n_jobs = rows * m - rows * (rows - 1) / 2;
-    } else {
-        return gdb_fail(GDB_ERR_INVALID, "unknown job_mode %d", a->job_mode);
-    }
-    if (a->n_starts < gs->n) return gdb_fail(GDB_ERR_INVALID, "starts has %u entries for %u graphs", a->n_starts, gs->n);
-    a->kernel_ms = a->h2d_ms = a->d2h_ms = 0.f;
-    a->cg_iterations = a->matvec_products = a->vector_elements = 0;
-    a->h2d_bytes = a->d2h_bytes = 0;
-    a->n_launches = 0;
-    if (n_jobs == 0) return GDB_OK;
-    if (a->store_diag && (a->nX != gs->n || a->nY != 1 || n_jobs != gs->n))
-        return gdb_fail(GDB_ERR_INVALID, "store_diag needs one (i, i) job per graph and nX = number of graphs");
-    if (a->normalize) {
-        if (p->nodal) return gdb_fail(GDB_ERR_INVALID, "fused normalization is defined for graph-level outputs only");
-        if (c->norm_gs != gs || c->norm_n != gs->n) return gdb_fail(GDB_ERR_INVALID, "normalize: no self-similarities stored for this graph set");
-        if (p->eval_gradient && c->norm_nj != a->nJ) return gdb_fail(GDB_ERR_INVALID, "normalize: stored self-similarities carry no matching Jacobian");
-    }
+namespace {
 
-    RT(cudaSetDevice(c->device));
-    cudaStream_t st = a->stream ? static_cast<cudaStream_t>(a->stream) : c->stream;
-    const uint64_t plane = (uint64_t)a->nX * a->nY;
-    const uint64_t grad_floats = p->eval_gradient ? plane * a->nJ : 0;
-    int rc;
-    if ((rc = dev_reserve(c->gram, plane * 4))) return rc;
-    if (grad_floats && (rc = dev_reserve(c->grad, grad_floats * 4))) return rc;
-    if ((rc = dev_reserve(c->starts, (size_t)a->n_starts * 4))) return rc;
-    if (a->job_mode == GDB_JOBS_LIST && (rc = dev_reserve(c->jobs, n_jobs * 8))) return rc;
+struct LaunchCfg {
+    CUfunction fn = nullptr;
+    int kind = 0;  // 0 general, 1 small, 2 large (cluster)
+    uint64_t grid = 0, smem = 0, scratch_stride = 0;
+    uint32_t graphs_need = 0, cluster = 1;
+    int block = 0;
+};
 
-    // ---- launch configuration -------------------------------------------------
+struct Tile {
+    uint32_t i0, i1, j0, j1;
+    uint64_t n_jobs;
+    uint64_t c0, c1;  // output columns complete once this launch (and all earlier ones) finished
+};
+
+uint64_t triu_jobs(uint64_t lo, uint64_t hi, uint64_t j1) {
+    const uint64_t rows = hi - lo, m = j1 - lo;
+    return rows * m - rows * (rows - 1) / 2;
+}
+
+}  // namespace
+
+static int pick_kernel(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, const gdb_solve_args *a, LaunchCfg &k) {
     const int block = p->info.block_size;
     const int nvec = p->eval_gradient ? 6 : 5;
-    const uint64_t maxN = (uint64_t)gs->max_node[0] * (a->job_mode == GDB_JOBS_LIST || true ? gs->max_node[0] : gs->max_node[1]);
+    const uint64_t maxN = (uint64_t)gs->max_node[0] * gs->max_node[0];
     const uint64_t maxNpad = (maxN + 3) & ~3ull;
     const uint64_t graphs_need = (uint64_t)gs->max_blob[0] + gs->max_blob[1];  // small kernel: whole blobs
     const uint64_t idx_need = (uint64_t)gs->max_idx[0] + gs->max_idx[1];       // general kernel: row index + edges
@@ -667,9 +750,12 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     } else {
         smem = 0;
     }
+    k.fn = p->fn;
+    k.kind = 0;
+    k.block = block;
+    k.graphs_need = (uint32_t)graphs_need;
     // small-pair kernel: blobs + cached edge products + diag + 4 vectors (x2 with
     // gradients) of the largest possible pair must fit in shared memory
-    CUfunction fn = p->fn;
     {
         const uint64_t nrhs = p->eval_gradient ? 2 : 1;
         // work area of mlgk_solve_small (same layout, from the maxima of the graph set):
@@ -691,26 +777,167 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
         const bool nodal_grad = p->eval_gradient && p->nodal != GDB_NODAL_NONE;
         if (gs->index16 && small_need <= small_cap && mapped && wmax < (1u << 24) && !nodal_grad &&
             !getenv("GDB_FORCE_GENERAL")) {
-            fn = p->fn_small;
+            k.fn = p->fn_small;
+            k.kind = 1;
             smem = small_need;
             spill = false;
         }
     }
-    a->used_small_kernel = (fn == p->fn_small);
+    (void)a;
     int blocks_per_sm = 0;
-    DRV(c, c->cuOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, block, (size_t)smem));
+    DRV(c, c->cuOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k.fn, block, (size_t)smem));
     uint64_t grid = (uint64_t)c->prop.multiProcessorCount * blocks_per_sm;
     if (spill) {
         // bound the arena: at most ~1/4 of device memory
         const uint64_t per_cta = nvec * maxNpad * 4;
         const uint64_t budget = c->prop.totalGlobalMem / 4;
         grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, budget / std::max<uint64_t>(per_cta, 1)));
+        int rc;
         if ((rc = dev_reserve(c->scratch, grid * per_cta))) return rc;
+        k.scratch_stride = nvec * maxNpad;
     }
-    grid = std::min<uint64_t>(grid, n_jobs);
+    k.grid = grid;
+    k.smem = smem;
+    return GDB_OK;
+}
+
+// Every output position a job set can touch must lie inside the nX x nY
+// output: a wrong starts / row0 / nX from an ABI caller is an error here, not
+// an out-of-bounds device write.
+static int check_extents(gdb_program_t p, gdb_graphset_t gs, const gdb_solve_args *a, uint64_t n_jobs) {
+    auto ext = [&](uint32_t g) -> uint64_t {
+        if (p->nodal == GDB_NODAL_FULL) return gs->n_node[g];
+        if (p->nodal == GDB_NODAL_BLOCK) return (uint64_t)gs->n_node[g] * gs->n_node[g];
+        return 1;
+    };
+    auto row_ok = [&](uint32_t g) { return (uint64_t)a->starts[g] >= a->row0 && (uint64_t)a->starts[g] - a->row0 + ext(g) <= a->nX; };
+    auto col_ok = [&](uint32_t g) { return (uint64_t)a->starts[g] >= a->col0 && (uint64_t)a->starts[g] - a->col0 + ext(g) <= a->nY; };
+    const bool cols = !p->diagonal && p->nodal != GDB_NODAL_BLOCK;
+    if (a->job_mode == GDB_JOBS_LIST) {
+        for (uint64_t k = 0; k < n_jobs; ++k) {
+            const uint32_t i = a->jobs[2 * k], j = a->jobs[2 * k + 1];
+            if (!row_ok(i) || (cols && !col_ok(j)) || (cols && p->symmetric && (!row_ok(j) || !col_ok(i))))
+                return gdb_fail(GDB_ERR_INVALID, "job %llu (%u, %u) writes outside the %u x %u output", (unsigned long long)k, i, j, a->nX, a->nY);
+        }
+        return GDB_OK;
+    }
+    const uint32_t jlo = a->job_mode == GDB_JOBS_TRIU ? a->i0 : a->j0;
+    for (uint32_t i = a->i0; i < a->i1; ++i)
+        if (!row_ok(i) || (cols && p->symmetric && !col_ok(i)))
+            return gdb_fail(GDB_ERR_INVALID, "graph %u: starts[] places its row outside the %u x %u output", i, a->nX, a->nY);
+    if (cols)
+        for (uint32_t j = jlo; j < a->j1; ++j)
+            if (!col_ok(j) || (p->symmetric && !row_ok(j)))
+                return gdb_fail(GDB_ERR_INVALID, "graph %u: starts[] places its column outside the %u x %u output", j, a->nX, a->nY);
+    return GDB_OK;
+}
+
+extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gdb_solve_args *a) {
+    if (!c || !p || !gs || !a) return gdb_fail(GDB_ERR_INVALID, "gdb_solve: null argument");
+    if (p->ctx != c || gs->ctx != c) return gdb_fail(GDB_ERR_INVALID, "program / graph set belong to another context");
+    if (!a->starts) return gdb_fail(GDB_ERR_INVALID, "gdb_solve: starts is required");
+    const bool own_dev = a->gramian_dev != nullptr;
+    const bool to_host = !a->keep_on_device && (a->gramian != nullptr || !own_dev);
+    // host output buffers are only needed when the results are copied back
+    if (to_host && !a->gramian) return gdb_fail(GDB_ERR_INVALID, "gdb_solve: gramian buffer required");
+    if (to_host && p->eval_gradient && !a->gradient)
+        return gdb_fail(GDB_ERR_INVALID, "program evaluates gradients: gradient buffer required");
+    if (own_dev && p->eval_gradient && !a->gradient_dev)
+        return gdb_fail(GDB_ERR_INVALID, "program evaluates gradients: gradient_dev required next to gramian_dev");
+    if (p->eval_gradient && a->nJ != p->layout[7])
+        return gdb_fail(GDB_ERR_INVALID, "nJ = %u but the program has %u hyper-parameters", a->nJ, p->layout[7]);
+    if (a->out_dtype != GDB_OUT_NONE) {
+        if (a->out_dtype != GDB_OUT_F64 && a->out_dtype != GDB_OUT_F32) return gdb_fail(GDB_ERR_INVALID, "unknown out_dtype %d", a->out_dtype);
+        if (!to_host || !a->out_gram || (p->eval_gradient && !a->out_grad))
+            return gdb_fail(GDB_ERR_INVALID, "out_dtype needs host staging (gramian / gradient) and out_gram / out_grad");
+        if (a->async) return gdb_fail(GDB_ERR_INVALID, "async solves cannot collect (out_dtype)");
+    }
+    uint64_t n_jobs = 0;
+    if (a->job_mode == GDB_JOBS_LIST) {
+        if (!a->jobs && a->n_jobs) return gdb_fail(GDB_ERR_INVALID, "job list missing");
+        n_jobs = a->n_jobs;
+        for (uint64_t k = 0; k < 2 * n_jobs; ++k)
+            if (a->jobs[k] >= gs->n) return gdb_fail(GDB_ERR_INVALID, "job %llu references graph %u of %u", (unsigned long long)(k / 2), a->jobs[k], gs->n);
+    } else if (a->job_mode == GDB_JOBS_RECT) {
+        if (a->i1 > gs->n || a->j1 > gs->n || a->i0 > a->i1 || a->j0 > a->j1) return gdb_fail(GDB_ERR_INVALID, "job rectangle out of range");
+        n_jobs = (uint64_t)(a->i1 - a->i0) * (a->j1 - a->j0);
+    } else if (a->job_mode == GDB_JOBS_TRIU) {
+        if (a->i1 > gs->n || a->j1 > gs->n || a->i0 > a->i1 || a->i1 > a->j1) return gdb_fail(GDB_ERR_INVALID, "job triangle out of range");
+        n_jobs = triu_jobs(a->i0, a->i1, a->j1);
+    } else {
+        return gdb_fail(GDB_ERR_INVALID, "unknown job_mode %d", a->job_mode);
+    }
+    if (a->n_starts < gs->n) return gdb_fail(GDB_ERR_INVALID, "starts has %u entries for %u graphs", a->n_starts, gs->n);
+    a->kernel_ms = a->h2d_ms = a->d2h_ms = 0.f;
+    a->cg_iterations = a->matvec_products = a->vector_elements = 0;
+    a->h2d_bytes = a->d2h_bytes = 0;
+    a->n_launches = 0;
+    if (n_jobs == 0) return GDB_OK;
+    if (a->store_diag && (a->nX != gs->n || a->nY != 1 || n_jobs != gs->n))
+        return gdb_fail(GDB_ERR_INVALID, "store_diag needs one (i, i) job per graph and nX = number of graphs");
+    if (a->normalize) {
+        if (p->nodal) return gdb_fail(GDB_ERR_INVALID, "fused normalization is defined for graph-level outputs only");
+        if (c->norm_gs != gs || c->norm_n != gs->n) return gdb_fail(GDB_ERR_INVALID, "normalize: no self-similarities stored for this graph set");
+        if (p->eval_gradient && c->norm_nj != a->nJ) return gdb_fail(GDB_ERR_INVALID, "normalize: stored self-similarities carry no matching Jacobian");
+    }
+    int rc;
+    if ((rc = check_extents(p, gs, a, n_jobs))) return rc;
+
+    RT(cudaSetDevice(c->device));
+    cudaStream_t st = a->stream ? static_cast<cudaStream_t>(a->stream) : c->stream;
+    const uint64_t plane = (uint64_t)a->nX * a->nY;
+    const uint64_t grad_floats = p->eval_gradient ? plane * a->nJ : 0;
+    float *d_gram = a->gramian_dev, *d_grad = a->gradient_dev;
+    if (!own_dev) {
+        if ((rc = dev_reserve(c->gram, plane * 4))) return rc;
+        if (grad_floats && (rc = dev_reserve(c->grad, grad_floats * 4))) return rc;
+        d_gram = static_cast<float *>(c->gram.ptr);
+        d_grad = static_cast<float *>(c->grad.ptr);
+    }
+    if ((rc = dev_reserve(c->starts, (size_t)a->n_starts * 4))) return rc;
+    if (a->job_mode == GDB_JOBS_LIST && (rc = dev_reserve(c->jobs, n_jobs * 8))) return rc;
+
+    LaunchCfg cfg;
+    if ((rc = pick_kernel(c, p, gs, a, cfg))) return rc;
+    a->used_small_kernel = cfg.kind == 1;
+
+    // ---- launch plan: one launch, or one per block of rows / columns -------------
+    std::vector<Tile> tiles;
+    auto col_at = [&](uint32_t g) -> uint64_t {  // first output column of graph g
+        if (g >= a->n_starts) return a->nY;
+        const uint64_t s = (uint64_t)a->starts[g] - a->col0;
+        return std::min<uint64_t>(s, a->nY);
+    };
+    const bool can_tile = a->tile > 0 && !p->diagonal && p->nodal != GDB_NODAL_BLOCK &&
+                          ((a->job_mode == GDB_JOBS_TRIU && p->symmetric && a->i1 == a->j1) || a->job_mode == GDB_JOBS_RECT);
+    if (!can_tile) {
+        // one launch.  A rectangle completes the columns of its graphs j0..j1 only
+        // (a tile of a larger device-resident matrix is copied back alone)
+        const bool rect = a->job_mode == GDB_JOBS_RECT && !p->diagonal && p->nodal != GDB_NODAL_BLOCK;
+        tiles.push_back({a->i0, a->i1, a->j0, a->j1, n_jobs, rect ? col_at(a->j0) : 0, rect ? col_at(a->j1) : a->nY});
+    } else if (a->job_mode == GDB_JOBS_TRIU) {
+        for (uint32_t lo = a->i0; lo < a->i1; lo += a->tile) {
+            const uint32_t hi = std::min(a->i1, lo + a->tile);
+            tiles.push_back({lo, hi, lo, a->j1, triu_jobs(lo, hi, a->j1), col_at(lo), col_at(hi)});
+        }
+    } else {
+        for (uint32_t lo = a->j0; lo < a->j1; lo += a->tile) {
+            const uint32_t hi = std::min(a->j1, lo + a->tile);
+            tiles.push_back({a->i0, a->i1, lo, hi, (uint64_t)(a->i1 - a->i0) * (hi - lo), col_at(lo), col_at(hi)});
+        }
+    }
+    const size_t nt = tiles.size();
+    if ((rc = dev_reserve(c->counters, nt * 32))) return rc;
+    // events: [0] start, [1] inputs done, [2] kernels done, [3] copies done + per tile (kernel done, copy done)
+    while (c->tile_ev.size() < 2 * nt) {
+        cudaEvent_t e;
+        RT(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->tile_ev.push_back(e);
+    }
 
     // ---- inputs -----------------------------------------------------------------
     RT(cudaEventRecord(c->ev[0], st));
+    if (!own_dev) RT(cudaStreamWaitEvent(st, c->ev_copy, 0));  // earlier async copies out of the context's buffers are done
     if (a->upload_graphs) {
         RT(cudaMemcpyAsync(gs->dev, gs->host, gs->bytes, cudaMemcpyHostToDevice, st));
         a->h2d_bytes += gs->bytes;
@@ -721,34 +948,32 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     }
     RT(cudaMemcpyAsync(c->starts.ptr, a->starts, (size_t)a->n_starts * 4, cudaMemcpyHostToDevice, st));
     a->h2d_bytes += (uint64_t)a->n_starts * 4;
-    RT(cudaMemsetAsync(c->counters.ptr, 0, 64, st));
-    RT(cudaMemsetAsync(c->gram.ptr, 0, plane * 4, st));
-    if (grad_floats) RT(cudaMemsetAsync(c->grad.ptr, 0, grad_floats * 4, st));
+    RT(cudaMemsetAsync(c->counters.ptr, 0, nt * 32, st));
+    if (!own_dev) {
+        RT(cudaMemsetAsync(d_gram, 0, plane * 4, st));
+        if (grad_floats) RT(cudaMemsetAsync(d_grad, 0, grad_floats * 4, st));
+    }
 
     std::vector<unsigned char> params(p->layout[0], 0);
     gdb_params_fixed_host f{};
     f.graphs = reinterpret_cast<uint64_t>(gs->dev);
     f.jobs = reinterpret_cast<uint64_t>(c->jobs.ptr);
     f.starts = reinterpret_cast<uint64_t>(c->starts.ptr);
-    f.gram = reinterpret_cast<uint64_t>(c->gram.ptr);
-    f.grad = reinterpret_cast<uint64_t>(c->grad.ptr);
+    f.gram = reinterpret_cast<uint64_t>(d_gram);
+    f.grad = reinterpret_cast<uint64_t>(d_grad);
     f.scratch = reinterpret_cast<uint64_t>(c->scratch.ptr);
-    f.counters = reinterpret_cast<uint64_t>(c->counters.ptr);
-    f.scratch_stride = spill ? nvec * maxNpad : 0;
-    f.n_jobs = n_jobs;
+    f.scratch_stride = cfg.scratch_stride;
     f.job_mode = (uint32_t)a->job_mode;
-    f.i0 = a->i0, f.i1 = a->i1, f.j0 = a->j0, f.j1 = a->j1;
     f.nX = a->nX, f.nY = a->nY, f.nJ = a->nJ;
     f.q = a->q, f.eps = a->eps, f.ftol = a->ftol, f.gtol = a->gtol;
-    f.smem_bytes = (uint32_t)smem;
+    f.smem_bytes = (uint32_t)cfg.smem;
     f.row0 = a->row0, f.col0 = a->col0;
-    f.blob_slot = (uint32_t)graphs_need;
+    f.blob_slot = cfg.graphs_need;
     if (a->normalize) {
         f.norm_n = c->norm_n;
         f.norm_diag = reinterpret_cast<uint64_t>(c->norm_diag.ptr);
         f.norm_ddiag = reinterpret_cast<uint64_t>(c->norm_ddiag.ptr);
     }
-    memcpy(params.data(), &f, sizeof f);
     const void *thetas[3] = {a->node_theta, a->edge_theta, a->p_theta};
     for (int k = 0; k < 3; ++k) {
         if (!p->theta_size[k]) continue;
@@ -758,40 +983,92 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     }
     void *kargs[1] = {params.data()};
 
+    // planes copied back: all of them, or only the active ones when collecting
+    std::vector<uint32_t> planes;  // Jacobian planes to copy / collect, in output order
+    for (uint32_t k = 0; k < (p->eval_gradient ? a->nJ : 0u); ++k)
+        if (a->out_dtype == GDB_OUT_NONE || !a->plane_mask || a->plane_mask[k]) planes.push_back(k);
+
     RT(cudaEventRecord(c->ev[1], st));
-    DRV(c, c->cuLaunchKernel(fn, (unsigned)grid, 1, 1, (unsigned)block, 1, 1, (unsigned)smem, (CUstream)st, kargs, nullptr));
-    a->n_launches = 1;
-    a->grid = (uint32_t)grid;
-    a->smem_bytes = (uint32_t)smem;
+    for (size_t t = 0; t < nt; ++t) {
+        const Tile &T = tiles[t];
+        f.counters = reinterpret_cast<uint64_t>(c->counters.ptr) + t * 32;
+        f.n_jobs = T.n_jobs;
+        f.i0 = T.i0, f.i1 = T.i1, f.j0 = T.j0, f.j1 = T.j1;
+        memcpy(params.data(), &f, sizeof f);
+        const uint64_t grid = std::min<uint64_t>(cfg.grid, T.n_jobs);
+        DRV(c, c->cuLaunchKernel(cfg.fn, (unsigned)grid, 1, 1, (unsigned)cfg.block, 1, 1, (unsigned)cfg.smem, (CUstream)st, kargs, nullptr));
+        a->n_launches++;
+        a->grid = (uint32_t)grid;
+        if (to_host && T.c1 > T.c0) {
+            // the finished column block leaves on the copy stream while the next launch runs
+            RT(cudaEventRecord(c->tile_ev[2 * t], st));
+            RT(cudaStreamWaitEvent(c->copy_stream, c->tile_ev[2 * t], 0));
+            const uint64_t off = T.c0 * a->nX, cnt = (T.c1 - T.c0) * a->nX;
+            RT(cudaMemcpyAsync(a->gramian + off, d_gram + off, cnt * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+            for (uint32_t k : planes)
+                RT(cudaMemcpyAsync(a->gradient + k * plane + off, d_grad + k * plane + off, cnt * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+            a->d2h_bytes += cnt * 4 * (1 + planes.size());
+            RT(cudaEventRecord(c->tile_ev[2 * t + 1], c->copy_stream));
+        }
+    }
+    a->smem_bytes = (uint32_t)cfg.smem;
     RT(cudaEventRecord(c->ev[2], st));
     if (a->store_diag) {
         if ((rc = dev_reserve(c->norm_diag, plane * 4))) return rc;
-        RT(cudaMemcpyAsync(c->norm_diag.ptr, c->gram.ptr, plane * 4, cudaMemcpyDeviceToDevice, st));
+        RT(cudaMemcpyAsync(c->norm_diag.ptr, d_gram, plane * 4, cudaMemcpyDeviceToDevice, st));
         c->norm_nj = 0;
         if (grad_floats) {
             if ((rc = dev_reserve(c->norm_ddiag, grad_floats * 4))) return rc;
-            RT(cudaMemcpyAsync(c->norm_ddiag.ptr, c->grad.ptr, grad_floats * 4, cudaMemcpyDeviceToDevice, st));
+            RT(cudaMemcpyAsync(c->norm_ddiag.ptr, d_grad, grad_floats * 4, cudaMemcpyDeviceToDevice, st));
             c->norm_nj = a->nJ;
         }
         c->norm_n = gs->n;
         c->norm_gs = gs;
     }
-    unsigned long long counters[4] = {0, 0, 0, 0};
-    RT(cudaMemcpyAsync(counters, c->counters.ptr, sizeof counters, cudaMemcpyDeviceToHost, st));
-    if (!a->keep_on_device) {
-        RT(cudaMemcpyAsync(a->gramian, c->gram.ptr, plane * 4, cudaMemcpyDeviceToHost, st));
-        if (grad_floats) RT(cudaMemcpyAsync(a->gradient, c->grad.ptr, grad_floats * 4, cudaMemcpyDeviceToHost, st));
-        a->d2h_bytes = (plane + grad_floats) * 4;
+    if (to_host) RT(cudaEventRecord(c->ev_copy, c->copy_stream));
+    if (a->async) return GDB_OK;
+
+    std::vector<unsigned long long> counters(nt * 4, 0);
+    RT(cudaMemcpyAsync(counters.data(), c->counters.ptr, nt * 32, cudaMemcpyDeviceToHost, st));
+    // ---- collection: convert every finished column block on the host threads ----
+    if (to_host && a->out_dtype != GDB_OUT_NONE) {
+        gdb_pool *pool = ctx_pool(c);
+        for (size_t t = 0; t < nt; ++t) {
+            const Tile &T = tiles[t];
+            if (T.c1 <= T.c0) continue;
+            RT(cudaEventSynchronize(c->tile_ev[2 * t + 1]));
+            const uint64_t off = T.c0 * a->nX, cnt = (T.c1 - T.c0) * a->nX;
+            // one parallel pass over (planes x chunks) of this column block
+            const size_t chunk = 1u << 15, per_plane = (size_t)((cnt + chunk - 1) / chunk);
+            const int dt = a->out_dtype;
+            const float *g_src = a->gramian, *d_src = a->gradient;
+            void *g_dst = a->out_gram, *d_dst = a->out_grad;
+            const uint32_t *pl = planes.data();
+            pool->parallel_for(per_plane * (planes.size() + 1), [=](size_t part) {
+                const size_t m = part / per_plane, ch = part % per_plane;
+                const uint64_t lo = ch * chunk, hi = std::min<uint64_t>(cnt, lo + chunk);
+                const float *src = m == 0 ? g_src + off : d_src + pl[m - 1] * plane + off;
+                const uint64_t dst_off = m == 0 ? off : (m - 1) * plane + off;
+                if (dt == GDB_OUT_F64) {
+                    double *dst = static_cast<double *>(m == 0 ? g_dst : d_dst) + dst_off;
+                    for (uint64_t k = lo; k < hi; ++k) dst[k] = (double)src[k];
+                } else {
+                    float *dst = static_cast<float *>(m == 0 ? g_dst : d_dst) + dst_off;
+                    memcpy(dst + lo, src + lo, (hi - lo) * 4);
+                }
+            });
+        }
     }
-    RT(cudaEventRecord(c->ev[3], st));
     RT(cudaStreamSynchronize(st));
+    if (to_host) RT(cudaStreamSynchronize(c->copy_stream));
     RT(cudaGetLastError());
     cudaEventElapsedTime(&a->h2d_ms, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&a->kernel_ms, c->ev[1], c->ev[2]);
-    cudaEventElapsedTime(&a->d2h_ms, c->ev[2], c->ev[3]);
-    a->cg_iterations = counters[1];
-    a->matvec_products = counters[2];
-    a->vector_elements = counters[3];
+    for (size_t t = 0; t < nt; ++t) {
+        a->cg_iterations += counters[4 * t + 1];
+        a->matvec_products += counters[4 * t + 2];
+        a->vector_elements += counters[4 * t + 3];
+    }
     return GDB_OK;
 }
 

@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "gdb_internal.h"
@@ -30,6 +32,7 @@ struct Sizes {
 struct Nz {
     uint32_t key;  // (trow, tcol, row, col) packed: trow<<19 | tcol<<6 | row<<3 | col
     uint32_t i, j, e;
+    uint32_t ord;  // position in the reference's [edges ; swapped edges] list (duplicate resolution)
 };
 
 bool collect(const gdb_graph_src *g, std::vector<Nz> &nz) {
@@ -38,19 +41,17 @@ bool collect(const gdb_graph_src *g, std::vector<Nz> &nz) {
     for (uint32_t k = 0; k < g->n_edge; ++k) {
         const uint32_t i = g->edge_i[k], j = g->edge_j[k];
         if (i >= g->n_node || j >= g->n_node) return false;
-        nz.push_back({0, i, j, k});
-        if (i != j) nz.push_back({0, j, i, k});
+        nz.push_back({0, i, j, k, k});
+        if (i != j) nz.push_back({0, j, i, k, g->n_edge + k});
     }
     for (auto &z : nz) z.key = ((z.i >> 3) << 19) | ((z.j >> 3) << 6) | ((z.i & 7) << 3) | (z.j & 7);
-    std::sort(nz.begin(), nz.end(), [](const Nz &a, const Nz &b) { return a.key < b.key; });
-    // duplicate directed entries (multi-edges): keep the last, like a dense assignment
+    // duplicate directed entries (multi-edges): keep the FIRST of the list
+    // [edges ; swapped edges], like the reference's np.unique(..., return_index=True)
+    // (_octilegraph.py:141-158)
+    std::sort(nz.begin(), nz.end(), [](const Nz &a, const Nz &b) { return a.key != b.key ? a.key < b.key : a.ord < b.ord; });
     size_t w = 0;
-    for (size_t r = 0; r < nz.size(); ++r) {
-        if (w > 0 && nz[w - 1].key == nz[r].key)
-            nz[w - 1] = nz[r];
-        else
-            nz[w++] = nz[r];
-    }
+    for (size_t r = 0; r < nz.size(); ++r)
+        if (w == 0 || nz[w - 1].key != nz[r].key) nz[w++] = nz[r];
     nz.resize(w);
     return true;
 }
@@ -238,4 +239,70 @@ extern "C" int gdb_graph_pack(const gdb_layout *L, const gdb_graph_src *g, void 
     }
     if (g->pool_bytes) std::memcpy(base + s.off_pool, g->pool, g->pool_bytes);
     return GDB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// batch packing: k graphs from column-concatenated inputs on a few host threads
+// ---------------------------------------------------------------------------
+extern "C" int gdb_graphs_pack_batch(const gdb_layout *L, const gdb_batch_src *src, uint64_t *blob_off, void *blobs,
+                                     uint64_t capacity, int32_t n_threads) {
+    if (!L || !src || !blob_off || !src->node_off || !src->edge_off)
+        return gdb_fail(GDB_ERR_INVALID, "gdb_graphs_pack_batch: null argument");
+    const uint32_t n = src->n_graphs;
+    auto graph_at = [&](uint32_t g) {
+        gdb_graph_src s{};
+        const uint64_t n0 = src->node_off[g], e0 = src->edge_off[g];
+        s.n_node = (uint32_t)(src->node_off[g + 1] - n0);
+        s.n_edge = (uint32_t)(src->edge_off[g + 1] - e0);
+        s.nodes = static_cast<const uint8_t *>(src->nodes) + n0 * L->node_size;
+        s.edge_i = src->edge_i + e0;
+        s.edge_j = src->edge_j + e0;
+        s.edge_w = src->edge_w ? src->edge_w + e0 : nullptr;
+        s.edge_labels = src->edge_labels ? static_cast<const uint8_t *>(src->edge_labels) + e0 * L->edge_label_size : nullptr;
+        if (src->pool_off) {
+            s.pool = static_cast<const uint8_t *>(src->pool) + src->pool_off[g];
+            s.pool_bytes = (uint32_t)(src->pool_off[g + 1] - src->pool_off[g]);
+        }
+        return s;
+    };
+    unsigned nt = n_threads > 0 ? (unsigned)n_threads : std::thread::hardware_concurrency();
+    nt = std::max(1u, std::min(nt, std::max(1u, n / 64u)));
+    std::vector<int> status(nt, GDB_OK);
+    std::vector<std::string> message(nt);
+    auto run = [&](auto &&body) {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back([&, t] {
+                const uint32_t lo = (uint32_t)((uint64_t)n * t / nt), hi = (uint32_t)((uint64_t)n * (t + 1) / nt);
+                for (uint32_t g = lo; g < hi && status[t] == GDB_OK; ++g) {
+                    const int rc = body(g);
+                    if (rc != GDB_OK) {
+                        status[t] = rc;
+                        message[t] = "graph " + std::to_string(g) + ": " + gdb_last_error();
+                    }
+                }
+            });
+        for (auto &t : th) t.join();
+        for (unsigned t = 0; t < nt; ++t)
+            if (status[t] != GDB_OK) return gdb_fail(status[t], "%s", message[t].c_str());
+        return GDB_OK;
+    };
+    if (!blobs) {
+        int rc = run([&](uint32_t g) {
+            const gdb_graph_src s = graph_at(g);
+            uint64_t bytes = 0;
+            const int r = gdb_graph_packed_size(L, &s, &bytes);
+            blob_off[g + 1] = bytes;
+            return r;
+        });
+        if (rc) return rc;
+        blob_off[0] = 0;
+        for (uint32_t g = 0; g < n; ++g) blob_off[g + 1] += blob_off[g];
+        return GDB_OK;
+    }
+    if (blob_off[n] > capacity) return gdb_fail(GDB_ERR_INVALID, "gdb_graphs_pack_batch: blob buffer too small");
+    return run([&](uint32_t g) {
+        const gdb_graph_src s = graph_at(g);
+        return gdb_graph_pack(L, &s, static_cast<uint8_t *>(blobs) + blob_off[g], blob_off[g + 1] - blob_off[g]);
+    });
 }

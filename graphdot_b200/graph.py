@@ -351,7 +351,11 @@ class Graph:
             elif keys != node_keys:
                 raise TypeError(f'Node {idx} attributes {keys} inconsistent '
                                 f'with {node_keys}')
-        nodes = DataFrame({'!i': range(len(graph.nodes))})
+        # node ids in ITERATION order (the attribute columns below follow the
+        # same order; the packer sorts rows by '!i').  The reference numbers
+        # them 0..n-1 regardless (reference graph/_from_networkx.py:49), which
+        # misplaces attributes when integer labels are not iterated sorted.
+        nodes = DataFrame({'!i': np.array(list(graph.nodes), dtype=np.uint32)})
         for key in node_keys or []:
             nodes[key] = [a[key] for a in graph.nodes.values()]
 

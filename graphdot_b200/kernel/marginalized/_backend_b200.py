@@ -20,6 +20,7 @@ import uuid
 import numpy as np
 
 from ... import native
+from ...graph import DataFrame
 from ._backend import Backend
 
 _FROZEN = np.dtype([('_data', np.uint64), ('size', np.int32)], align=True)
@@ -261,6 +262,7 @@ class B200Backend(Backend):
 
     pair_jobs = PairJobs     # front ends may hand over implicit job grids
     fused_normalization = True   # store_diag= / normalize= are honoured
+    collect = None               # set below: front ends may fuse the collection
 
     @staticmethod
     def array(ndarray):
@@ -292,10 +294,20 @@ class B200Backend(Backend):
         self._graphsets = []     # small LRU of (key, GraphSet)
         self._graphset_cache = graphset_cache
         self.last = {}           # diagnostics of the most recent solve
+        self.resend_graphs = False   # True: every call re-sends the packed
+        #                              graphs host -> device (end-to-end timing)
+        self._inflight = []      # host inputs of asynchronous solves
+        self.totals = {}         # running sums over all solves (bench)
+        self.reset_totals()
         native.load()            # fail loudly if the library is missing
 
     def __deepcopy__(self, memo):
         return self              # kernels cloned by theta share the engine
+
+    def reset_totals(self):
+        self.totals.update(launches=0, solves=0, pairs=0, kernel_ms=0.0,
+                           cg_iterations=0, matvec_products=0,
+                           vector_elements=0, h2d_bytes=0, d2h_bytes=0)
 
     # -- context -----------------------------------------------------------
     @property
@@ -370,12 +382,106 @@ class B200Backend(Backend):
         graph.cookie[self.uuid] = packed
         return packed
 
+    def pack_graphs(self, graphs, n_threads=0):
+        """Octile-pack a list of graphs (cached in each ``graph.cookie``).
+        Graphs with scalar attributes only are packed in ONE native call from
+        column-concatenated arrays on several host threads
+        (``gdb_graphs_pack_batch``); graphs with variable-length features take
+        the per-graph path."""
+        out = [g.cookie.get(self.uuid) for g in graphs]
+        todo = [k for k, p in enumerate(out) if p is None]
+        if not todo:
+            return out
+        nl, el, weighted = self._layouts(graphs[todo[0]])
+        if len(todo) < 16 or nl.ptr_offsets or el.ptr_offsets:
+            for k in todo:
+                out[k] = self.pack_graph(graphs[k])
+            return out
+        lib = native.load()
+        G = [graphs[k] for k in todo]
+        n = len(G)
+
+        def cat(frames, key, counts):
+            try:
+                if all(type(f) is DataFrame for f in frames[:1]):
+                    a = np.concatenate([f._data[key] for f in frames])
+                else:
+                    a = np.concatenate([f[key] for f in frames])
+            except KeyError:
+                raise TypeError(f'attribute {key!r} missing in a graph: all '
+                                'nodes/edges must be of the same type')
+            if len(a) != counts.sum():
+                raise TypeError(f'attribute {key!r}: column length mismatch')
+            return a
+
+        nodes = [g.nodes for g in G]
+        edges = [g.edges for g in G]
+        ncnt = np.fromiter((len(f['!i']) for f in nodes), np.int64, n)
+        ecnt = np.fromiter((len(f['!i']) for f in edges), np.int64, n)
+        if not ncnt.all():
+            raise ValueError('graph without nodes')
+        noff = np.zeros(n + 1, np.uint64)
+        eoff = np.zeros(n + 1, np.uint64)
+        np.cumsum(ncnt, out=noff[1:])
+        np.cumsum(ecnt, out=eoff[1:])
+        # node rows in node-index order
+        ids = cat(nodes, '!i', ncnt).astype(np.int64)
+        local = np.arange(len(ids)) - np.repeat(noff[:-1].astype(np.int64),
+                                                ncnt)
+        order = None
+        if not np.array_equal(ids, local):
+            gid = np.repeat(np.arange(n), ncnt)
+            order = np.lexsort((ids, gid))
+        rows = np.zeros(len(ids), dtype=nl.dtype)
+        for key, dt, _ in nl.fields:
+            if key in nodes[0]:
+                col = cat(nodes, key, ncnt)
+                if col.dtype != dt:
+                    raise TypeError(
+                        f'node attribute {key!r} has mixed types; try '
+                        '`Graph.unify_datatype`.')
+                rows[key] = col if order is None else col[order]
+        labels = np.zeros(int(ecnt.sum()), dtype=el.dtype)
+        for key, dt, _ in el.fields:
+            if key in edges[0]:
+                col = cat(edges, key, ecnt)
+                if col.dtype != dt:
+                    raise TypeError(
+                        f'edge attribute {key!r} has mixed types; try '
+                        '`Graph.unify_datatype`.')
+                labels[key] = col
+        ei = np.ascontiguousarray(cat(edges, '!i', ecnt), dtype=np.uint32)
+        ej = np.ascontiguousarray(cat(edges, '!j', ecnt), dtype=np.uint32)
+        ew = (np.ascontiguousarray(cat(edges, '!w', ecnt), dtype=np.float32)
+              if weighted else None)
+        L = self._layout_c(nl, el, weighted)
+        src = native.BatchSrc(
+            n, noff.ctypes.data, eoff.ctypes.data, None, rows.ctypes.data,
+            ei.ctypes.data, ej.ctypes.data,
+            ew.ctypes.data if weighted else None, labels.ctypes.data, None)
+        boff = np.zeros(n + 1, np.uint64)
+        native.check(lib.gdb_graphs_pack_batch(
+            C.byref(L), C.byref(src), boff.ctypes.data, None, 0, n_threads))
+        buf = np.empty(int(boff[-1]), dtype=np.uint8)
+        native.check(lib.gdb_graphs_pack_batch(
+            C.byref(L), C.byref(src), boff.ctypes.data, buf.ctypes.data,
+            buf.nbytes, n_threads))
+        key = (nl.key, el.key, weighted)
+        cuts = boff.astype(np.int64).tolist()
+        uid = self.uuid
+        for k, g, a, b, nn in zip(todo, G, cuts[:-1], cuts[1:],
+                                  ncnt.tolist()):
+            pk = PackedGraph(buf[a:b], nn, key)
+            g.cookie[uid] = pk
+            out[k] = pk
+        return out
+
     def graphset(self, graphs):
         """Device graph set for a list of graphs (LRU-cached)."""
-        packed = [self.pack_graph(g) for g in graphs]
+        packed = self.pack_graphs(graphs)
         first = packed[0]
-        for g, p in zip(graphs, packed):
-            if p.key != first.key:
+        if len({p.key for p in packed}) > 1:
+            if True:
                 raise TypeError(
                     'All nodes/edges must be of the same type and graphs '
                     'must be all weighted or all unweighted. If the '
@@ -391,6 +497,16 @@ class B200Backend(Backend):
         gs.layouts = (nl, el, weighted)
         self._graphsets.insert(0, (key, gs))
         del self._graphsets[self._graphset_cache:]
+        return gs
+
+    def graphset_from_packed(self, packed, layouts):
+        """Device graph set from blobs packed elsewhere (e.g. by rank 0 of a
+        multi-GPU job: the graph set is packed once per node, not once per
+        rank).  ``layouts`` is the ``(node layout, edge layout, weighted)``
+        triple of ``_layouts``."""
+        nl, el, weighted = layouts
+        gs = GraphSet(self, self._layout_c(nl, el, weighted), packed)
+        gs.layouts = layouts
         return gs
 
     # -- programs ----------------------------------------------------------
@@ -475,8 +591,13 @@ class B200Backend(Backend):
     def __call__(self, graphs, node_kernel, edge_kernel, p, q, eps, ftol,
                  gtol, jobs, starts, gramian, gradient, nX, nY, nJ, traits,
                  timer, stream=None, keep_on_device=False, store_diag=False,
-                 normalize=False):
-        lib = native.load()
+                 normalize=False, **launch_options):
+        """The reference's 17-argument back-end call (reference
+        _backend_cuda.py:247-248).  Keyword extras (all optional, this
+        package's front end uses them): ``collect=Collect(...)`` fuses the
+        host-side conversion of the outputs with the copy-back, ``tile=``
+        pipelines the solve in row / column blocks, ``gramian_dev=`` /
+        ``gradient_dev=`` leave the results in caller-owned device memory."""
         timer.tic('transferring graphs to GPU')
         gs = self.graphset(list(graphs))
         timer.toc('transferring graphs to GPU')
@@ -489,14 +610,16 @@ class B200Backend(Backend):
         a = self.launch(gs, prog, node_kernel, edge_kernel, p, q, eps, ftol,
                         gtol, jobs, starts, gramian, gradient, nX, nY, nJ,
                         stream=stream, keep_on_device=keep_on_device,
-                        store_diag=store_diag, normalize=normalize)
+                        store_diag=store_diag, normalize=normalize,
+                        upload=self.resend_graphs, **launch_options)
         timer.toc('GPU kernel execution')
         return a
 
     def launch(self, gs, prog, node_kernel, edge_kernel, p, q, eps, ftol,
                gtol, jobs, starts, gramian, gradient, nX, nY, nJ, row0=0,
                col0=0, stream=None, keep_on_device=False, upload=False,
-               store_diag=False, normalize=False):
+               store_diag=False, normalize=False, tile=0, collect=None,
+               gramian_dev=None, gradient_dev=None, async_=False):
         """One ``gdb_solve`` call.  ``jobs`` is an explicit (i, j) array or a
         ``PairJobs`` grid descriptor (no per-pair host data)."""
         lib = native.load()
@@ -529,7 +652,30 @@ class B200Backend(Backend):
         a.nX, a.nY, a.nJ = int(nX), int(nY), int(nJ)
         a.stream = stream
         a.keep_on_device = int(keep_on_device)
+        a.gramian_dev = gramian_dev
+        a.gradient_dev = gradient_dev
+        a.tile = int(tile or 0)
+        a.async_ = int(bool(async_))
+        if collect is not None:
+            a.out_dtype = collect.code
+            a.out_gram = collect.gram.ctypes.data
+            a.out_grad = (collect.grad.ctypes.data
+                          if collect.grad is not None else None)
+            a.plane_mask = (collect.mask.ctypes.data
+                            if collect.mask is not None else None)
         native.check(lib.gdb_solve(self.context, prog, gs.handle, C.byref(a)))
+        if async_:      # keep the host inputs alive until synchronize()
+            self._inflight.append((starts, jobs, bufs))
+        t = self.totals
+        t['launches'] += a.n_launches
+        t['solves'] += 1
+        t['pairs'] += n_jobs
+        t['kernel_ms'] += a.kernel_ms
+        t['cg_iterations'] += a.cg_iterations
+        t['matvec_products'] += a.matvec_products
+        t['vector_elements'] += a.vector_elements
+        t['h2d_bytes'] += a.h2d_bytes
+        t['d2h_bytes'] += a.d2h_bytes
         self.last = dict(kernel_ms=a.kernel_ms, h2d_ms=a.h2d_ms,
                          d2h_ms=a.d2h_ms, cg_iterations=a.cg_iterations,
                          matvec_products=a.matvec_products,
@@ -540,15 +686,20 @@ class B200Backend(Backend):
                          smem_bytes=a.smem_bytes)
         return a
 
+    def synchronize(self):
+        """Wait for asynchronous solves (``async_=True``) and their copies."""
+        native.check(native.load().gdb_context_synchronize(self.context))
+        self._inflight.clear()
 
     def device_outputs(self, rows, cols, n_jac=0):
-        """The Gram matrix (and Jacobian) of the most recent solve as torch
-        CUDA tensors, copied device-to-device out of the engine's output
-        buffers (``keep_on_device=True`` solves leave them there): shapes
-        (rows, cols) and (rows, cols, n_jac), float32.  This is what lets a
-        caller such as the GPR training loop (reference
-        model/gaussian_process/gpr.py:259-296) keep the 4 (1 + nJ) bytes per
-        pair off the PCIe bus."""
+        """The Gram matrix (and Jacobian) of the most recent
+        ``keep_on_device`` solve as torch CUDA tensors, copied out of the
+        engine's own output buffers: shapes (rows, cols) and (rows, cols,
+        n_jac), float32.  The engine's stream is idle when ``gdb_solve``
+        returns; the copies run on torch's current stream, which is
+        synchronized before returning so that the next solve cannot overwrite
+        the buffers under them.  (``device_gram`` avoids the copy altogether
+        by handing torch-owned tensors to the solver.)"""
         import torch
         g, d = C.c_void_p(), C.c_void_p()
         native.check(native.load().gdb_last_outputs(self.context, C.byref(g),
@@ -564,10 +715,38 @@ class B200Backend(Backend):
         # Fortran order [r + c rows (+ k rows cols)] = C order (k, c, r)
         K = torch.as_tensor(_View(g.value, (cols, rows)), device=dev)
         K = K.clone().t()
-        if not n_jac:
-            return K, None
-        dK = torch.as_tensor(_View(d.value, (n_jac, cols, rows)), device=dev)
-        return K, dK.clone().permute(2, 1, 0)
+        dK = None
+        if n_jac:
+            dK = torch.as_tensor(_View(d.value, (n_jac, cols, rows)),
+                                 device=dev).clone().permute(2, 1, 0)
+        torch.cuda.current_stream(dev).synchronize()
+        return K, dK
+
+
+class Collect:
+    """Destination of a solve's host-side collection step: Fortran-ordered
+    result arrays of ``dtype`` (float64 or float32) and the mask of the
+    Jacobian planes to keep (reference _kernel.py:247-264 does this with
+    reshape / fancy indexing / astype after the launch)."""
+
+    def __init__(self, rows, cols, n_jac, mask, dtype):
+        dtype = np.dtype(dtype)
+        if dtype == np.float64:
+            self.code = native.OUT_F64
+        elif dtype == np.float32:
+            self.code = native.OUT_F32
+        else:
+            raise TypeError(f'collection into {dtype} is not supported')
+        self.gram = np.empty((rows, cols), dtype=dtype, order='F')
+        self.mask = self.grad = None
+        if n_jac:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            self.mask = mask
+            self.grad = np.empty((rows, cols, int(mask.sum())), dtype=dtype,
+                                 order='F')
+
+
+B200Backend.collect = Collect
 
 
 # --------------------------------------------------------------------------

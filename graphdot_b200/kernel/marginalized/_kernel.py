@@ -196,16 +196,45 @@ class MarginalizedGraphKernel:
             else:
                 starts[nx:] = np.arange(ny + 1)
             rows, cols = nx, ny
-        if _device:     # results stay in the engine's device buffers
+        want_grad = traits.eval_gradient is True
+        coll = None
+        if _device:
+            # results go straight into torch-owned device tensors: C order
+            # (k, c, r) is the solver's Fortran order [r + c rows + k rows cols]
+            import torch
+            dev = torch.device('cuda', backend.device)
+            Kt = torch.zeros((cols, rows), dtype=torch.float32, device=dev)
+            dKt = (torch.zeros((self.n_dims, cols, rows), dtype=torch.float32,
+                               device=dev) if want_grad else None)
             gramian = gradient = None
+            extra_out = dict(
+                gramian_dev=Kt.data_ptr(),
+                gradient_dev=dKt.data_ptr() if want_grad else None,
+                stream=torch.cuda.current_stream(dev).cuda_stream)
         else:
             gramian = backend.empty(rows * cols, np.float32)
             gradient = (backend.empty(self.n_dims * rows * cols, np.float32)
-                        if traits.eval_gradient is True else None)
+                        if want_grad else None)
+            extra_out = {}
+            make = getattr(backend, 'collect', None)
+            mask = np.asarray(self.active_theta_mask, dtype=bool)
+            dtype = np.dtype(self.element_dtype)
+            plain = dtype == np.float32 and (not want_grad or mask.all())
+            if (make is not None and not plain
+                    and dtype in (np.float32, np.float64)):
+                # conversion to `dtype` and the active-plane selection happen
+                # per finished column block on the engine's host threads
+                coll = make(rows, cols, self.n_dims if want_grad else 0,
+                            mask, dtype)
+                extra_out['collect'] = coll
+            if make is not None and len(pairs) >= 65536:
+                # pipeline: ~8 launches, copy-back overlaps the next launch
+                extra_out['tile'] = max(32, -(-(nx if traits.symmetric
+                                                else ny) // 8))
         timer.toc('creating output buffer')
 
         timer.tic('calling GPU kernel (overall)')
-        extra = {}
+        extra = dict(extra_out)
         if _fused_normalization:
             # self-similarities of every graph stay on the device ...
             n = len(graphs)
@@ -215,44 +244,42 @@ class MarginalizedGraphKernel:
                     self.q, self.eps, self.ftol, self.gtol,
                     backend.array(djobs),
                     np.arange(n + 1, dtype=np.uint32),
-                    backend.empty(n, np.float32),
-                    backend.empty(n * self.n_dims, np.float32)
-                    if traits.eval_gradient is True else None,
-                    n, 1, self.n_dims,
+                    None, None, n, 1, self.n_dims,
                     self.traits(diagonal=True, lmin=lmin,
                                 eval_gradient=eval_gradient),
-                    timer, store_diag=True, keep_on_device=True)
+                    timer, store_diag=True, keep_on_device=True,
+                    stream=extra.get('stream'))
             extra['normalize'] = True   # ... and scale the main solve
-        if _device:
-            extra['keep_on_device'] = True
         backend(graphs, self.node_kernel, self.edge_kernel, self.p, self.q,
                 self.eps, self.ftol, self.gtol, jobs, starts, gramian,
                 gradient, rows, cols, self.n_dims, traits, timer, **extra)
         timer.toc('calling GPU kernel (overall)')
 
         if _device:
-            K, dK = backend.device_outputs(
-                rows, cols, self.n_dims if traits.eval_gradient is True else 0)
-            if dK is None:
+            K = Kt.t()
+            if dKt is None:
                 return K
-            import torch
             mask = torch.as_tensor(np.asarray(self.active_theta_mask),
-                                   device=dK.device)
-            return K, dK[:, :, mask]
+                                   device=dev)
+            return K, dKt.permute(2, 1, 0)[:, :, mask]
 
         timer.tic('collecting result')
-        gramian = gramian.reshape(rows, cols, order='F')
-        if gradient is not None:
-            gradient = self._active_planes(
-                gradient.reshape((rows, cols, self.n_dims), order='F'),
-                self.active_theta_mask, self.element_dtype)
+        if coll is not None:
+            gramian, gradient = coll.gram, coll.grad
+        else:
+            gramian = gramian.reshape(rows, cols, order='F')
+            if gradient is not None:
+                gradient = self._active_planes(
+                    gradient.reshape((rows, cols, self.n_dims), order='F'),
+                    self.active_theta_mask, self.element_dtype)
+            gramian = gramian.astype(self.element_dtype, copy=False)
         timer.toc('collecting result')
         if timing:
             timer.report(unit='ms')
 
         if gradient is not None:
-            return gramian.astype(self.element_dtype), gradient
-        return gramian.astype(self.element_dtype)
+            return gramian, gradient
+        return gramian
 
     @staticmethod
     def _active_planes(jacobian, mask, dtype):

@@ -63,21 +63,39 @@ class StoreTileQueue:
             yield self.tiles[t]
 
 
+def col_tiles(ny, cols):
+    """Column blocks of an X-by-Y job rectangle."""
+    return [(j0, min(j0 + cols, ny)) for j0 in range(0, ny, cols)]
+
+
 class GramTileWorker:
-    """Evaluates tiles of the symmetric Gram matrix of ``graphs`` on one
-    device.  All graphs are resident on the device; outputs are tile-sized
-    page-locked host arrays that are reused from tile to tile."""
+    """Evaluates tiles of a Gram matrix on one device; all graphs are resident
+    on the device.
+
+    Symmetric mode (``nx=None``): row-block tiles ``rows [i0,i1) x columns
+    [i,n)`` of the Gram matrix of ``graphs`` with itself (``run_tile``).
+    Rectangular mode (``nx`` given): ``graphs = X + Y`` and tiles are column
+    blocks ``X x Y[j0:j1)`` of the off-diagonal block (``run_cols``), the
+    BASELINE configuration C5.
+
+    Tile outputs go either to tile-sized page-locked host arrays that are
+    reused from tile to tile, or -- ``run_cols(..., dev=, host=)`` -- into a
+    full-size matrix in caller-owned device memory and from there,
+    asynchronously, into a full-size host matrix (for instance a shared-memory
+    mapping that all per-GPU processes of a node fill: the assembled Gram)."""
 
     def __init__(self, kernel, graphs, backend=None, eval_gradient=False,
-                 max_rows=64, stream=None):
+                 max_rows=64, stream=None, nx=None, packed=None):
         self.kernel = kernel
         self.backend = backend or kernel.backend
-        self.graphs = list(graphs)
-        self.n = len(self.graphs)
+        self.graphs = list(graphs) if graphs is not None else None
         self.eval_gradient = eval_gradient
         self.stream = stream
         be = self.backend
-        self.gs = be.graphset(self.graphs)
+        self.gs = packed if packed is not None else be.graphset(self.graphs)
+        self.n = self.gs.n
+        self.nx = nx
+        self.ny = None if nx is None else self.n - nx
         T = MarginalizedGraphKernel.traits
         k = kernel
         self.prog = be.program(gs=self.gs, node_kernel=k.node_kernel,
@@ -88,21 +106,30 @@ class GramTileWorker:
                                     traits=T(diagonal=True,
                                              eval_gradient=eval_gradient))
         self.nJ = k.n_dims
-        self.starts = np.arange(self.n + 1, dtype=np.uint32)
+        if nx is None:
+            self.starts = np.arange(self.n + 1, dtype=np.uint32)
+            width = self.n
+        else:      # rows of X, columns of Y (reference _kernel.py:193-198)
+            self.starts = np.concatenate([np.arange(nx), np.arange(
+                self.ny + 1)]).astype(np.uint32)
+            width = nx
         self.max_rows = max_rows
-        self.out = be.empty(max_rows * self.n, np.float32)
-        self.dout = (be.empty(max_rows * self.n * self.nJ, np.float32)
-                     if eval_gradient else None)
+        self.out = self.dout = None
+        if max_rows:
+            self.out = be.empty(max_rows * width, np.float32)
+            self.dout = (be.empty(max_rows * width * self.nJ, np.float32)
+                         if eval_gradient else None)
         self.stats = dict(kernel_ms=0.0, cg_iterations=0, matvec_products=0,
                           vector_elements=0, h2d_bytes=0, d2h_bytes=0,
                           launches=0, pairs=0)
 
-    def _launch(self, prog, jobs, out, dout, nX, nY, row0=0, **kw):
+    def _launch(self, prog, jobs, out, dout, nX, nY, starts=None, **kw):
         k = self.kernel
         a = self.backend.launch(self.gs, prog, k.node_kernel, k.edge_kernel,
                                 k.p, k.q, k.eps, k.ftol, k.gtol, jobs,
-                                self.starts, out, dout, nX, nY, self.nJ,
-                                row0=row0, stream=self.stream, **kw)
+                                self.starts if starts is None else starts,
+                                out, dout, nX, nY, self.nJ,
+                                stream=self.stream, **kw)
         s = self.stats
         s['kernel_ms'] += a.kernel_ms
         s['cg_iterations'] += a.cg_iterations
@@ -114,28 +141,33 @@ class GramTileWorker:
         s['pairs'] += len(jobs)
         return a
 
-    def diag(self, upload=False, store=False):
+    def diag(self, upload=False, store=False, fetch=True):
         """Self-similarities (and their Jacobians) of all graphs; ``store``
-        keeps them on the device for ``run_tile(normalize=True)``."""
+        keeps them on the device for normalized tiles."""
         n = self.n
         jobs = np.empty(n, dtype=[('i', np.uint32), ('j', np.uint32)])
         jobs['i'] = jobs['j'] = np.arange(n)
-        d = self.backend.empty(n, np.float32)
-        dd = (self.backend.empty(n * self.nJ, np.float32)
-              if self.eval_gradient else None)
+        d = dd = None
+        if fetch:
+            d = self.backend.empty(n, np.float32)
+            dd = (self.backend.empty(n * self.nJ, np.float32)
+                  if self.eval_gradient else None)
         self._launch(self.prog_diag, jobs, d, dd, n, 1, upload=upload,
-                     store_diag=store)
+                     store_diag=store, keep_on_device=not fetch,
+                     starts=np.arange(n + 1, dtype=np.uint32))
+        if not fetch:
+            return None, None
         d = np.array(d, dtype=float)
         if dd is not None:
             dd = np.array(dd, dtype=float).reshape(n, self.nJ, order='F')
         return d, dd
 
     def run_tile(self, i0, i1, keep_on_device=False, normalize=False):
-        """Tile ``K[i - i0, j]`` for i in [i0,i1), j in [i,n) (zeros left of
-        the diagonal), raw or -- after ``diag(store=True)`` -- normalized on
-        the device; views into reused pinned buffers."""
+        """Symmetric mode: tile ``K[i - i0, j]`` for i in [i0,i1), j in [i,n)
+        (zeros left of the diagonal), raw or -- after ``diag(store=True)`` --
+        normalized on the device; views into reused pinned buffers."""
         rows = i1 - i0
-        assert rows <= self.max_rows
+        assert self.nx is None and rows <= self.max_rows
         out = self.out[:rows * self.n]
         dout = (self.dout[:rows * self.n * self.nJ]
                 if self.dout is not None else None)
@@ -148,6 +180,37 @@ class GramTileWorker:
         dK = (dout.reshape(rows, self.n, self.nJ, order='F')
               if dout is not None else None)
         return K, dK
+
+    def run_cols(self, j0, j1, normalize=False, dev=None, host=None,
+                 keep_on_device=False, async_=False):
+        """Rectangular mode: the column block ``K[:, j0:j1)`` of X x Y.
+
+        Without ``dev`` the tile lands in the worker's reused pinned buffers
+        and is returned as (nx, j1 - j0[, nJ]) views.  With ``dev=(K, dK)``
+        -- device addresses of full (nx, ny[, nJ]) Fortran-ordered float32
+        matrices -- the tile is written in place there; ``host=(K, dK)``
+        (addresses of page-locked matrices of the same shape) makes its
+        copy-back follow on the engine's copy stream, overlapping the next
+        tile when ``async_`` (finish with ``backend.synchronize()``)."""
+        nx, ny, w = self.nx, self.ny, j1 - j0
+        jobs = PairJobs.rect(0, nx, nx + j0, nx + j1)
+        if dev is None:
+            assert w <= self.max_rows
+            out = self.out[:w * nx]
+            dout = (self.dout[:w * nx * self.nJ]
+                    if self.dout is not None else None)
+            self._launch(self.prog, jobs, out, dout, nx, w, col0=j0,
+                         keep_on_device=keep_on_device, normalize=normalize)
+            if keep_on_device:
+                return None, None
+            return (out.reshape(nx, w, order='F'),
+                    dout.reshape(nx, w, self.nJ, order='F')
+                    if dout is not None else None)
+        hk, hd = host if host is not None else (None, None)
+        self._launch(self.prog, jobs, _Addr(hk), _Addr(hd), nx, ny,
+                     normalize=normalize, gramian_dev=dev[0],
+                     gradient_dev=dev[1], async_=async_)
+        return None, None
 
     @staticmethod
     def normalize_tile(K, dK, i0, d, dd):
@@ -164,6 +227,19 @@ class GramTileWorker:
         dKn = (sl[:, None, None] * dK * sr[None, :, None]
                - 0.5 * Kn[:, :, None] * (rl[:, None, :] + rr[None, :, :]))
         return Kn, dKn
+
+
+class _Addr:
+    """A raw host address where the back end expects an array
+    (``.ctypes.data``); None stays None."""
+
+    def __new__(cls, addr):
+        if addr is None:
+            return None
+        self = object.__new__(cls)
+        self.ctypes = self
+        self.data = int(addr)
+        return self
 
 
 def gram_tiled(kernel, graphs, devices=(0,), eval_gradient=False,

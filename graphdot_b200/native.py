@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, 'libgraphdot_b200.so')
 
 GDB_OK = 0
 JOBS_LIST, JOBS_RECT, JOBS_TRIU = 0, 1, 2
+OUT_NONE, OUT_F64, OUT_F32 = 0, 1, 2
 NODAL_CODES = {False: 0, True: 1, 'block': 2}
 
 
@@ -71,6 +72,14 @@ class GraphSrc(C.Structure):
                 ('pool_bytes', C.c_uint32)]
 
 
+class BatchSrc(C.Structure):
+    _fields_ = [('n_graphs', C.c_uint32), ('node_off', C.c_void_p),
+                ('edge_off', C.c_void_p), ('pool_off', C.c_void_p),
+                ('nodes', C.c_void_p), ('edge_i', C.c_void_p),
+                ('edge_j', C.c_void_p), ('edge_w', C.c_void_p),
+                ('edge_labels', C.c_void_p), ('pool', C.c_void_p)]
+
+
 class Layout(C.Structure):
     _fields_ = [('node_size', C.c_uint32), ('edge_label_size', C.c_uint32),
                 ('edge_label_align', C.c_uint32), ('weighted', C.c_int32),
@@ -95,6 +104,10 @@ class SolveArgs(C.Structure):
                 ('store_diag', C.c_int32), ('normalize', C.c_int32),
                 ('upload_graphs', C.c_int32),
                 ('stream', C.c_void_p), ('keep_on_device', C.c_int32),
+                ('gramian_dev', C.c_void_p), ('gradient_dev', C.c_void_p),
+                ('tile', C.c_uint32), ('out_dtype', C.c_int32),
+                ('out_gram', C.c_void_p), ('out_grad', C.c_void_p),
+                ('plane_mask', C.c_void_p), ('async_', C.c_int32),
                 ('kernel_ms', C.c_float), ('h2d_ms', C.c_float),
                 ('d2h_ms', C.c_float), ('cg_iterations', C.c_uint64),
                 ('matvec_products', C.c_uint64),
@@ -116,6 +129,8 @@ SYMBOLS = [
     ('gdb_context_synchronize', C.c_int, [_P]),
     ('gdb_host_alloc', C.c_int, [C.c_size_t, C.POINTER(_P)]),
     ('gdb_host_free', C.c_int, [_P]),
+    ('gdb_host_register', C.c_int, [_P, C.c_size_t]),
+    ('gdb_host_unregister', C.c_int, [_P]),
     ('gdb_program_create', C.c_int, [_P, C.POINTER(ProgramDesc),
                                      C.POINTER(_P)]),
     ('gdb_program_info_get', C.c_int, [_P, C.POINTER(ProgramInfo)]),
@@ -130,6 +145,8 @@ SYMBOLS = [
                                         C.POINTER(C.c_uint64)]),
     ('gdb_graph_pack', C.c_int, [C.POINTER(Layout), C.POINTER(GraphSrc), _P,
                                  C.c_uint64]),
+    ('gdb_graphs_pack_batch', C.c_int, [C.POINTER(Layout), C.POINTER(BatchSrc),
+                                        _P, _P, C.c_uint64, C.c_int32]),
     ('gdb_graphset_create', C.c_int, [_P, C.POINTER(Layout), C.c_uint32,
                                       C.POINTER(_P), C.POINTER(C.c_uint64),
                                       C.POINTER(_P)]),
@@ -167,28 +184,69 @@ def check(status):
         raise NativeError(status, load().gdb_last_error().decode())
 
 
+# Page-locking is slow (cudaHostAlloc of the 96 MB C3 output takes tens of
+# milliseconds), and every front-end call asks for fresh output buffers: freed
+# blocks are therefore kept in a small size-bucketed pool and handed out again.
+_POOL = {}              # capacity -> [ptr, ...]
+_POOL_BYTES = [0]
+_POOL_LIMIT = 8 << 30   # bytes kept for reuse
+
+
+def _bucket(nbytes):
+    b = 4096
+    while b < nbytes:
+        b *= 2
+    # above 1 MiB: 1/8-octave steps, so that large buffers waste <= 12.5 %
+    if b > (1 << 20):
+        step = b // 16
+        b = -(-nbytes // step) * step
+    return b
+
+
 def pinned_empty(count, dtype):
-    """numpy array over page-locked host memory (freed with the array)."""
+    """numpy array over page-locked host memory (pooled; released with the
+    array)."""
     lib = load()
     dtype = np.dtype(dtype)
     nbytes = max(1, int(count) * dtype.itemsize)
-    ptr = C.c_void_p()
-    check(lib.gdb_host_alloc(nbytes, C.byref(ptr)))
-    raw = (C.c_ubyte * nbytes).from_address(ptr.value)
+    cap = _bucket(nbytes)
+    free = _POOL.get(cap)
+    if free:
+        ptr = free.pop()
+        _POOL_BYTES[0] -= cap
+    else:
+        p = C.c_void_p()
+        check(lib.gdb_host_alloc(cap, C.byref(p)))
+        ptr = p.value
+    raw = (C.c_ubyte * nbytes).from_address(ptr)
     # the ctypes buffer is the ultimate .base of every view numpy derives from
     # this array, so tying the holder to it keeps the allocation alive exactly
     # as long as any view exists
-    raw._gdb_holder = _PinnedHolder(ptr.value)
+    raw._gdb_holder = _PinnedHolder(ptr, cap)
     return np.frombuffer(raw, dtype=dtype, count=int(count))
 
 
+def pinned_pool_clear():
+    for cap, ptrs in _POOL.items():
+        for ptr in ptrs:
+            if _lib is not None:
+                _lib.gdb_host_free(C.c_void_p(ptr))
+    _POOL.clear()
+    _POOL_BYTES[0] = 0
+
+
 class _PinnedHolder:
-    def __init__(self, ptr):
-        self.ptr = ptr
+    def __init__(self, ptr, cap):
+        self.ptr, self.cap = ptr, cap
 
     def __del__(self):
         try:
-            if self.ptr and _lib is not None:
+            if not self.ptr or _lib is None:
+                return
+            if _POOL_BYTES[0] + self.cap <= _POOL_LIMIT:
+                _POOL.setdefault(self.cap, []).append(self.ptr)
+                _POOL_BYTES[0] += self.cap
+            else:
                 _lib.gdb_host_free(C.c_void_p(self.ptr))
         except Exception:
             pass

@@ -66,6 +66,12 @@ int gdb_context_synchronize(gdb_context_t ctx);
  * context; falls back to nothing: fails if no CUDA device is present. */
 int gdb_host_alloc(size_t bytes, void **out);
 int gdb_host_free(void *ptr);
+/* Page-lock / unlock memory the caller owns (e.g. a POSIX shared-memory
+ * mapping that several per-GPU processes fill with Gram tiles: the
+ * "gathering Gram tiles back to host" of a multi-GPU run needs no
+ * collective).  Portable across contexts. */
+int gdb_host_register(void *ptr, size_t bytes);
+int gdb_host_unregister(void *ptr);
 
 /* ---- program: NVRTC-compiled solver ------------------------------------
  * Replaces CUDABackend.gencode_kernel / gencode_probability / template
@@ -182,6 +188,30 @@ int gdb_graph_packed_size(const gdb_layout *layout, const gdb_graph_src *g,
 int gdb_graph_pack(const gdb_layout *layout, const gdb_graph_src *g,
                    void *blob, uint64_t capacity);
 
+/* Pack k graphs at once on `n_threads` host threads (0 = hardware
+ * concurrency) from column-concatenated inputs: graph g owns nodes
+ * [node_off[g], node_off[g+1]) of `nodes`, undirected edges
+ * [edge_off[g], edge_off[g+1]) of edge_i/edge_j/edge_w/edge_labels (end
+ * points local to the graph) and bytes [pool_off[g], pool_off[g+1]) of
+ * `pool` (pool_off may be NULL: no variable-length features).  Two calls:
+ * with blobs == NULL only blob_off[0..k] (prefix sums of the blob sizes) is
+ * written; with blobs != NULL of capacity >= blob_off[k] the blobs are
+ * written back to back.  Replaces the per-graph Python loop over OctileGraph
+ * (reference _backend_cuda.py:252-259, _octilegraph.py:37-177), which is
+ * milliseconds per graph. */
+typedef struct gdb_batch_src {
+    uint32_t n_graphs;
+    const uint64_t *node_off, *edge_off, *pool_off;
+    const void *nodes;
+    const uint32_t *edge_i, *edge_j;
+    const float *edge_w;
+    const void *edge_labels;
+    const void *pool;
+} gdb_batch_src;
+int gdb_graphs_pack_batch(const gdb_layout *layout, const gdb_batch_src *src,
+                          uint64_t *blob_off, void *blobs, uint64_t capacity,
+                          int32_t n_threads);
+
 /* Assemble packed blobs into one device-resident graph set. */
 int gdb_graphset_create(gdb_context_t ctx, const gdb_layout *layout,
                         uint32_t n_graphs, const void *const *blobs,
@@ -200,6 +230,9 @@ int gdb_graphset_destroy(gdb_graphset_t gs);
 #define GDB_JOBS_LIST 0 /* explicit (i, j) pairs                          */
 #define GDB_JOBS_RECT 1 /* all (i, j) with i in [i0,i1), j in [j0,j1)     */
 #define GDB_JOBS_TRIU 2 /* all (i, j) with i in [i0,i1), j in [i,j1)      */
+#define GDB_OUT_NONE 0
+#define GDB_OUT_F64 1
+#define GDB_OUT_F32 2
 
 typedef struct gdb_solve_args {
     int32_t job_mode;
@@ -231,6 +264,31 @@ typedef struct gdb_solve_args {
     void *stream;             /* CUstream to run on; NULL = context stream */
     int32_t keep_on_device;   /* 1: skip the device->host copy; outputs
                                  stay in the context's device buffers      */
+    /* caller-owned DEVICE outputs (same Fortran layout, nX*nY [*nJ] floats):
+     * the kernels write there instead of the context's buffers and nothing
+     * is zero-filled first.  With host buffers given as well, finished
+     * column blocks are copied from there to the host.                     */
+    float *gramian_dev, *gradient_dev;
+    /* Pipelined execution: split a TRIU job grid of a symmetric program into
+     * launches of `tile` rows, a RECT grid into launches of `tile` columns
+     * (0 = one launch).  A finished launch completes a block of output
+     * COLUMNS, whose device->host copy (on a second stream) and host-side
+     * collection overlap the next launch.                                  */
+    uint32_t tile;
+    /* Host-side collection, fused with the copy-back (replaces the
+     * reshape / active-theta masking / astype of reference
+     * _kernel.py:247-264, which is a serial numpy pass over 4(1+nJ) B per
+     * pair): out_dtype GDB_OUT_F64 / GDB_OUT_F32 converts every finished
+     * column block on the context's host threads into out_gram (nX*nY) and
+     * out_grad (nX*nY*n_active, only planes with plane_mask[k] != 0; NULL =
+     * all).  `gramian` / `gradient` are then the page-locked float staging. */
+    int32_t out_dtype;
+    void *out_gram, *out_grad;
+    const uint8_t *plane_mask;
+    /* 1: return without waiting for the device; the copies into `gramian` /
+     * `gradient` are complete after gdb_context_synchronize().  Not combined
+     * with out_dtype; diagnostics below are not filled.                   */
+    int32_t async;
     /* diagnostics (out) */
     float kernel_ms;          /* device time of the solver kernel          */
     float h2d_ms, d2h_ms;

@@ -150,7 +150,24 @@ def solve_pair(g1, g2, knode, kedge, q, p=None, lmin=0,
         sparse = len(g1.nodes) * len(g2.nodes) > 3000
     s = pair_system(g1, g2, knode, kedge, q, jac=eval_gradient, sparse=sparse)
     n1, n2, D, V, W = s['n1'], s['n2'], s['D'], s['V'], s['W']
-    if sparse:
+    if sparse and n1 * n2 > 12000:
+        # large pairs (config C4: small-world graphs of 200-500 nodes, N up to
+        # 250 000): a sparse LU fills in catastrophically, so the system is
+        # solved like the reference's own oracle does (scipy CG, reference
+        # test_kernel.py:58-63) -- in float64, Jacobi-preconditioned, and
+        # iterated to a relative residual of 1e-14
+        import scipy.sparse as sp
+        import scipy.sparse.linalg as spla
+        A = (sp.diags(D / V) - W).tocsr()
+        Minv = spla.LinearOperator(A.shape, matvec=lambda r: r * (V / D))
+
+        def solve(rhs):
+            sol, info = spla.cg(A, rhs, rtol=1e-14, atol=0.0, M=Minv,
+                                maxiter=20000)
+            if info != 0:
+                raise RuntimeError(f'oracle CG did not converge ({info})')
+            return sol
+    elif sparse:
         import scipy.sparse as sp
         import scipy.sparse.linalg as spla
         lu = spla.splu((sp.diags(D / V) - W).tocsc())

@@ -1,0 +1,279 @@
+"""Round-2 paths of the CUDA engine, through the C ABI: pipelined tiled solves
+with fused host-side collection (the reference does reshape / active-theta
+masking / astype in numpy after the launch, reference
+kernel/marginalized/_kernel.py:247-264), caller-owned device outputs,
+asynchronous tile copy-back into one host matrix, output-extent validation,
+and the BASELINE configurations at their stated sizes (C3 2000-graph output
+sampled against the oracle, C4 pairs of 200+ nodes with gradients, a C5
+X-by-Y block)."""
+import numpy as np
+import pytest
+
+from graphdot_b200 import native
+from graphdot_b200.kernel.fix import Normalization
+from graphdot_b200.kernel.marginalized import MarginalizedGraphKernel
+from graphdot_b200.kernel.marginalized._backend_b200 import (B200Backend,
+                                                             PairJobs)
+from graphdot_b200.kernel.marginalized._tiles import (GramTileWorker,
+                                                      col_tiles)
+from graphdot_b200.microkernel import (KroneckerDelta, SquareExponential,
+                                       TensorProduct)
+from graphdot_b200.synthetic import make_config_graphs, make_config_kernel
+from oracle import mlgk_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+GRAM_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+
+
+@pytest.fixture(scope='module')
+def backend():
+    return B200Backend()
+
+
+def rel_err(got, want):
+    want = np.asarray(want, float)
+    return np.abs(np.asarray(got, float) - want).max() / np.abs(want).max()
+
+
+def plain_solve(kernel, graphs, nx, symmetric, eval_gradient):
+    """One un-tiled launch into float32 buffers, no collection: what a
+    reference-style front end gets from ``Backend.__call__``."""
+    be = kernel.backend
+    n = len(graphs)
+    ny = nx if symmetric else n - nx
+    T = MarginalizedGraphKernel.traits
+    jobs = (PairJobs.triu(0, nx) if symmetric
+            else PairJobs.rect(0, nx, nx, n))
+    starts = (np.arange(n + 1) if symmetric else np.concatenate(
+        [np.arange(nx), np.arange(ny + 1)])).astype(np.uint32)
+    K = be.empty(nx * ny, np.float32)
+    dK = be.empty(nx * ny * kernel.n_dims, np.float32) if eval_gradient \
+        else None
+    from graphdot_b200.util import Timer
+    be(graphs, kernel.node_kernel, kernel.edge_kernel, kernel.p, kernel.q,
+       kernel.eps, kernel.ftol, kernel.gtol, jobs, starts, K, dK, nx, ny,
+       kernel.n_dims, T(symmetric=symmetric, eval_gradient=eval_gradient),
+       Timer())
+    assert be.last['n_launches'] == 1
+    K = K.reshape(nx, ny, order='F')
+    if dK is not None:
+        dK = dK.reshape(nx, ny, kernel.n_dims, order='F')
+    return K, dK
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_pipelined_symmetric_solve_is_bit_identical_to_one_launch(backend,
+                                                                  dtype):
+    """>= 65536 pairs: the front end splits the triangle into row-block
+    launches whose column blocks are copied back and converted while the next
+    launch runs.  Same bits as one launch + numpy post-processing."""
+    G = make_config_graphs('C2', 400)
+    kernel = make_config_kernel('C3', backend=backend, dtype=dtype)
+    K, dK = kernel(G, eval_gradient=True)
+    assert backend.last['n_launches'] > 1
+    assert K.dtype == dtype and dK.dtype == dtype
+    assert K.shape == (400, 400) and dK.shape == (400, 400, 5)
+    K1, dK1 = plain_solve(kernel, G, 400, True, True)
+    assert np.array_equal(K, K1.astype(dtype))
+    assert np.array_equal(dK, dK1.astype(dtype))
+    assert np.array_equal(K, K.T)
+
+
+def test_pipelined_rectangular_solve_with_fixed_hyperparameters(backend):
+    """X x Y with column-block launches; fixed hyper-parameters are dropped
+    during collection (reference _kernel.py:249-251)."""
+    G = make_config_graphs('C5', 620)
+    X, Y = G[:300], G[300:]
+    kn = TensorProduct(element=KroneckerDelta(0.5, h_bounds='fixed'),
+                       x=SquareExponential(1.0))
+    ke = TensorProduct(length=SquareExponential(0.1))
+    kernel = MarginalizedGraphKernel(kn, ke, q=0.05, backend=backend)
+    assert list(kernel.active_theta_mask) == [False, True, False, True, True]
+    K, dK = kernel(X, Y, eval_gradient=True)
+    assert backend.last['n_launches'] > 1
+    assert K.shape == (300, 320) and dK.shape == (300, 320, 3)
+    K1, dK1 = plain_solve(kernel, X + Y, 300, False, True)
+    assert np.array_equal(K, K1.astype(float))
+    assert np.array_equal(dK, dK1[:, :, [1, 3, 4]].astype(float))
+    # float32 with a mask goes through the float32 collection
+    k32 = MarginalizedGraphKernel(kn, ke, q=0.05, backend=backend,
+                                  dtype=np.float32)
+    K32, dK32 = k32(X, Y, eval_gradient=True)
+    assert K32.dtype == np.float32 and np.array_equal(K32, K1)
+    assert np.array_equal(dK32, dK1[:, :, [1, 3, 4]])
+
+
+def test_normalized_public_call_pipelined(backend):
+    """Normalization(kernel)(G, eval_gradient=True) on enough graphs to
+    pipeline: unit diagonal, symmetric, equal to the host formulas."""
+    G = make_config_graphs('C2', 380)
+    kernel = make_config_kernel('C3', backend=backend)
+    K, dK = Normalization(kernel)(G, eval_gradient=True)
+    assert backend.last['n_launches'] > 1
+    assert np.allclose(np.diag(K), 1.0, atol=2e-7)
+    assert np.array_equal(K, K.T)
+    Kh, dKh = Normalization(kernel)._host_normalized(G, None, True)
+    assert np.allclose(K, Kh, rtol=2e-6, atol=0)
+    assert rel_err(dK, dKh) < 1e-5
+
+
+def test_device_gram_matches_host_result(backend):
+    """device_gram writes straight into torch-owned tensors (no clone of the
+    engine's buffers, nothing to race with the next solve)."""
+    import torch
+    G = make_config_graphs('C2', 64)
+    kernel = make_config_kernel('C3', backend=backend)
+    K, dK = kernel(G, eval_gradient=True)
+    for _ in range(2):        # back-to-back solves must not disturb each other
+        Kd, dKd = kernel.device_gram(G, eval_gradient=True)
+        Kn, dKn = Normalization(kernel).device_gram(G, eval_gradient=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(Kd.cpu().numpy().astype(float), K)
+    assert np.array_equal(dKd.cpu().numpy().astype(float), dK)
+    Kh, dKh = Normalization(kernel)(G, eval_gradient=True)
+    assert np.array_equal(Kn.cpu().numpy().astype(float), Kh)
+    assert np.array_equal(dKn.cpu().numpy().astype(float), dKh)
+
+
+def test_tile_worker_fills_one_host_matrix_asynchronously(backend):
+    """C5-style job: column tiles of X x Y written into a full-size device
+    matrix and copied, asynchronously, into ONE page-locked host matrix --
+    equal to the public X x Y call."""
+    import torch
+    G = make_config_graphs('C5', 200)
+    nx, ny = 120, 80
+    kernel = make_config_kernel('C3', backend=backend)
+    w = GramTileWorker(kernel, G, backend, eval_gradient=True, max_rows=0,
+                       nx=nx)
+    nJ = kernel.n_dims
+    Kd = torch.zeros((ny, nx), dtype=torch.float32, device='cuda')
+    dKd = torch.zeros((nJ, ny, nx), dtype=torch.float32, device='cuda')
+    Kh = native.pinned_empty(nx * ny, np.float32)
+    dKh = native.pinned_empty(nx * ny * nJ, np.float32)
+    Kh[:] = -1
+    dKh[:] = -1
+    torch.cuda.synchronize()
+    w.diag(store=True, fetch=False)
+    for j0, j1 in col_tiles(ny, 24):
+        w.run_cols(j0, j1, normalize=True, dev=(Kd.data_ptr(),
+                                                dKd.data_ptr()),
+                   host=(Kh.ctypes.data, dKh.ctypes.data), async_=True)
+    backend.synchronize()
+    want_K, want_dK = Normalization(kernel)(G[:nx], G[nx:],
+                                            eval_gradient=True)
+    got_K = Kh.reshape(nx, ny, order='F')
+    got_dK = dKh.reshape(nx, ny, nJ, order='F')
+    assert np.array_equal(got_K.astype(float), want_K)
+    assert np.array_equal(got_dK.astype(float), want_dK)
+    assert np.array_equal(Kd.t().cpu().numpy(), got_K)
+    # tile-sized pinned outputs (no device matrix) give the same columns
+    w2 = GramTileWorker(kernel, G, backend, eval_gradient=True, max_rows=24,
+                        nx=nx)
+    Kt, dKt = w2.run_cols(24, 48, normalize=True)
+    assert np.array_equal(Kt, got_K[:, 24:48])
+    assert np.array_equal(dKt, got_dK[:, 24:48])
+
+
+def test_outputs_outside_the_buffers_are_rejected(backend):
+    """A starts / nX that would make the kernel write out of bounds is an
+    error of the ABI call, not a device fault."""
+    G = make_config_graphs('C2', 6)
+    kernel = make_config_kernel('C2', backend=backend)
+    gs = backend.graphset(G)
+    T = MarginalizedGraphKernel.traits
+    prog = backend.program(gs, kernel.node_kernel, kernel.edge_kernel,
+                           kernel.p, T(symmetric=True))
+    out = backend.empty(36, np.float32)
+    k = kernel
+    args = (gs, prog, k.node_kernel, k.edge_kernel, k.p, k.q, k.eps, k.ftol,
+            k.gtol, PairJobs.triu(0, 6))
+    backend.launch(*args, np.arange(7, dtype=np.uint32), out, None, 6, 6, 5)
+    with pytest.raises(native.NativeError, match='outside'):
+        backend.launch(*args, np.arange(7, dtype=np.uint32) + 3, out, None,
+                       6, 6, 5)
+    with pytest.raises(native.NativeError, match='outside'):
+        backend.launch(*args, np.arange(7, dtype=np.uint32), out, None, 5, 6,
+                       5)
+    with pytest.raises(native.NativeError, match='outside'):
+        backend.launch(*args, np.arange(7, dtype=np.uint32), out, None, 6, 6,
+                       5, row0=2)
+
+
+def test_c3_full_size_output_sampled_vs_oracle(backend):
+    """The 2000-graph normalized Gram + Jacobian that bench.py times, sampled
+    against the float64 oracle."""
+    G = make_config_graphs('C2', 2000)
+    kernel = make_config_kernel('C3', backend=backend)
+    K, dK = Normalization(kernel)(G, eval_gradient=True)
+    assert K.shape == (2000, 2000) and dK.shape == (2000, 2000, 5)
+    assert np.array_equal(K, K.T)
+    assert np.allclose(np.diag(K), 1.0, atol=2e-7)
+    rng = np.random.default_rng(7)
+    kw = dict(knode=kernel.node_kernel, kedge=kernel.edge_kernel, q=kernel.q,
+              eval_gradient=True)
+    diff = np.zeros(5)
+    scale = np.zeros(5)
+    for i, j in zip(rng.integers(0, 2000, 24), rng.integers(0, 2000, 24)):
+        R, J = oracle.gram([G[i], G[j]], **kw)
+        kn = R[0, 1] / np.sqrt(R[0, 0] * R[1, 1])
+        dn = (J[0, 1] / np.sqrt(R[0, 0] * R[1, 1])
+              - 0.5 * kn * (J[0, 0] / R[0, 0] + J[1, 1] / R[1, 1]))
+        assert K[i, j] == pytest.approx(kn, rel=GRAM_RTOL)
+        diff = np.maximum(diff, np.abs(dK[i, j] - dn))
+        scale = np.maximum(scale, np.abs(dn))
+    assert (diff / scale).max() < GRAD_RTOL
+
+
+def test_c5_offdiagonal_block_vs_oracle(backend):
+    """A block of BASELINE config C5 (seed 5005): X x Y with X and Y disjoint,
+    Gram + Jacobian, raw and normalized."""
+    G = make_config_graphs('C5', 56)
+    X, Y = G[:30], G[30:]
+    kernel = make_config_kernel('C3', backend=backend)
+    K, dK = kernel(X, Y, eval_gradient=True)
+    kw = dict(knode=kernel.node_kernel, kedge=kernel.edge_kernel, q=kernel.q)
+    Ko, dKo = oracle.gram(X, Y, eval_gradient=True, **kw)
+    assert K.shape == (30, 26)
+    assert rel_err(K, Ko) < GRAM_RTOL
+    for m in range(5):
+        assert rel_err(dK[:, :, m], dKo[:, :, m]) < GRAD_RTOL
+    Kn = Normalization(kernel)(X, Y)
+    dx = oracle.diag(X, **kw)
+    dy = oracle.diag(Y, **kw)
+    assert rel_err(Kn, Ko / np.sqrt(np.outer(dx, dy))) < GRAM_RTOL
+
+
+@pytest.mark.parametrize('pair', [(4, 2), (4, 4), (2, 0)])
+def test_c4_full_size_pair_with_gradient_vs_oracle(backend, pair):
+    """BASELINE config C4 at its stated size: both graphs have 200-500 nodes
+    (203 x 233, 203 x 203 and 233 x 432: N = 41 000 ... 101 000), Convolution
+    node kernel over vector features, Gram AND Jacobian against the float64
+    oracle (Jacobi-CG to 1e-14 at this size)."""
+    G = make_config_graphs('C4', 5)
+    a, b = pair
+    assert min(len(G[a].nodes), len(G[b].nodes)) >= 200
+    kernel = make_config_kernel('C4', backend=backend)
+    K, dK = kernel([G[a]], [G[b]], eval_gradient=True)
+    assert not backend.last['small_kernel']
+    _, ko, go = oracle.solve_pair(G[a], G[b], kernel.node_kernel,
+                                  kernel.edge_kernel, kernel.q, kernel.p,
+                                  eval_gradient=True)
+    assert K[0, 0] == pytest.approx(ko, rel=GRAM_RTOL)
+    assert np.allclose(dK[0, 0], go, rtol=GRAD_RTOL,
+                       atol=GRAD_RTOL * np.abs(go).max())
+
+
+def test_c4_symmetric_gram_small_set(backend):
+    """Symmetric Gram of two full-size C4 graphs through the public call;
+    normalized diagonal is 1."""
+    G = make_config_graphs('C4', 5)
+    G = [G[4], G[2]]
+    kernel = make_config_kernel('C4', backend=backend)
+    K = kernel(G)
+    Ko = oracle.gram(G, knode=kernel.node_kernel, kedge=kernel.edge_kernel,
+                     q=kernel.q)
+    assert rel_err(K, Ko) < GRAM_RTOL
+    assert np.array_equal(K, K.T)
+    Kn = Normalization(kernel)(G)
+    assert np.allclose(np.diag(Kn), 1.0, atol=2e-7)
