@@ -216,14 +216,16 @@ def check_parity(pool, G, pairs, K, dK, diag_cache=None):
         dn = dab / np.sqrt(kaa * kbb) - 0.5 * kn * (daa / kaa + dbb / kbb)
         err_k = max(err_k, abs(K[r, c] - kn) / abs(kn))
         diff_g = np.maximum(diff_g, np.abs(dK[r, c, :] - dn))
-        scale_g = np.maximum(scale_g, np.abs(dn))
+        # scale: the raw-gradient term of the quotient rule (the plane of the
+        # starting probability cancels to exactly 0 after normalization)
+        scale_g = np.maximum(scale_g, np.abs(dab) / np.sqrt(kaa * kbb))
     err_g = float(np.max(diff_g / scale_g))
     return {'max_rel_gram': float(err_k), 'max_rel_grad': err_g,
             'n': len(pairs), 'tolerance': {'gram': 1e-5, 'grad': 1e-4},
             'ok': bool(err_k < 1e-5 and err_g < 1e-4),
             'against': 'oracle/mlgk_oracle.py (float64 dense solve), '
                        'gradient error per plane relative to the largest '
-                       'sampled entry of that plane'}
+                       'sampled |dK_ij| / sqrt(K_ii K_jj) of that plane'}
 
 
 # ---------------------------------------------------------------------------

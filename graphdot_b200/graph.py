@@ -113,6 +113,7 @@ class DataFrame:
     # -- mapping protocol --------------------------------------------------
     def __setitem__(self, key, value):
         self._data[key] = value if isinstance(value, Series) else Series(value)
+        self._sig = None    # cached type signature (see Graph.has_unified_types)
 
     def __getitem__(self, key):
         if isinstance(key, str):
@@ -191,6 +192,7 @@ class DataFrame:
         if inplace:
             for k in keys:
                 self._data.pop(k, None)
+            self._sig = None
             return None
         return self[[k for k in self.columns if k not in keys]]
 
@@ -281,6 +283,29 @@ class Graph:
         """True, or ``(component, first, offender)`` for the first mismatch."""
         graphs = list(graphs)
         first = graphs[0]
+
+        def signature(frame):
+            # (column, element type) pairs: equal signatures <=> equal
+            # rowtype().  Cached on the frame (reset by every column
+            # assignment / drop): 2000 graphs are checked in well under a
+            # millisecond instead of building 4000 numpy struct dtypes.
+            sig = frame.__dict__.get('_sig')
+            if sig is None:
+                sig = frame.__dict__['_sig'] = tuple(
+                    (k, c.concrete_type) for k, c in frame._data.items())
+            return sig
+
+        try:
+            nt, et = signature(first.nodes), signature(first.edges)
+            for g in graphs:
+                if signature(g.nodes) != nt:
+                    break
+                if signature(g.edges) != et:
+                    break
+            else:
+                return True
+        except AttributeError:      # foreign frame types: the generic way
+            pass
         nt, et = first.nodes.rowtype(), first.edges.rowtype()
         for g in graphs:
             if g.nodes.rowtype() != nt:

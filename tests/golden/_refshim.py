@@ -2,7 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY.  Used by ``make_golden.py`` (and nothing else) to
 import ``/root/reference/graphdot`` without pycuda/ase/mendeleev and under
-numpy >= 2, so that golden vectors come from the reference's own code:
+numpy >= 2, so that golden vectors come from the reference's own code, and by
+``tests/test_gpu_reference_frontend.py`` to import the copy staged under
+``baseline/_ref`` (``stage_reference.py``) on the GPU box:
 
 * numpy 2 removed ``np.float/np.int/np.object/np.issctype/np.issubsctype``
   (used at reference graphdot/kernel/marginalized/_kernel.py:62,
@@ -30,7 +32,8 @@ def _is_scalar_type(t):
     return dt.kind != 'O' and dt.names is None
 
 
-def install():
+def install(root=None):
+    root = root or REFERENCE_ROOT
     # -- numpy >= 2 aliases ------------------------------------------------
     for name, val in (('float', float), ('int', int), ('object', object),
                       ('bool', bool)):
@@ -95,6 +98,6 @@ def install():
     pc.gpuarray = stub('pycuda.gpuarray',
                        empty=lambda n, dtype: np.empty(n, dtype))
 
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import scipy.sparse.linalg  # noqa: F401  (test_kernel.py uses sp.linalg.cg)

@@ -1,0 +1,224 @@
+"""Host-side logic added in round 2 (no GPU): batch packing, duplicate-edge
+resolution, networkx node order, cached type signatures, range-check
+warnings, a second pin of the microkernels, the C-ABI surface."""
+import ctypes as C
+import re
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from graphdot_b200 import Graph, native
+from graphdot_b200.graph import DataFrame
+from graphdot_b200.kernel.marginalized import MarginalizedGraphKernel
+from graphdot_b200.kernel.marginalized._backend_b200 import B200Backend
+from graphdot_b200.microkernel import (Constant, DotProduct, KroneckerDelta,
+                                       RationalQuadratic, SquareExponential,
+                                       TensorProduct)
+from graphdot_b200.synthetic import make_config_graphs
+
+
+def test_header_and_bindings_declare_the_same_symbols():
+    text = open(os.path.join(ROOT, 'include', 'graphdot_b200.h')).read()
+    declared = set(re.findall(r'\b(gdb_[a-z0-9_]+)\s*\(', text))
+    bound = {name for name, _, _ in native.SYMBOLS}
+    assert declared == bound
+    lib = native.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    for new in ('gdb_graphs_pack_batch', 'gdb_host_register',
+                'gdb_host_unregister'):
+        assert new in declared
+
+
+def test_solve_args_binding_matches_the_header_field_order():
+    text = open(os.path.join(ROOT, 'include', 'graphdot_b200.h')).read()
+    head = 'typedef struct gdb_solve_args {'
+    body = text[text.index(head) + len(head):text.index('} gdb_solve_args;')]
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    names = []
+    for decl in body.split(';'):
+        decl = decl.strip()
+        if not decl or decl.startswith('typedef'):
+            continue
+        for part in decl.split(','):
+            names.append(re.sub(r'[\s\*]', ' ', part).split()[-1])
+    bound = [n.rstrip('_') for n, _ in native.SolveArgs._fields_]
+    assert names == bound
+
+
+def test_batch_packing_equals_per_graph_packing():
+    G = make_config_graphs('C5', 300)
+    # one graph with a permuted node table: rows must be sorted by '!i'
+    g = G[7]
+    perm = np.random.default_rng(0).permutation(len(g.nodes))
+    for key in list(g.nodes.columns):
+        g.nodes[key] = np.asarray(g.nodes[key])[perm]
+    a, b = B200Backend(), B200Backend()
+    batch = a.pack_graphs(G)
+    single = [b.pack_graph(x) for x in G]
+    assert all(x.key == y.key and x.n_node == y.n_node
+               and np.array_equal(x.blob, y.blob)
+               for x, y in zip(batch, single))
+    assert all(a.uuid in x.cookie for x in G)
+    assert a.pack_graphs(G)[5] is batch[5]          # cached
+    # unweighted, unlabeled graphs (phantom edge label) batch as well
+    U = make_config_graphs('C1', 40)
+    assert all(np.array_equal(x.blob, y.blob) for x, y in
+               zip(B200Backend().pack_graphs(U),
+                   [b.pack_graph(x) for x in U]))
+
+
+def test_batch_packing_rejects_mixed_types():
+    G = make_config_graphs('C5', 40)
+    G[11].nodes['x'] = np.asarray(G[11].nodes['x']).astype(np.float64)
+    with pytest.raises(TypeError):
+        B200Backend().pack_graphs(G)
+
+
+def _adjacency(blob, edge_size):
+    h = blob[:80].view(np.int32)
+    n, nnz = int(h[0]), int(h[2])
+    off_edge = int(blob[32:36].view(np.uint32)[0])
+    off_rowptr, off_rowadj = (int(v) for v in blob[52:60].view(np.uint32))
+    rowptr = blob[off_rowptr:off_rowptr + 4 * (n + 1)].view(np.uint32)
+    rowadj = blob[off_rowadj:off_rowadj + 4 * nnz].view(np.uint32)
+    A = np.zeros((n, n), np.float32)
+    for i in range(n):
+        for k in range(rowptr[i], rowptr[i + 1]):
+            e = int(rowadj[k] >> 16)
+            w = blob[off_edge + e * edge_size:off_edge + e * edge_size + 4]
+            A[i, rowadj[k] & 0xffff] = w.view(np.float32)[0]
+    return A
+
+
+def test_parallel_edges_keep_the_first_entry_like_the_reference():
+    """reference _octilegraph.py:141-158: np.unique(..., return_index=True)
+    over [edges ; swapped edges] keeps the first duplicate; the degree still
+    sums every duplicate (:113-117)."""
+    nodes = DataFrame({'!i': np.arange(3, dtype=np.uint32)})
+    edges = DataFrame({'!i': np.array([0, 1, 1, 0], np.uint32),
+                       '!j': np.array([1, 2, 0, 1], np.uint32),
+                       '!w': np.array([1.0, 2.0, 3.0, 4.0], np.float32)})
+    p = B200Backend().pack_graph(Graph(nodes, edges))
+    A = _adjacency(p.blob, 8)       # edge_t = {weight, phantom label}
+    # (0,1): forward entries k=0 (w=1) and k=3 (w=4) precede the swapped k=2
+    assert A[0, 1] == 1.0
+    # (1,0): forward entry k=2 (w=3) precedes the swapped copies of k=0, k=3
+    assert A[1, 0] == 3.0
+    assert A[1, 2] == 2.0 and A[2, 1] == 2.0
+    off_deg = int(p.blob[16:20].view(np.uint32)[0])
+    deg = p.blob[off_deg:off_deg + 12].view(np.float32)
+    assert list(deg) == [8.0, 10.0, 2.0]
+
+
+def test_from_networkx_keeps_attributes_on_their_nodes():
+    nx = pytest.importorskip('networkx')
+    g = nx.Graph()
+    for label, z in ((2, 22), (0, 10), (1, 11)):     # not in sorted order
+        g.add_node(label, z=z)
+    g.add_edge(0, 1, w=1.0)
+    g.add_edge(1, 2, w=2.0)
+    G = Graph.from_networkx(g, weight='w')
+    by_id = dict(zip(np.asarray(G.nodes['!i']).tolist(),
+                     np.asarray(G.nodes['z']).tolist()))
+    assert by_id == {0: 10, 1: 11, 2: 22}
+    nl, _, _ = B200Backend._layouts(G)
+    p = B200Backend().pack_graph(G)
+    off_node = int(p.blob[20:24].view(np.uint32)[0])
+    rows = p.blob[off_node:off_node + 3 * nl.dtype.itemsize].view(nl.dtype)
+    assert rows['z'].tolist() == [10, 11, 22]
+
+
+def test_type_signature_cache_is_invalidated_by_column_assignment():
+    G = make_config_graphs('C2', 30)
+    assert Graph.has_unified_types(G) is True
+    assert Graph.has_unified_types(G) is True        # cached signatures
+    G[9].edges['length'] = np.asarray(G[9].edges['length']).astype(np.float64)
+    verdict = Graph.has_unified_types(G)
+    assert verdict is not True and verdict[0] == 'edges'
+    Graph.unify_datatype(G, inplace=True)
+    assert Graph.has_unified_types(G) is True
+
+
+class _NullBackend:
+    def __new__(cls):
+        from graphdot_b200.kernel.marginalized._backend import Backend
+
+        class Null(Backend):
+            def __call__(self, *a, **k):
+                raise RuntimeError
+        return Null()
+
+
+def test_kernel_range_check_warnings():
+    """reference test/kernel/marginalized/test_kernel.py:572-605"""
+    be = _NullBackend()
+    with pytest.warns(DeprecationWarning):
+        MarginalizedGraphKernel(
+            TensorProduct(a=KroneckerDelta(0.5), b=SquareExponential(1.0))
+            + 1, KroneckerDelta(0.5), backend=be)          # node > 1
+    with pytest.warns(DeprecationWarning):
+        MarginalizedGraphKernel(
+            KroneckerDelta(0.5), KroneckerDelta(0.5) + 1, backend=be)  # edge > 1
+    with pytest.warns(DeprecationWarning):
+        MarginalizedGraphKernel(
+            KroneckerDelta(0.5) * 0.0, KroneckerDelta(0.5), backend=be)  # node 0
+    with warnings.catch_warnings():
+        warnings.simplefilter('error')
+        MarginalizedGraphKernel(KroneckerDelta(0.5), KroneckerDelta(0.5),
+                                backend=be)
+        MarginalizedGraphKernel(Constant(1.0), Constant(1.0), backend=be)
+
+
+@pytest.mark.parametrize('kernel, x, y', [
+    (RationalQuadratic(0.7, 1.5), 0.3, 1.1),
+    (RationalQuadratic(2.0, 0.5), -1.0, 0.25),
+    (DotProduct(), np.array([1.0, 2.0, -0.5]), np.array([0.5, 0.1, 3.0])),
+    (TensorProduct(a=KroneckerDelta(0.4),
+                   b=SquareExponential(0.8)).normalized, (1, 0.3), (2, 0.9)),
+])
+def test_microkernels_against_closed_forms(kernel, x, y):
+    """Second pin of the host evaluation, independent of
+    tests/golden/microkernel_reference.json: closed forms of the definitions
+    (reference microkernel/rational_quadratic.py:11-26, dotproduct.py:9-35,
+    _base.py:388-478) and central differences for the Jacobian."""
+    name = type(kernel).__name__
+    if 'RationalQuadratic' in repr(kernel):
+        ls, al = kernel.theta
+        want = (1 + (x - y) ** 2 / (2 * al * ls ** 2)) ** -al
+        got, jac = kernel(x, y, jac=True)
+    elif 'DotProduct' in repr(kernel) and 'normal' not in repr(kernel):
+        want = float(np.dot(x, y))
+        got, jac = kernel(x, y, jac=True)
+    else:
+        from graphdot_b200.util import flatten
+
+        def rec(a, b):
+            return type('R', (dict,), {'a': a, 'b': b})(a=a, b=b)
+        X, Y = rec(*x), rec(*y)
+        h, ls = flatten(kernel.theta)
+
+        def k(p, q_):
+            return (1.0 if p.a == q_.a else h) * np.exp(
+                -0.5 * (p.b - q_.b) ** 2 / ls ** 2)
+        want = k(X, Y) / np.sqrt(k(X, X) * k(Y, Y))
+        got, jac = kernel(X, Y, jac=True)
+        x, y = X, Y
+    assert got == pytest.approx(want, rel=1e-12), name
+    from graphdot_b200.util import flatten, fold_like
+    theta = np.array(list(flatten(kernel.theta)), float)
+    for m in range(len(theta)):
+        step = 1e-6 * max(1.0, abs(theta[m]))
+        vals = []
+        for sgn in (+1, -1):
+            t = theta.copy()
+            t[m] += sgn * step
+            import copy
+            kk = copy.deepcopy(kernel)
+            kk.theta = fold_like(t, kernel.theta)
+            vals.append(kk(x, y))
+        fd = (vals[0] - vals[1]) / (2 * step)
+        assert np.ravel(jac)[m] == pytest.approx(fd, rel=1e-5, abs=1e-9)
