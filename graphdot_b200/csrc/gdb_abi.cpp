@@ -32,6 +32,7 @@
 extern const char *const gdb_embedded_prelude;
 extern const char *const gdb_embedded_solver;
 extern const char *const gdb_embedded_small;
+extern const char *const gdb_embedded_large;
 
 // ---------------------------------------------------------------------------
 // errors
@@ -54,7 +55,7 @@ extern "C" void gdb_free(void *p) { free(p); }
 
 extern "C" const char *gdb_solver_template(void) {
     static std::string joined = std::string(gdb_embedded_prelude) + "\n/* <generated splice> */\n" + gdb_embedded_solver +
-                                "\n" + gdb_embedded_small;
+                                "\n" + gdb_embedded_small + "\n" + gdb_embedded_large;
     return joined.c_str();
 }
 
@@ -248,7 +249,10 @@ struct gdb_program_s {
     CUmodule mod = nullptr;
     CUfunction fn = nullptr;        // mlgk_solve: any pair size
     CUfunction fn_small = nullptr;  // mlgk_solve_small: pair resident in shared memory
-    int small_regs = 0, small_static_smem = 0;
+    CUfunction fn_large = nullptr;  // mlgk_solve_large: one cluster per pair (graph-level outputs)
+    int small_regs = 0, small_static_smem = 0, large_static_smem = 0;
+    int cluster = 4, lcpt = 16, lell = 12;
+    uint32_t edge_size = 0;
     unsigned layout[8] = {};
     std::string source, log;
     gdb_program_info info{};
@@ -280,6 +284,13 @@ static int pick_wpt(const gdb_program_desc *d) { return d->workers_per_thread <=
 
 static int pick_rpw(const gdb_program_desc *d) { return d->rows_per_warp <= 0 ? 8 : d->rows_per_warp; }
 static int pick_adj(const gdb_program_desc *d) { return d->slots_per_lane <= 0 ? 4 : d->slots_per_lane; }
+static int pick_cluster(const gdb_program_desc *d) {
+    int c = d->cluster_size <= 0 ? 4 : d->cluster_size;
+    if (const char *env = getenv("GDB_CLUSTER")) c = atoi(env);  // tuning hook
+    return c;
+}
+static int pick_lcpt(const gdb_program_desc *d) { return d->cols_per_lane <= 0 ? 16 : d->cols_per_lane; }
+static int pick_lell(const gdb_program_desc *d) { return d->ell_slots <= 0 ? 12 : d->ell_slots; }
 
 static int render(const gdb_program_desc *d, std::string &src) {
     if (!d || !d->node_decl || !d->edge_decl || !d->node_kernel.expr || !d->edge_kernel.expr || !d->p_start.expr)
@@ -290,6 +301,12 @@ static int render(const gdb_program_desc *d, std::string &src) {
     if (pick_wpt(d) > 4) return gdb_fail(GDB_ERR_INVALID, "workers_per_thread must be 1..4");
     if (pick_rpw(d) > 8) return gdb_fail(GDB_ERR_INVALID, "rows_per_warp must be 1..8");
     if (pick_adj(d) != 2 && pick_adj(d) != 4) return gdb_fail(GDB_ERR_INVALID, "slots_per_lane must be 2 or 4");
+    {
+        const int c = pick_cluster(d);
+        if (c != 1 && c != 2 && c != 4 && c != 8) return gdb_fail(GDB_ERR_INVALID, "cluster_size must be 1, 2, 4 or 8");
+        if (pick_lcpt(d) > 32) return gdb_fail(GDB_ERR_INVALID, "cols_per_lane must be 1..32");
+        if (pick_lell(d) > 64) return gdb_fail(GDB_ERR_INVALID, "ell_slots must be 1..64");
+    }
     std::ostringstream o;
     o << gdb_embedded_prelude << "\n";
     o << "// ---- generated splice ----\n";
@@ -309,6 +326,9 @@ static int render(const gdb_program_desc *d, std::string &src) {
     o << "#define GDB_WPT " << pick_wpt(d) << "\n";
     o << "#define GDB_RPW " << pick_rpw(d) << "\n";
     o << "#define GDB_ADJ " << pick_adj(d) << "\n";
+    o << "#define GDB_CLUSTER " << pick_cluster(d) << "\n";
+    o << "#define GDB_LCPT " << pick_lcpt(d) << "\n";
+    o << "#define GDB_LELL " << pick_lell(d) << "\n";
     o << "#define GDB_WEIGHTED " << (d->weighted ? 1 : 0) << "\n";
     o << "#define GDB_DIAGONAL " << (d->diagonal ? 1 : 0) << "\n";
     o << "#define GDB_SYMMETRIC " << (d->symmetric ? 1 : 0) << "\n";
@@ -334,7 +354,7 @@ static int render(const gdb_program_desc *d, std::string &src) {
             o << "static_assert(sizeof(" << names[k] << "_theta_t) == " << fs[k]->theta_size << ", \"" << names[k]
               << " hyper-parameter layout differs from the host dtype\");\n";
     o << "// ---- end of generated splice ----\n";
-    o << gdb_embedded_solver << "\n" << gdb_embedded_small << "\n";
+    o << gdb_embedded_solver << "\n" << gdb_embedded_small << "\n" << gdb_embedded_large << "\n";
     src = o.str();
     return GDB_OK;
 }
@@ -452,6 +472,19 @@ extern "C" int gdb_program_create(gdb_context_t c, const gdb_program_desc *d, gd
     DRV(c, c->cuFuncSetAttribute(p->fn_small, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
                                  (int)c->prop.sharedMemPerBlockOptin - p->small_static_smem));
     p->info.num_regs_small = p->small_regs;
+    p->cluster = pick_cluster(d);
+    p->lcpt = pick_lcpt(d);
+    p->lell = pick_lell(d);
+    p->edge_size = p->layout[6];
+    if (d->nodal == GDB_NODAL_NONE) {
+        DRV(c, c->cuModuleGetFunction(&p->fn_large, p->mod, "mlgk_solve_large"));
+        int v2 = 0;
+        c->cuFuncGetAttribute(&v2, CU_FUNC_ATTRIBUTE_NUM_REGS, p->fn_large);
+        p->info.num_regs_large = v2;
+        c->cuFuncGetAttribute(&p->large_static_smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, p->fn_large);
+        DRV(c, c->cuFuncSetAttribute(p->fn_large, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                     (int)c->prop.sharedMemPerBlockOptin - p->large_static_smem));
+    }
     p->info.n_jac = (int)p->layout[7];
     p->info.from_cache = 0;
     p->info.compile_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -499,6 +532,8 @@ struct gdb_graphset_s {
     // mlgk_small.cuh)
     uint32_t max_ovf[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     uint32_t max_idx[2] = {0, 0};   // two largest (row index + edge elements) byte counts
+    uint32_t max_tc = 0, max_degree = 0;  // large-pair kernel: longest neighbour-row list, largest degree
+    uint64_t sum_node = 0;
     bool index16 = true;            // every graph carries a valid 16-bit row index
 };
 
@@ -574,6 +609,9 @@ extern "C" int gdb_graphset_create(gdb_context_t c, const gdb_layout *L, uint32_
         top2(gs->max_node, (uint32_t)h->n_node);
         top2(gs->max_nnz, (uint32_t)h->nnz);
         if (!(h->flags & 2u)) gs->index16 = false;
+        gs->max_tc = std::max(gs->max_tc, h->max_tc);
+        gs->max_degree = std::max(gs->max_degree, h->max_degree);
+        gs->sum_node += (uint64_t)h->n_node;
         {
             const uint32_t *rowptr = reinterpret_cast<const uint32_t *>(dst + h->off_rowptr);
             const uint32_t *lanemap = reinterpret_cast<const uint32_t *>(dst + h->off_lanemap);
@@ -784,6 +822,43 @@ static int pick_kernel(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, cons
         }
     }
     (void)a;
+    // large-pair kernel: one cluster per pair, when the vectors of the largest pair would
+    // otherwise live in a per-CTA arena (graph-level outputs; 16-bit row index)
+    if (spill && k.kind == 0 && p->fn_large && gs->index16 && !getenv("GDB_FORCE_GENERAL") &&
+        (uint64_t)gs->max_node[0] <= 32ull * p->lcpt) {
+        const uint64_t n2p = ((uint64_t)gs->max_node[0] + 3) & ~3ull;
+        const uint64_t D = std::min<uint64_t>(gs->max_degree, (uint64_t)p->lell);
+        const uint64_t ell = ((D * n2p * 2 + 15) & ~15ull) + ((D * n2p * p->edge_size + 15) & ~15ull) + ((n2p * 2 + 15) & ~15ull);
+        const uint64_t buf = (uint64_t)gs->max_tc * n2p * 4;
+        const uint64_t lcap = std::min<uint64_t>(cap, (uint64_t)c->prop.sharedMemPerBlockOptin - p->large_static_smem);
+        uint64_t need = ell + 2 * buf;
+        if (need > lcap) need = ell + buf;  // single staging buffer
+        if (need <= lcap) {
+            // clusters in flight: what the device can co-schedule, capped so that the
+            // vectors of all of them stay L2-resident
+            const int nvecs = p->eval_gradient ? 6 : 5;
+            const uint64_t per_cluster = (uint64_t)nvecs * gs->max_node[0] * n2p * 4;
+            int ctas_per_sm = 0;
+            DRV(c, c->cuOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, p->fn_large, 256, (size_t)need));
+            uint64_t clusters = (uint64_t)c->prop.multiProcessorCount * std::max(1, ctas_per_sm) / p->cluster;
+            const double mean_n = (double)gs->sum_node / gs->n;
+            const double typical = nvecs * mean_n * mean_n * 4.0 * 1.15;
+            double budget = 0.75 * (double)c->prop.l2CacheSize;
+            if (const char *env = getenv("GDB_L2_BUDGET_MB")) budget = atof(env) * 1048576.0;
+            clusters = std::max<uint64_t>(1, std::min<uint64_t>(clusters, (uint64_t)(budget / typical)));
+            if (const char *env = getenv("GDB_LARGE_CLUSTERS")) clusters = std::max(1, atoi(env));
+            int rc;
+            if ((rc = dev_reserve(c->scratch, clusters * per_cluster))) return rc;
+            k.fn = p->fn_large;
+            k.kind = 2;
+            k.block = 256;
+            k.cluster = (uint32_t)p->cluster;
+            k.grid = clusters * p->cluster;
+            k.smem = need;
+            k.scratch_stride = per_cluster / 4;
+            return GDB_OK;
+        }
+    }
     int blocks_per_sm = 0;
     DRV(c, c->cuOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k.fn, block, (size_t)smem));
     uint64_t grid = (uint64_t)c->prop.multiProcessorCount * blocks_per_sm;
@@ -899,7 +974,7 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
 
     LaunchCfg cfg;
     if ((rc = pick_kernel(c, p, gs, a, cfg))) return rc;
-    a->used_small_kernel = cfg.kind == 1;
+    a->used_small_kernel = cfg.kind;
 
     // ---- launch plan: one launch, or one per block of rows / columns -------------
     std::vector<Tile> tiles;
@@ -995,7 +1070,8 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
         f.n_jobs = T.n_jobs;
         f.i0 = T.i0, f.i1 = T.i1, f.j0 = T.j0, f.j1 = T.j1;
         memcpy(params.data(), &f, sizeof f);
-        const uint64_t grid = std::min<uint64_t>(cfg.grid, T.n_jobs);
+        uint64_t grid = std::min<uint64_t>(cfg.grid, T.n_jobs);
+        if (cfg.kind == 2) grid = std::min<uint64_t>(cfg.grid, T.n_jobs * cfg.cluster);  // whole clusters
         DRV(c, c->cuLaunchKernel(cfg.fn, (unsigned)grid, 1, 1, (unsigned)cfg.block, 1, 1, (unsigned)cfg.smem, (CUstream)st, kargs, nullptr));
         a->n_launches++;
         a->grid = (uint32_t)grid;

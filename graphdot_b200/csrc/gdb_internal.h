@@ -4,7 +4,7 @@
 
 #include "../../include/graphdot_b200.h"
 
-#define GDB_HDR_BYTES 80
+#define GDB_HDR_BYTES 96
 
 // Host mirrors of the device structs in mlgk_solver.cuh.
 struct gdb_graph_hdr_host {
@@ -16,6 +16,13 @@ struct gdb_graph_hdr_host {
     uint32_t off_ellslot;  // u32[nnz] "rowpos": CSR position -> row | (index within the row << 16)
     uint32_t off_lanemap;  // u32[n_node]: [p] & 0xffff = node at degree-sorted position p, [i] >> 16 = position of node i
     uint32_t vcols;        // virtual columns: sum ceil(deg / 2) | sum ceil(deg / 4) << 16 (each >= 1 per node)
+    // neighbour-row lists of the large-pair kernel: for every tile row (8 rows) the
+    // sorted distinct columns its elements touch -- the rows of the search direction
+    // that the matvec of that tile row stages in shared memory
+    uint32_t off_tcptr;    // u32[n_tile + 1]: CSR over tile rows into tccol
+    uint32_t off_tccol;    // u16[]: distinct columns of a tile row, ascending
+    uint32_t off_tcslot;   // u16[nnz]: CSR element k -> index of its column in its tile row's list
+    uint32_t max_tc;       // longest list
 };
 static_assert(sizeof(gdb_graph_hdr_host) == GDB_HDR_BYTES, "header layout");
 

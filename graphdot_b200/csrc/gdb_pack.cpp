@@ -27,6 +27,8 @@ struct Sizes {
     uint32_t nnz, n_octile, n_tile;
     uint64_t off_degree, off_node, off_octile, off_tilerow, off_edge, off_pool, total;
     uint64_t off_emeta, off_rowptr, off_rowadj, off_tileelem, off_ellslot, off_lanemap;
+    uint64_t off_tcptr, off_tccol, off_tcslot;
+    uint32_t n_tc;
 };
 
 struct Nz {
@@ -86,7 +88,24 @@ void plan(const gdb_layout *L, const gdb_graph_src *g, const std::vector<Nz> &nz
     s.off_tileelem = s.off_rowadj + pad16(4ull * s.nnz);
     s.off_ellslot = s.off_tileelem + pad16(4ull * (s.n_tile + 1));
     s.off_lanemap = s.off_ellslot + pad16(4ull * s.nnz);
-    s.off_pool = s.off_lanemap + pad16(4ull * g->n_node);
+    // distinct columns per tile row: nz is sorted by (tile row, tile col, row, col)
+    {
+        std::vector<uint32_t> cols;
+        uint32_t n_tc = 0;
+        size_t k = 0;
+        while (k < nz.size()) {
+            const uint32_t t = nz[k].i >> 3;
+            cols.clear();
+            for (; k < nz.size() && (nz[k].i >> 3) == t; ++k) cols.push_back(nz[k].j);
+            std::sort(cols.begin(), cols.end());
+            n_tc += (uint32_t)(std::unique(cols.begin(), cols.end()) - cols.begin());
+        }
+        s.n_tc = n_tc;
+    }
+    s.off_tcptr = s.off_lanemap + pad16(4ull * g->n_node);
+    s.off_tccol = s.off_tcptr + pad16(4ull * (s.n_tile + 1));
+    s.off_tcslot = s.off_tccol + pad16(2ull * s.n_tc);
+    s.off_pool = s.off_tcslot + pad16(2ull * s.nnz);
     s.total = s.off_pool + pad16(g->pool_bytes);
 }
 
@@ -223,6 +242,31 @@ extern "C" int gdb_graph_pack(const gdb_layout *L, const gdb_graph_src *g, void 
         // nz is sorted by (tile row, tile col, row, col): filling in this order
         // leaves every row's neighbours sorted by column
         for (uint32_t k = 0; k < s.nnz; ++k) rowadj[fill[nz[k].i]++] = (nz[k].j & 0xffffu) | (k << 16);
+        // neighbour-row lists per tile row and the slot of every CSR element in them
+        {
+            uint32_t *tcptr = reinterpret_cast<uint32_t *>(base + s.off_tcptr);
+            uint16_t *tccol = reinterpret_cast<uint16_t *>(base + s.off_tccol);
+            uint16_t *tcslot = reinterpret_cast<uint16_t *>(base + s.off_tcslot);
+            h->off_tcptr = (uint32_t)s.off_tcptr;
+            h->off_tccol = (uint32_t)s.off_tccol;
+            h->off_tcslot = (uint32_t)s.off_tcslot;
+            std::vector<uint32_t> cols;
+            uint32_t at = 0, max_tc = 0;
+            for (uint32_t t = 0; t < s.n_tile; ++t) {
+                tcptr[t] = at;
+                const uint32_t r0 = t * 8u, r1 = std::min(g->n_node, r0 + 8u);
+                cols.clear();
+                for (uint32_t kk = rowptr[r0]; kk < rowptr[r1]; ++kk) cols.push_back(rowadj[kk] & 0xffffu);
+                std::sort(cols.begin(), cols.end());
+                cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+                for (uint32_t c : cols) tccol[at++] = (uint16_t)c;
+                for (uint32_t kk = rowptr[r0]; kk < rowptr[r1]; ++kk)
+                    tcslot[kk] = (uint16_t)(std::lower_bound(cols.begin(), cols.end(), rowadj[kk] & 0xffffu) - cols.begin());
+                max_tc = std::max<uint32_t>(max_tc, (uint32_t)cols.size());
+            }
+            tcptr[s.n_tile] = at;
+            h->max_tc = max_tc;
+        }
         uint32_t k = 0;
         for (uint32_t t = 0; t <= s.n_tile; ++t) {
             while (k < s.nnz && (nz[k].i >> 3) < t) ++k;

@@ -1,0 +1,562 @@
+// mlgk_large.cuh -- solver for LARGE graph pairs (BASELINE configuration C4:
+// 200-500 nodes per graph, N = n1 n2 = 4e4 ... 2.5e5 product-graph nodes): one
+// thread-block CLUSTER per pair.  Same algorithm and results contract as
+// mlgk_solve (mlgk_solver.cuh); replaces reference
+// graphdot/cpp/marginalized_kernel.h:189-490 (compute), :492-804
+// (compute_duo), :806-997 (derivative) and the job loop of reference
+// kernel/marginalized/template.cu:29-475 for pairs in this regime.
+//
+// Why a cluster: the CG vectors of one pair are 5 N floats = 0.8 ... 5 MB.
+// With one CTA per pair, 148+ concurrent pairs stream > 1 GB of vectors through
+// HBM in every iteration (round 1: 16 % of the copy bandwidth, latency bound).
+// With GDB_CLUSTER CTAs per pair only SMs / GDB_CLUSTER pairs are in flight,
+// their vectors stay L2-resident, and every vector pass is split over the
+// cluster's CTAs.
+//
+// Per pair (G1 = rows, G2 = columns, element i = i1 n2p + i2 with the row
+// stride n2p = n2 rounded up to 4):
+//  * the tile rows (8 rows) of G1 are dealt to the CTAs of the cluster in
+//    contiguous blocks; a CTA owns the elements of its rows in ALL vector passes;
+//  * matvec of one tile row: the rows of the search direction p that the tile
+//    row's elements touch -- the packer's sorted list of distinct neighbour
+//    columns of that tile row (gdb_pack.cpp: tcptr / tccol / tcslot), about 14
+//    rows for a banded graph instead of the 24 rows of its 3 octiles -- are
+//    staged in shared memory with cp.async (16-byte LDGSTS, L2 -> smem),
+//    DOUBLE BUFFERED: the rows of tile row t + 1 are in flight while tile row
+//    t is computed.  Warp w of the CTA computes row 8 t + w, lanes own the
+//    columns lane, lane + 32, ...: every gather of p is a conflict-free LDS;
+//  * G2 is held per CTA in shared memory in ELL form (slot-major:
+//    ell[t][column]), so that the lanes' loads of (neighbour, edge label) are
+//    conflict-free as well; the elements of row i1 of G1 sit in registers;
+//    the edge microkernel is evaluated on the fly (nnz1 nnz2 = 2e6 products
+//    per matvec do not fit on chip);
+//  * dot products: warp shuffles -> shared memory -> one DSMEM store per CTA
+//    pair (st.shared::cluster) -> barrier.cluster; every CTA sums the same
+//    partials in the same order, so alpha / beta are bit-identical cluster-wide;
+//  * x, r, p, A p, diag (and y) live in this cluster's slice of a global arena
+//    and are streamed with 128-bit loads; pad columns hold zeros.
+// No atomics, fixed summation order => bit-reproducible results.
+//
+// Macros from the generated header: GDB_CLUSTER (CTAs per pair), GDB_LELL (ELL
+// slots per column held in shared memory; further neighbours are read from
+// global memory).
+#pragma once
+
+#ifndef GDB_CLUSTER
+#define GDB_CLUSTER 4
+#endif
+#ifndef GDB_LELL
+#define GDB_LELL 12
+#endif
+#define GDB_LBLOCK 256  // 8 warps = the 8 rows of a tile row
+#define GDB_LU 8        // elements of a row of G1 held in registers at a time
+
+#if GDB_NODAL == 0  // graph-level outputs only; nodal outputs run in mlgk_solve
+
+__device__ __forceinline__ unsigned gdb_cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned gdb_cluster_id() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void gdb_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store into the same shared-memory variable of CTA `rank` of this cluster (DSMEM)
+__device__ __forceinline__ void gdb_st_cluster(float *local, unsigned rank, float v) {
+    unsigned ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(gdb_smem_u32(local)), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+__device__ __forceinline__ void gdb_st_cluster_u64(unsigned long long *local, unsigned rank, unsigned long long v) {
+    unsigned ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(gdb_smem_u32(local)), "r"(rank));
+    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(ra), "l"(v) : "memory");
+}
+__device__ __forceinline__ void gdb_cp_async16(unsigned dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void gdb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int N> __device__ __forceinline__ void gdb_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct gdb_large_shared {
+    float warp[GDB_LBLOCK / 32][4];     // per-warp partial sums
+    float part[2][GDB_CLUSTER][4];      // per-CTA partial sums, written by every CTA of the cluster
+    unsigned long long job;             // next job, written by the cluster's first CTA
+};
+
+// Sum of K <= 4 values over the whole cluster; one block barrier + one cluster
+// barrier.  Every CTA returns the same bits.
+template<int K> __device__ __forceinline__ void gdb_cluster_sum(float (&v)[K], gdb_large_shared &S, int &flip) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float t = gdb_warp_sum(v[k]);
+        if (lane == 0) S.warp[warp][k] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < GDB_CLUSTER * K) {
+        const unsigned k = threadIdx.x % K, dst = threadIdx.x / K;
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < GDB_LBLOCK / 32; ++w) t += S.warp[w][k];
+        gdb_st_cluster(&S.part[flip][gdb_cluster_rank()][k], dst, t);
+    }
+    gdb_cluster_sync();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float t = 0.f;
+#pragma unroll
+        for (int c = 0; c < GDB_CLUSTER; ++c) t += S.part[flip][c][k];
+        v[k] = t;
+    }
+    flip ^= 1;
+}
+
+struct gdb_large_graph {
+    const float *degree;
+    const node_t *node;
+    const edge_t *edge;
+    const unsigned *rowptr, *rowadj, *rowpos, *tcptr;
+    const unsigned short *tccol, *tcslot;
+    int n, nnz, n_tile, max_degree, max_tc;
+};
+
+__device__ __forceinline__ gdb_large_graph gdb_large_view(const unsigned char *base) {
+    const gdb_graph_hdr *h = reinterpret_cast<const gdb_graph_hdr *>(base);
+    gdb_large_graph v;
+    v.degree = reinterpret_cast<const float *>(base + h->off_degree);
+    v.node = reinterpret_cast<const node_t *>(base + h->off_node);
+    v.edge = reinterpret_cast<const edge_t *>(base + h->off_edge);
+    v.rowptr = reinterpret_cast<const unsigned *>(base + h->off_rowptr);
+    v.rowadj = reinterpret_cast<const unsigned *>(base + h->off_rowadj);
+    v.rowpos = reinterpret_cast<const unsigned *>(base + h->off_ellslot);
+    v.tcptr = reinterpret_cast<const unsigned *>(base + h->off_tcptr);
+    v.tccol = reinterpret_cast<const unsigned short *>(base + h->off_tccol);
+    v.tcslot = reinterpret_cast<const unsigned short *>(base + h->off_tcslot);
+    v.n = h->n_node;
+    v.nnz = h->nnz;
+    v.n_tile = h->n_tile;
+    v.max_degree = (int)h->max_degree;
+    v.max_tc = (int)h->max_tc;
+    return v;
+}
+
+// Everything a CTA needs to sweep its tile rows of the product graph.
+struct gdb_large_ctx {
+    gdb_large_graph g1, g2;
+    unsigned n2p;                 // row stride of the vectors (floats)
+    int t_lo, t_hi;               // this CTA's tile rows of G1
+    unsigned short *ell_col;      // [D2][n2p] neighbour (column of G2) in slot t of column c
+    edge_t *ell_e;                // [D2][n2p] its edge
+    unsigned short *deg2;         // [n2p] stored elements of column c (0 for pad columns)
+    int D2;                       // ELL slots in shared memory
+    float *stage[2];              // staged rows of the gathered vector
+    bool dbl;                     // both staging buffers usable
+};
+
+// cp.async the rows of `vec` that tile row t of G1 touches into staging buffer b
+__device__ __forceinline__ void gdb_large_stage(const gdb_large_ctx &C, const float *vec, int t, int b) {
+    const unsigned c0 = C.g1.tcptr[t], cnt = C.g1.tcptr[t + 1] - c0;
+    const unsigned per_row = C.n2p / 4u;  // 16-byte chunks per row
+    const unsigned dst0 = gdb_smem_u32(C.stage[b]);
+    const unsigned lane = threadIdx.x & 31u;
+    // a warp copies whole rows, its lanes consecutive 16-byte chunks (no index division)
+    for (unsigned s = threadIdx.x >> 5; s < cnt; s += GDB_LBLOCK / 32) {
+        const float *src = vec + (size_t)C.g1.tccol[c0 + s] * C.n2p;
+        const unsigned dst = dst0 + s * C.n2p * 4u;
+#pragma unroll 4
+        for (unsigned ch = lane; ch < per_row; ch += 32u) gdb_cp_async16(dst + ch * 16u, src + ch * 4u);
+    }
+}
+
+// One sweep over this CTA's tile rows with `vec` staged.
+//  MODE 0 (matvec):  out[i] = diag[i] vec[i] - sum_j W_ij vec[j]; returns sum vec[i] out[i] in res[0]
+//  MODE 1 (edge Jacobian): res[m] += sum_i yv[i] sum_j w1 w2 dkE_m(e1, e2) vec[j]
+template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_params &P, const gdb_large_ctx &C,
+                                                                   const float *vec, const float *__restrict__ diag,
+                                                                   float *__restrict__ out, const float *__restrict__ yv,
+                                                                   float *res) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int n1 = C.g1.n, n2 = C.g2.n;
+    const unsigned n2p = C.n2p;
+    if (C.t_lo < C.t_hi) {
+        gdb_large_stage(C, vec, C.t_lo, 0);
+        gdb_cp_async_commit();
+    }
+    for (int t = C.t_lo; t < C.t_hi; ++t) {
+        const int b = C.dbl ? ((t - C.t_lo) & 1) : 0;
+        if (C.dbl && t + 1 < C.t_hi) {
+            gdb_large_stage(C, vec, t + 1, b ^ 1);
+            gdb_cp_async_commit();
+            gdb_cp_async_wait<1>();
+        } else {
+            gdb_cp_async_wait<0>();
+        }
+        __syncthreads();  // staged rows of tile row t visible to every warp
+        const int i1 = 8 * t + (int)warp;
+        if (i1 < n1) {
+            const unsigned k1beg = C.g1.rowptr[i1], deg1 = C.g1.rowptr[i1 + 1] - k1beg;
+            const unsigned stage_sa = gdb_smem_u32(C.stage[b]);
+            constexpr int NACC = MODE == 0 ? 1 : (GDB_NE > 0 ? GDB_NE : 1);
+            // acc[] += (edge value | edge Jacobian) of (e1, e2) times the staged vector entry
+            auto product = [&](const edge_t &e1, const edge_t &e2, float pj, float (&acc)[NACC]) {
+                if constexpr (MODE == 0) {
+                    acc[0] = fmaf(gdb_edge_value(P, e1, e2), pj, acc[0]);
+                } else {
+#if GDB_NE > 0
+                    float de[GDB_NE];
+                    P.edge_kernel.jacobian(e1.label, e2.label, de);
+#if GDB_WEIGHTED
+                    pj *= e1.weight * e2.weight;
+#endif
+#pragma unroll
+                    for (int a = 0; a < GDB_NE; ++a) acc[a] = fmaf(de[a], pj, acc[a]);
+#endif
+                }
+            };
+            // the first GDB_LU elements of row i1 stay in registers for all columns (warp-uniform)
+            edge_t e1r[GDB_LU];
+            unsigned base[GDB_LU];
+            const unsigned nu = min((unsigned)GDB_LU, deg1);
+#pragma unroll
+            for (int u = 0; u < GDB_LU; ++u) {
+                const unsigned k1 = k1beg + min((unsigned)u, nu - 1u);
+                e1r[u] = C.g1.edge[C.g1.rowadj[k1] >> 16];
+                base[u] = stage_sa + (unsigned)C.g1.tcslot[k1] * n2p * 4u;
+            }
+#pragma unroll 1
+            for (unsigned c0 = 0; c0 < (unsigned)n2; c0 += 32u) {  // rolled: the body must stay in the instruction cache
+                const unsigned c = c0 + lane;
+                const bool live = c < (unsigned)n2;
+                const unsigned d2 = live ? C.deg2[c] : 0u;
+                const unsigned d2s = min(d2, (unsigned)C.D2);
+                float acc[NACC];
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
+                for (unsigned t2 = 0; t2 < d2s; ++t2) {
+                    const unsigned j2 = C.ell_col[t2 * n2p + c];
+                    const edge_t e2 = C.ell_e[t2 * n2p + c];
+#pragma unroll
+                    for (int u = 0; u < GDB_LU; ++u) {
+                        if ((unsigned)u < nu) {  // warp-uniform
+                            float pj;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(base[u] + j2 * 4u));
+                            product(e1r[u], e2, pj, acc);
+                        }
+                    }
+                    // rows of G1 with more than GDB_LU elements (rare): the rest from global memory
+                    for (unsigned k1 = k1beg + GDB_LU; k1 < k1beg + deg1; ++k1)
+                        product(C.g1.edge[C.g1.rowadj[k1] >> 16], e2, C.stage[b][(unsigned)C.g1.tcslot[k1] * n2p + j2], acc);
+                }
+                if (d2 > d2s) {  // rare: neighbours beyond the ELL slots, from global memory
+                    const unsigned kb = C.g2.rowptr[c];
+                    for (unsigned t2 = d2s; t2 < d2; ++t2) {
+                        const unsigned a2 = C.g2.rowadj[kb + t2], j2 = a2 & 0xffffu;
+                        const edge_t e2 = C.g2.edge[a2 >> 16];
+                        for (unsigned k1 = k1beg; k1 < k1beg + deg1; ++k1)
+                            product(C.g1.edge[C.g1.rowadj[k1] >> 16], e2, C.stage[b][(unsigned)C.g1.tcslot[k1] * n2p + j2], acc);
+                    }
+                }
+                if (live) {  // own element
+                    const size_t i = (size_t)i1 * n2p + c;
+                    if constexpr (MODE == 0) {
+                        const float v = vec[i];
+                        const float r = fmaf(diag[i], v, -acc[0]);
+                        out[i] = r;
+                        res[0] = fmaf(v, r, res[0]);
+                    } else {
+                        const float yi = yv[i];
+#pragma unroll
+                        for (int a = 0; a < NACC; ++a) res[a] = fmaf(yi, acc[a], res[a]);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // every warp is done with buffer b before it is refilled
+        if (!C.dbl && t + 1 < C.t_hi) {
+            gdb_large_stage(C, vec, t + 1, 0);
+            gdb_cp_async_commit();
+        }
+    }
+}
+
+// Jacobi-PCG over the cluster for A x = rhs, x0 = 0.  On entry r = rhs on this
+// CTA's elements [e_lo, e_hi); on exit x holds the solution there.
+__device__ __forceinline__ int gdb_large_pcg(const gdb_params &P, const gdb_large_ctx &C, const float *__restrict__ diag,
+                                             float *__restrict__ x, float *__restrict__ r, float *p, float *__restrict__ Ap,
+                                             size_t e_lo, size_t e_hi, int N, float tol, gdb_large_shared &S, int &flip) {
+    float4 *x4 = reinterpret_cast<float4 *>(x), *r4 = reinterpret_cast<float4 *>(r), *p4 = reinterpret_cast<float4 *>(p);
+    const float4 *d4 = reinterpret_cast<const float4 *>(diag), *a4 = reinterpret_cast<const float4 *>(Ap);
+    const size_t q_lo = e_lo / 4, q_hi = e_hi / 4;  // float4 range (rows are multiples of 4 floats)
+    float s1[1] = {0.f};
+    for (size_t i = q_lo + threadIdx.x; i < q_hi; i += GDB_LBLOCK) {
+        const float4 rv = r4[i], dv = d4[i];
+        const float4 z = make_float4(__fdividef(rv.x, dv.x), __fdividef(rv.y, dv.y), __fdividef(rv.z, dv.z), __fdividef(rv.w, dv.w));
+        x4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        p4[i] = z;
+        s1[0] += rv.x * z.x + rv.y * z.y + rv.z * z.z + rv.w * z.w;
+    }
+    gdb_cluster_sum(s1, S, flip);  // cluster barrier: p is complete everywhere
+    float rho = s1[0];
+    const float thresh2 = (tol * (float)N) * (tol * (float)N);
+    int k = 0;
+    while (k < N && rho != 0.f) {
+        float pAp[1] = {0.f};
+        gdb_large_sweep<0>(P, C, p, diag, Ap, nullptr, pAp);
+        gdb_cluster_sum(pAp, S, flip);
+        if (pAp[0] == 0.f) break;
+        ++k;
+        const float alpha = __fdividef(rho, pAp[0]);
+        float s2[2] = {0.f, 0.f};
+        for (size_t i = q_lo + threadIdx.x; i < q_hi; i += GDB_LBLOCK) {
+            const float4 pv = p4[i], av = a4[i], dv = d4[i];
+            float4 xv = x4[i], rv = r4[i];
+            xv.x = fmaf(alpha, pv.x, xv.x), xv.y = fmaf(alpha, pv.y, xv.y), xv.z = fmaf(alpha, pv.z, xv.z), xv.w = fmaf(alpha, pv.w, xv.w);
+            rv.x = fmaf(-alpha, av.x, rv.x), rv.y = fmaf(-alpha, av.y, rv.y), rv.z = fmaf(-alpha, av.z, rv.z), rv.w = fmaf(-alpha, av.w, rv.w);
+            x4[i] = xv;
+            r4[i] = rv;
+            s2[0] += rv.x * rv.x + rv.y * rv.y + rv.z * rv.z + rv.w * rv.w;
+            s2[1] += rv.x * __fdividef(rv.x, dv.x) + rv.y * __fdividef(rv.y, dv.y) + rv.z * __fdividef(rv.z, dv.z) +
+                     rv.w * __fdividef(rv.w, dv.w);
+        }
+        gdb_cluster_sum(s2, S, flip);
+        if (s2[0] < thresh2) break;
+        const float beta = __fdividef(s2[1], rho);
+        for (size_t i = q_lo + threadIdx.x; i < q_hi; i += GDB_LBLOCK) {
+            const float4 pv = p4[i], rv = r4[i], dv = d4[i];
+            p4[i] = make_float4(fmaf(beta, pv.x, __fdividef(rv.x, dv.x)), fmaf(beta, pv.y, __fdividef(rv.y, dv.y)),
+                                fmaf(beta, pv.z, __fdividef(rv.z, dv.z)), fmaf(beta, pv.w, __fdividef(rv.w, dv.w)));
+        }
+        rho = s2[1];
+        gdb_cluster_sync();  // p complete everywhere before the next matvec stages its rows
+    }
+    return k;
+}
+
+extern "C" __global__ void __cluster_dims__(GDB_CLUSTER, 1, 1) __launch_bounds__(GDB_LBLOCK, 1)
+    mlgk_solve_large(const __grid_constant__ gdb_params P) {
+    extern __shared__ __align__(16) unsigned char gdb_smem[];
+    __shared__ gdb_large_shared S;
+    int flip = 0;
+    const gdb_params_fixed &F = P.f;
+    const unsigned rank = gdb_cluster_rank();
+#if GDB_GRADIENT
+    constexpr int NVEC = 6;
+#else
+    constexpr int NVEC = 5;
+#endif
+    float *const arena = F.scratch + (size_t)gdb_cluster_id() * F.scratch_stride;
+    gdb_cluster_sync();  // every CTA of the cluster has started: its shared memory may be written remotely
+
+    while (true) {
+        // ---- the cluster's first CTA claims a job and tells the others (DSMEM) ------
+        if (rank == 0 && threadIdx.x < GDB_CLUSTER) {
+            unsigned long long job = 0;
+            if (threadIdx.x == 0) job = atomicAdd(F.counters, 1ull);
+            job = __shfl_sync((1u << GDB_CLUSTER) - 1u, job, 0);
+            gdb_st_cluster_u64(&S.job, threadIdx.x, job);
+        }
+        gdb_cluster_sync();
+        const unsigned long long job = S.job;
+        if (job >= F.n_jobs) break;
+        unsigned ja, jb;
+        gdb_decode_job(F, job, ja, jb);
+        const gdb_graph_ref ref1 = F.graphs[ja], ref2 = F.graphs[jb];
+        gdb_large_ctx C;
+        C.g1 = gdb_large_view(ref1.blob);
+        C.g2 = gdb_large_view(ref2.blob);
+        const int n1 = C.g1.n, n2 = C.g2.n, N = n1 * n2;
+        const unsigned n2p = ((unsigned)n2 + 3u) & ~3u;
+        C.n2p = n2p;
+        // tile rows of G1 dealt to the CTAs in contiguous, balanced blocks
+        C.t_lo = (int)((long long)C.g1.n_tile * rank / GDB_CLUSTER);
+        C.t_hi = (int)((long long)C.g1.n_tile * (rank + 1) / GDB_CLUSTER);
+        const int row_lo = min(8 * C.t_lo, n1), row_hi = min(8 * C.t_hi, n1);
+        const size_t e_lo = (size_t)row_lo * n2p, e_hi = (size_t)row_hi * n2p;
+        const size_t Npad = (size_t)n1 * n2p;
+
+        // ---- shared memory: ELL copy of G2 | staging buffers ---------------------------
+        C.D2 = min(C.g2.max_degree, GDB_LELL);
+        unsigned off = 0;
+        C.ell_col = reinterpret_cast<unsigned short *>(gdb_smem);
+        off += (((unsigned)C.D2 * n2p * 2u) + 15u) & ~15u;
+        C.ell_e = reinterpret_cast<edge_t *>(gdb_smem + off);
+        off += (((unsigned)C.D2 * n2p * (unsigned)sizeof(edge_t)) + 15u) & ~15u;
+        C.deg2 = reinterpret_cast<unsigned short *>(gdb_smem + off);
+        off += ((n2p * 2u) + 15u) & ~15u;
+        const unsigned buf_bytes = (unsigned)C.g1.max_tc * n2p * 4u;
+        C.stage[0] = reinterpret_cast<float *>(gdb_smem + off);
+        C.dbl = off + 2u * buf_bytes <= F.smem_bytes;
+        C.stage[1] = C.dbl ? reinterpret_cast<float *>(gdb_smem + off + buf_bytes) : C.stage[0];
+        for (unsigned c = threadIdx.x; c < n2p; c += GDB_LBLOCK)
+            C.deg2[c] = c < (unsigned)n2 ? (unsigned short)(C.g2.rowptr[c + 1] - C.g2.rowptr[c]) : (unsigned short)0;
+        for (unsigned k2 = threadIdx.x; k2 < (unsigned)C.g2.nnz; k2 += GDB_LBLOCK) {
+            const unsigned rp = C.g2.rowpos[k2], c = rp & 0xffffu, t2 = rp >> 16;
+            if (t2 < (unsigned)C.D2) {
+                const unsigned a2 = C.g2.rowadj[k2];
+                C.ell_col[t2 * n2p + c] = (unsigned short)(a2 & 0xffffu);
+                C.ell_e[t2 * n2p + c] = C.g2.edge[a2 >> 16];
+            }
+        }
+
+        float *x = arena, *r = arena + Npad, *p = arena + 2 * Npad, *Ap = arena + 3 * Npad, *diag = arena + 4 * Npad;
+        const float Q = 1.0f / (1.0f - F.q), Q2 = Q * Q;
+
+        // ---- setup on this CTA's rows: diag = Dx / Vx, rhs = Dx; pad columns neutral ----
+        for (size_t e = e_lo + threadIdx.x; e < e_hi; e += GDB_LBLOCK) {
+            const unsigned i1 = (unsigned)(e / n2p), i2 = (unsigned)(e - (size_t)i1 * n2p);
+            float d = 1.f, b = 0.f;
+            if (i2 < (unsigned)n2) {
+                b = C.g1.degree[i1] * C.g2.degree[i2] * Q2;
+                d = __fdividef(b, P.node_kernel(C.g1.node[i1], C.g2.node[i2]));
+            }
+            diag[e] = d;
+            r[e] = b;
+            Ap[e] = 0.f;
+        }
+        __syncthreads();  // ELL copy complete (the first cluster barrier inside the solve orders the rest)
+        int iters = gdb_large_pcg(P, C, diag, x, r, p, Ap, e_lo, e_hi, N, F.ftol, S, flip);
+#if GDB_GRADIENT
+        float *y = arena + 5 * Npad;
+        for (size_t e = e_lo + threadIdx.x; e < e_hi; e += GDB_LBLOCK) {
+            const unsigned i1 = (unsigned)(e / n2p), i2 = (unsigned)(e - (size_t)i1 * n2p);
+            r[e] = i2 < (unsigned)n2 ? P.p_start(C.g1.node[i1]) * P.p_start(C.g2.node[i2]) : 0.f;
+        }
+        iters += gdb_large_pcg(P, C, diag, y, r, p, Ap, e_lo, e_hi, N, F.ftol, S, flip);
+#endif
+        if (rank == 0 && threadIdx.x == 0) {
+            atomicAdd(F.counters + 1, (unsigned long long)iters);
+            atomicAdd(F.counters + 2, (unsigned long long)iters * (unsigned long long)C.g1.nnz * (unsigned long long)C.g2.nnz);
+            atomicAdd(F.counters + 3, (unsigned long long)iters * (unsigned long long)N);
+        }
+
+        // ---- epilogue over this CTA's elements --------------------------------------------
+        constexpr int NACC = 1 + (GDB_GRADIENT ? GDB_NP + 1 + GDB_NV : 0);
+        float acc[NACC];
+#pragma unroll
+        for (int m = 0; m < NACC; ++m) acc[m] = 0.f;
+        for (size_t e = e_lo + threadIdx.x; e < e_hi; e += GDB_LBLOCK) {
+            const unsigned i1 = (unsigned)(e / n2p), i2 = (unsigned)(e - (size_t)i1 * n2p);
+            if (i2 >= (unsigned)n2) continue;
+            const node_t &u1 = C.g1.node[i1];
+            const node_t &u2 = C.g2.node[i2];
+            const float p1 = P.p_start(u1), p2 = P.p_start(u2);
+            const float dx = C.g1.degree[i1] * C.g2.degree[i2] * Q2;
+            const float v = __fdividef(dx, diag[e]);  // Vx recovered from the cached diagonal
+            const float xi = x[e];
+            float xs = xi;
+#if GDB_LMIN == 1
+            xs -= v;
+#endif
+            acc[0] = fmaf(xs, p1 * p2, acc[0]);
+#if GDB_GRADIENT
+            const float yi = y[e];
+#if GDB_NP > 0
+            {
+                float d1[GDB_NP], d2[GDB_NP];
+                P.p_start.jacobian(u1, d1);
+                P.p_start.jacobian(u2, d2);
+#pragma unroll
+                for (int m = 0; m < GDB_NP; ++m) acc[1 + m] = fmaf(fmaf(d1[m], p2, p1 * d2[m]), xs, acc[1 + m]);
+            }
+#endif
+            acc[1 + GDB_NP] += 2.f * Q * dx * yi * (1.f - __fdividef(xi, v));
+#if GDB_NV > 0
+            {
+                float dv[GDB_NV];
+                P.node_kernel.jacobian(u1, u2, dv);
+                const float cc = yi * xi * __fdividef(dx, v * v);
+#pragma unroll
+                for (int m = 0; m < GDB_NV; ++m) {
+                    float t = cc * dv[m];
+#if GDB_LMIN == 1
+                    t -= p1 * p2 * dv[m];
+#endif
+                    acc[2 + GDB_NP + m] += t;
+                }
+            }
+#endif
+#endif
+        }
+#if GDB_GRADIENT && GDB_NE > 0
+        float eacc[GDB_NE];
+#pragma unroll
+        for (int m = 0; m < GDB_NE; ++m) eacc[m] = 0.f;
+        gdb_large_sweep<1>(P, C, x, nullptr, nullptr, y, eacc);
+#endif
+#pragma unroll
+        for (int m0 = 0; m0 < NACC; m0 += 4) {
+            float part[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) part[k] = (m0 + k < NACC) ? acc[m0 + k] : 0.f;
+            gdb_cluster_sum(part, S, flip);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (m0 + k < NACC) acc[m0 + k] = part[k];
+        }
+#if GDB_GRADIENT && GDB_NE > 0
+#pragma unroll
+        for (int m0 = 0; m0 < GDB_NE; m0 += 4) {
+            float part[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) part[k] = (m0 + k < GDB_NE) ? eacc[m0 + k] : 0.f;
+            gdb_cluster_sum(part, S, flip);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (m0 + k < GDB_NE) eacc[m0 + k] = part[k];
+        }
+#endif
+        if (rank == 0 && threadIdx.x == 0) {
+            const unsigned I1 = F.starts[ja] - F.row0, I2 = F.starts[jb] - F.col0;
+            const unsigned long long plane = (unsigned long long)F.nX * F.nY;
+            (void)plane;
+            (void)I2;
+#if !GDB_DIAGONAL
+            const float norm_rs = gdb_norm_scale(F, ja, jb);
+            acc[0] *= norm_rs;
+#endif
+#if GDB_DIAGONAL
+            F.gram[I1] = acc[0];
+#else
+            F.gram[(unsigned long long)I1 + (unsigned long long)I2 * F.nX] = acc[0];
+#if GDB_SYMMETRIC
+            if (ja != jb) F.gram[(unsigned long long)I2 + (unsigned long long)I1 * F.nX] = acc[0];
+#endif
+#endif
+#if GDB_GRADIENT
+#pragma unroll
+            for (int m = 0; m < GDB_NJ; ++m) {
+                float val;
+                if (m < GDB_NP + 1 + GDB_NV) {
+                    val = acc[1 + m];
+                } else {
+#if GDB_NE > 0
+                    val = eacc[m - (GDB_NP + 1 + GDB_NV)];
+#else
+                    val = 0.f;
+#endif
+                }
+#if GDB_DIAGONAL
+                F.grad[(unsigned long long)I1 + (unsigned long long)m * F.nX] = val;
+#else
+                val = gdb_norm_grad(F, ja, jb, m, norm_rs, acc[0], val);
+                F.grad[(unsigned long long)I1 + (unsigned long long)I2 * F.nX + m * plane] = val;
+#if GDB_SYMMETRIC
+                if (ja != jb) F.grad[(unsigned long long)I2 + (unsigned long long)I1 * F.nX + m * plane] = val;
+#endif
+#endif
+            }
+#endif
+        }
+        // the next job's setup overwrites the arena and the shared-memory tables: every
+        // CTA of the cluster must be done reading them (the job-claim barrier at the top
+        // of the loop provides that)
+    }
+}
+
+#endif  // GDB_NODAL == 0

@@ -57,6 +57,7 @@ struct gdb_graph_hdr {
     unsigned off_edge, off_pool, blob_bytes, flags;
     unsigned off_emeta, off_rowptr, off_rowadj, off_tileelem;
     unsigned max_degree, off_ellslot, off_lanemap, vcols;
+    unsigned off_tcptr, off_tccol, off_tcslot, max_tc;
 };
 
 struct gdb_octile {

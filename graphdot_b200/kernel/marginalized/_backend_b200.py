@@ -226,6 +226,11 @@ class GraphSet:
         # neighbour slots per lane of the small-pair kernel
         nnz = sum(int(p.blob[:16].view(np.int32)[2]) for p in packed)
         self.mean_degree = nnz / max(1, int(self.sizes.sum()))
+        # header word 16 = largest degree: sizes the ELL copy of the large-pair
+        # kernel (only looked at for sets of large graphs)
+        self.max_degree = (max(int(p.blob[64:68].view(np.uint32)[0])
+                               for p in packed)
+                           if int(self.sizes.max()) > 32 else 0)
 
     @property
     def nbytes(self):
@@ -283,11 +288,12 @@ class B200Backend(Backend):
         return native.pinned_empty(size, dtype)
 
     def __init__(self, device=0, block_size=None, nvrtc_extra=(),
-                 graphset_cache=4, slots_per_lane=None):
+                 graphset_cache=4, slots_per_lane=None, cluster_size=None):
         self.uuid = uuid.uuid4()
         self.device = device
         self.block_size = block_size
         self.slots_per_lane = slots_per_lane   # 2 / 4 / None = by mean degree
+        self.cluster_size = cluster_size       # CTAs per large pair; None = 4
         self.nvrtc_extra = list(nvrtc_extra)
         self._context = None
         self._programs = {}
@@ -574,6 +580,14 @@ class B200Backend(Backend):
                                  gs.mean_degree)
         d, keep, key = self._desc(nl, el, weighted, node_kernel, edge_kernel,
                                   p, traits, block, self.nvrtc_extra)
+        # large-pair (cluster) kernel: columns per lane from the largest
+        # graph, ELL depth from the largest degree
+        n_max = int(np.max(gs.sizes))
+        large = (self.cluster_size or 0,
+                 -(-n_max // 32) if 32 < n_max <= 1024 else 0,
+                 min(16, max(1, gs.max_degree)) if n_max > 32 else 0)
+        d.cluster_size, d.cols_per_lane, d.ell_slots = large
+        key = key + large
         prog = self._programs.get(key)
         if prog is None:
             prog = C.c_void_p()
@@ -682,7 +696,10 @@ class B200Backend(Backend):
                          vector_elements=a.vector_elements,
                          h2d_bytes=a.h2d_bytes, d2h_bytes=a.d2h_bytes,
                          n_jobs=n_jobs, n_launches=a.n_launches,
-                         small_kernel=bool(a.used_small_kernel), grid=a.grid,
+                         small_kernel=a.used_small_kernel == 1,
+                         kernel=('mlgk_solve', 'mlgk_solve_small',
+                                 'mlgk_solve_large')[a.used_small_kernel],
+                         grid=a.grid,
                          smem_bytes=a.smem_bytes)
         return a
 

@@ -53,12 +53,14 @@ class ProgramDesc(C.Structure):
                 ('workers_per_thread', C.c_int32),
                 ('rows_per_warp', C.c_int32),
                 ('slots_per_lane', C.c_int32),
-                ('extra_options', C.c_char_p)]
+                ('extra_options', C.c_char_p),
+                ('cluster_size', C.c_int32), ('cols_per_lane', C.c_int32),
+                ('ell_slots', C.c_int32)]
 
 
 class ProgramInfo(C.Structure):
     _fields_ = [('block_size', C.c_int32), ('num_regs', C.c_int32),
-                ('num_regs_small', C.c_int32),
+                ('num_regs_small', C.c_int32), ('num_regs_large', C.c_int32),
                 ('static_smem', C.c_int32), ('local_bytes', C.c_int32),
                 ('max_dynamic_smem', C.c_int32), ('n_jac', C.c_int32),
                 ('from_cache', C.c_int32), ('compile_ms', C.c_float)]

@@ -116,12 +116,20 @@ typedef struct gdb_program_desc {
                                 4; 0 = 4.  Columns of higher degree borrow
                                 the idle lanes of the warp as helpers       */
     const char *extra_options; /* extra NVRTC options, space separated     */
+    /* large-pair kernel (one thread-block cluster per pair; used when the CG
+     * vectors of the largest pair do not fit in shared memory)            */
+    int32_t cluster_size;    /* CTAs per pair: 1, 2, 4 or 8; 0 = 4          */
+    int32_t cols_per_lane;   /* columns of the second graph per lane, 1..32;
+                                32 * cols_per_lane >= nodes; 0 = 16          */
+    int32_t ell_slots;       /* neighbours per column of the second graph
+                                held in shared memory (ELL), 1..64; 0 = 12   */
 } gdb_program_desc;
 
 typedef struct gdb_program_info {
     int32_t block_size;
     int32_t num_regs;        /* general kernel (mlgk_solve)                */
     int32_t num_regs_small;  /* shared-memory kernel (mlgk_solve_small)    */
+    int32_t num_regs_large;  /* cluster kernel (mlgk_solve_large), 0 = none */
     int32_t static_smem;
     int32_t local_bytes;     /* spill / stack per thread                   */
     int32_t max_dynamic_smem;
@@ -148,10 +156,11 @@ void gdb_free(void *p);
  * Replaces OctileGraph (reference _octilegraph.py:11-189) and graph_t
  * (reference graphdot/cpp/graph.h:8-33).  A packed graph is ONE
  * position-independent, 16-byte aligned blob
- *   [header 80 B | degree f32[n] | node_t[n] | octile[n_oct]
+ *   [header 96 B | degree f32[n] | node_t[n] | octile[n_oct]
  *    | tile_row u32[T+1] | edge_t[nnz]
  *    | elem_meta u32[nnz] | row_ptr u32[n+1] | row_adj u32[nnz]
  *    | tile_elem u32[T+1] | row_pos u32[nnz] | lane_map u32[n]
+ *    | tc_ptr u32[T+1] | tc_col u16[] | tc_slot u16[nnz]
  *    | variable-length feature pool]
  * with 8x8 octiles sorted by (tile row, tile column), a row-major 64-bit
  * non-zero mask per octile and compact row-major elements.  Degrees are the
@@ -297,7 +306,8 @@ typedef struct gdb_solve_args {
     uint64_t vector_elements; /* total N = n1*n2 summed over CG iterations */
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t n_launches;
-    int32_t used_small_kernel; /* 1: mlgk_solve_small ran, 0: mlgk_solve    */
+    int32_t used_small_kernel; /* 1: mlgk_solve_small ran, 2: mlgk_solve_large,
+                                  0: mlgk_solve                              */
     uint32_t grid, smem_bytes; /* launch configuration used                 */
 } gdb_solve_args;
 

@@ -40,6 +40,7 @@ def main():
     ap.add_argument('--c4-graphs', type=int, default=24)
     ap.add_argument('--c5-graphs', type=int, default=4000)
     ap.add_argument('--only', default='')
+    ap.add_argument('--c4-grad', action='store_true')
     args = ap.parse_args()
     be = B200Backend()
     rows = []
@@ -50,6 +51,8 @@ def main():
                    pairs_per_s=pairs / secs,
                    kernel_ms=last.get('kernel_ms'),
                    small_kernel=last.get('small_kernel'),
+                   kernel=last.get('kernel'), grid=last.get('grid'),
+                   smem_bytes=last.get('smem_bytes'),
                    cg_iterations_per_pair=last.get('cg_iterations', 0) / max(1, last.get('n_jobs', 1)),
                    **extra)
         rows.append(row)
@@ -76,7 +79,10 @@ def main():
     if not only or 'C4' in only:
         G = make_config_graphs('C4', args.c4_graphs)
         k = make_config_kernel('C4', backend=be)
-        K, t = timed(lambda: k(G), repeat=1)
+        if args.c4_grad:
+            (K, dK), t = timed(lambda: k(G, eval_gradient=True), repeat=1)
+        else:
+            K, t = timed(lambda: k(G), repeat=1)
         n = np.array([len(g.nodes) for g in G])
         # SURVEY 8(d) byte model of the large-pair regime: per pair
         # it (40 N + (nnz1 + nnz2) |edge_t|) + 12 N; sum(it N) and sum(it nnz1 nnz2)
@@ -85,7 +91,8 @@ def main():
         sum_N = float(np.outer(n, n)[iu].sum())
         model_bytes = 40.0 * be.last['vector_elements'] + 12.0 * sum_N
         gbps = model_bytes / (be.last['kernel_ms'] * 1e-3) / 1e9
-        record('C4', len(G) * (len(G) + 1) // 2, t, n_graphs=len(G),
+        record('C4' + ('+grad' if args.c4_grad else ''),
+               len(G) * (len(G) + 1) // 2, t, n_graphs=len(G),
                mean_N=float(np.mean(np.outer(n, n))),
                model_GBps=gbps, hbm_peak_GBps=6551.0,
                hbm_frac=gbps / 6551.0,
