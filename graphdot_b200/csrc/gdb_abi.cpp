@@ -252,7 +252,7 @@ struct gdb_program_s {
     CUfunction fn_large = nullptr;  // mlgk_solve_large: one cluster per pair (graph-level outputs)
     int small_regs = 0, small_static_smem = 0, large_static_smem = 0;
     int cluster = 4, lcpt = 16, lell = 12;
-    uint32_t edge_size = 0;
+    uint32_t edge_size = 0, ell_entry = 8, large_block = 1024;
     unsigned layout[8] = {};
     std::string source, log;
     gdb_program_info info{};
@@ -478,6 +478,16 @@ extern "C" int gdb_program_create(gdb_context_t c, const gdb_program_desc *d, gd
     p->edge_size = p->layout[6];
     if (d->nodal == GDB_NODAL_NONE) {
         DRV(c, c->cuModuleGetFunction(&p->fn_large, p->mod, "mlgk_solve_large"));
+        {
+            CUdeviceptr ll = 0;
+            size_t ll_bytes = 0;
+            unsigned vals[2] = {0, 0};
+            DRV(c, c->cuModuleGetGlobal(&ll, &ll_bytes, p->mod, "gdb_large_layout"));
+            if (ll_bytes != sizeof vals) return gdb_fail(GDB_ERR_LAYOUT, "gdb_large_layout has %zu bytes", ll_bytes);
+            RT(cudaMemcpy(vals, reinterpret_cast<void *>(ll), sizeof vals, cudaMemcpyDeviceToHost));
+            p->ell_entry = vals[0];
+            p->large_block = vals[1];
+        }
         int v2 = 0;
         c->cuFuncGetAttribute(&v2, CU_FUNC_ATTRIBUTE_NUM_REGS, p->fn_large);
         p->info.num_regs_large = v2;
@@ -533,6 +543,7 @@ struct gdb_graphset_s {
     uint32_t max_ovf[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     uint32_t max_idx[2] = {0, 0};   // two largest (row index + edge elements) byte counts
     uint32_t max_tc = 0, max_degree = 0;  // large-pair kernel: longest neighbour-row list, largest degree
+    uint32_t max_tile_nnz = 0;            // ... and most elements in one tile row (8 rows)
     uint64_t sum_node = 0;
     bool index16 = true;            // every graph carries a valid 16-bit row index
 };
@@ -612,6 +623,10 @@ extern "C" int gdb_graphset_create(gdb_context_t c, const gdb_layout *L, uint32_
         gs->max_tc = std::max(gs->max_tc, h->max_tc);
         gs->max_degree = std::max(gs->max_degree, h->max_degree);
         gs->sum_node += (uint64_t)h->n_node;
+        {
+            const uint32_t *te = reinterpret_cast<const uint32_t *>(dst + h->off_tileelem);
+            for (int32_t t = 0; t < h->n_tile; ++t) gs->max_tile_nnz = std::max(gs->max_tile_nnz, te[t + 1] - te[t]);
+        }
         {
             const uint32_t *rowptr = reinterpret_cast<const uint32_t *>(dst + h->off_rowptr);
             const uint32_t *lanemap = reinterpret_cast<const uint32_t *>(dst + h->off_lanemap);
@@ -748,7 +763,7 @@ struct LaunchCfg {
     CUfunction fn = nullptr;
     int kind = 0;  // 0 general, 1 small, 2 large (cluster)
     uint64_t grid = 0, smem = 0, scratch_stride = 0;
-    uint32_t graphs_need = 0, cluster = 1;
+    uint32_t graphs_need = 0, cluster = 1, row_cap = 0;
     int block = 0;
 };
 
@@ -828,7 +843,10 @@ static int pick_kernel(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, cons
         (uint64_t)gs->max_node[0] <= 32ull * p->lcpt) {
         const uint64_t n2p = ((uint64_t)gs->max_node[0] + 3) & ~3ull;
         const uint64_t D = std::min<uint64_t>(gs->max_degree, (uint64_t)p->lell);
-        const uint64_t ell = ((D * n2p * 2 + 15) & ~15ull) + ((D * n2p * p->edge_size + 15) & ~15ull) + ((n2p * 2 + 15) & ~15ull);
+        const uint64_t ell_entry = p->ell_entry;  // sizeof(gdb_ell_t), read back from the module
+        const uint64_t row_cap = std::min<uint64_t>(gs->max_tile_nnz, 512);
+        const uint64_t ell = ((D * n2p * ell_entry + 15) & ~15ull) + ((n2p * 2 + 15) & ~15ull) +
+                             2 * ((row_cap * ell_entry + 15) & ~15ull);
         const uint64_t buf = (uint64_t)gs->max_tc * n2p * 4;
         const uint64_t lcap = std::min<uint64_t>(cap, (uint64_t)c->prop.sharedMemPerBlockOptin - p->large_static_smem);
         uint64_t need = ell + 2 * buf;
@@ -839,7 +857,7 @@ static int pick_kernel(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, cons
             const int nvecs = p->eval_gradient ? 6 : 5;
             const uint64_t per_cluster = (uint64_t)nvecs * gs->max_node[0] * n2p * 4;
             int ctas_per_sm = 0;
-            DRV(c, c->cuOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, p->fn_large, 256, (size_t)need));
+            DRV(c, c->cuOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, p->fn_large, (int)p->large_block, (size_t)need));
             uint64_t clusters = (uint64_t)c->prop.multiProcessorCount * std::max(1, ctas_per_sm) / p->cluster;
             const double mean_n = (double)gs->sum_node / gs->n;
             const double typical = nvecs * mean_n * mean_n * 4.0 * 1.15;
@@ -851,7 +869,8 @@ static int pick_kernel(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, cons
             if ((rc = dev_reserve(c->scratch, clusters * per_cluster))) return rc;
             k.fn = p->fn_large;
             k.kind = 2;
-            k.block = 256;
+            k.block = (int)p->large_block;
+            k.row_cap = (uint32_t)row_cap;
             k.cluster = (uint32_t)p->cluster;
             k.grid = clusters * p->cluster;
             k.smem = need;
@@ -1044,6 +1063,7 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     f.smem_bytes = (uint32_t)cfg.smem;
     f.row0 = a->row0, f.col0 = a->col0;
     f.blob_slot = cfg.graphs_need;
+    f.pad3 = cfg.row_cap;
     if (a->normalize) {
         f.norm_n = c->norm_n;
         f.norm_diag = reinterpret_cast<uint64_t>(c->norm_diag.ptr);

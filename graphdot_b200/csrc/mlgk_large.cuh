@@ -23,11 +23,13 @@
 //    rows for a banded graph instead of the 24 rows of its 3 octiles -- are
 //    staged in shared memory with cp.async (16-byte LDGSTS, L2 -> smem),
 //    DOUBLE BUFFERED: the rows of tile row t + 1 are in flight while tile row
-//    t is computed.  Warp w of the CTA computes row 8 t + w, lanes own the
-//    columns lane, lane + 32, ...: every gather of p is a conflict-free LDS;
+//    t is computed.  The CTA's 32 warps are (8 rows of the tile row) x (4
+//    groups of columns); a warp's lanes own 32 consecutive columns at a time:
+//    every gather of p is a conflict-free LDS;
 //  * G2 is held per CTA in shared memory in ELL form (slot-major:
-//    ell[t][column]), so that the lanes' loads of (neighbour, edge label) are
-//    conflict-free as well; the elements of row i1 of G1 sit in registers;
+//    ell[t][column] = {neighbour, edge}), so that the lanes' loads are
+//    conflict-free as well; the elements of the tile row of G1 are staged next
+//    to the rows they gather from and read by broadcast loads;
 //    the edge microkernel is evaluated on the fly (nnz1 nnz2 = 2e6 products
 //    per matvec do not fit on chip);
 //  * dot products: warp shuffles -> shared memory -> one DSMEM store per CTA
@@ -48,8 +50,10 @@
 #ifndef GDB_LELL
 #define GDB_LELL 12
 #endif
-#define GDB_LBLOCK 256  // 8 warps = the 8 rows of a tile row
-#define GDB_LU 8        // elements of a row of G1 held in registers at a time
+#ifndef GDB_LBLOCK
+#define GDB_LBLOCK 1024  // 32 warps = (8 rows of a tile row) x (4 groups of columns)
+#endif
+#define GDB_LGROUPS (GDB_LBLOCK / 256)
 
 #if GDB_NODAL == 0  // graph-level outputs only; nodal outputs run in mlgk_solve
 
@@ -146,20 +150,43 @@ __device__ __forceinline__ gdb_large_graph gdb_large_view(const unsigned char *b
     return v;
 }
 
+// One ELL entry of G2 in shared memory: byte offset of the neighbour inside a
+// staged row and the edge -- one 64-bit load for 4-byte edge types.
+struct __align__(8) gdb_ell_t {
+    unsigned off;
+    edge_t e;
+};
+static_assert(sizeof(gdb_ell_t) % 8 == 0, "ELL entries are loaded 8 bytes at a time");
+extern "C" __device__ const unsigned gdb_large_layout[2] = {(unsigned)sizeof(gdb_ell_t), GDB_LBLOCK};
+
+// load an entry through its 32-bit shared-window address (always LDS, no generic-address arithmetic)
+__device__ __forceinline__ gdb_ell_t gdb_lds_ell(unsigned addr) {
+    unsigned w[sizeof(gdb_ell_t) / 4];
+#pragma unroll
+    for (unsigned k = 0; k < sizeof(gdb_ell_t) / 8; ++k)
+        asm("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w[2 * k]), "=r"(w[2 * k + 1]) : "r"(addr + 8u * k));
+    gdb_ell_t out;
+    memcpy(&out, w, sizeof out);
+    return out;
+}
+
 // Everything a CTA needs to sweep its tile rows of the product graph.
 struct gdb_large_ctx {
     gdb_large_graph g1, g2;
     unsigned n2p;                 // row stride of the vectors (floats)
     int t_lo, t_hi;               // this CTA's tile rows of G1
-    unsigned short *ell_col;      // [D2][n2p] neighbour (column of G2) in slot t of column c
-    edge_t *ell_e;                // [D2][n2p] its edge
+    gdb_ell_t *ell;               // [D2][n2p] slot t of column c of G2
     unsigned short *deg2;         // [n2p] stored elements of column c (0 for pad columns)
     int D2;                       // ELL slots in shared memory
     float *stage[2];              // staged rows of the gathered vector
+    gdb_ell_t *rowel[2];          // elements of the tile row of G1 (CSR order): {shared-window address of the
+                                  // staged row the element gathers from, edge}
+    unsigned cap;                 // elements per tile row held in shared memory
     bool dbl;                     // both staging buffers usable
 };
 
-// cp.async the rows of `vec` that tile row t of G1 touches into staging buffer b
+// cp.async the rows of `vec` that tile row t of G1 touches into staging buffer b,
+// and copy the tile row's elements (edge, staged-row address) next to them
 __device__ __forceinline__ void gdb_large_stage(const gdb_large_ctx &C, const float *vec, int t, int b) {
     const unsigned c0 = C.g1.tcptr[t], cnt = C.g1.tcptr[t + 1] - c0;
     const unsigned per_row = C.n2p / 4u;  // 16-byte chunks per row
@@ -171,6 +198,13 @@ __device__ __forceinline__ void gdb_large_stage(const gdb_large_ctx &C, const fl
         const unsigned dst = dst0 + s * C.n2p * 4u;
 #pragma unroll 4
         for (unsigned ch = lane; ch < per_row; ch += 32u) gdb_cp_async16(dst + ch * 16u, src + ch * 4u);
+    }
+    const unsigned k0 = C.g1.rowptr[8 * t], k1 = C.g1.rowptr[min(8 * t + 8, C.g1.n)];
+    for (unsigned k = threadIdx.x; k < min(k1 - k0, C.cap); k += GDB_LBLOCK) {
+        gdb_ell_t el;
+        el.off = dst0 + (unsigned)C.g1.tcslot[k0 + k] * C.n2p * 4u;
+        el.e = C.g1.edge[C.g1.rowadj[k0 + k] >> 16];
+        C.rowel[b][k] = el;
     }
 }
 
@@ -198,10 +232,14 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
             gdb_cp_async_wait<0>();
         }
         __syncthreads();  // staged rows of tile row t visible to every warp
-        const int i1 = 8 * t + (int)warp;
+        const int i1 = 8 * t + (int)(warp & 7u);
         if (i1 < n1) {
+            const unsigned k0 = C.g1.rowptr[8 * t];
             const unsigned k1beg = C.g1.rowptr[i1], deg1 = C.g1.rowptr[i1 + 1] - k1beg;
-            const unsigned stage_sa = gdb_smem_u32(C.stage[b]);
+            // elements of this row that sit in shared memory (the rest, rare, in global memory)
+            const unsigned u_sh = k1beg - k0 >= C.cap ? 0u : min(deg1, C.cap - (k1beg - k0));
+            const unsigned row_sa = gdb_smem_u32(C.rowel[b]) + (k1beg - k0) * (unsigned)sizeof(gdb_ell_t);
+            const unsigned ell_sa = gdb_smem_u32(C.ell), ell_stride = n2p * (unsigned)sizeof(gdb_ell_t);
             constexpr int NACC = MODE == 0 ? 1 : (GDB_NE > 0 ? GDB_NE : 1);
             // acc[] += (edge value | edge Jacobian) of (e1, e2) times the staged vector entry
             auto product = [&](const edge_t &e1, const edge_t &e2, float pj, float (&acc)[NACC]) {
@@ -219,47 +257,40 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
 #endif
                 }
             };
-            // the first GDB_LU elements of row i1 stay in registers for all columns (warp-uniform)
-            edge_t e1r[GDB_LU];
-            unsigned base[GDB_LU];
-            const unsigned nu = min((unsigned)GDB_LU, deg1);
-#pragma unroll
-            for (int u = 0; u < GDB_LU; ++u) {
-                const unsigned k1 = k1beg + min((unsigned)u, nu - 1u);
-                e1r[u] = C.g1.edge[C.g1.rowadj[k1] >> 16];
-                base[u] = stage_sa + (unsigned)C.g1.tcslot[k1] * n2p * 4u;
-            }
+            // warps (row, group q) share out the columns in blocks of 32: rolled loops, the
+            // body must stay in the instruction cache
 #pragma unroll 1
-            for (unsigned c0 = 0; c0 < (unsigned)n2; c0 += 32u) {  // rolled: the body must stay in the instruction cache
+            for (unsigned c0 = 32u * (warp >> 3); c0 < (unsigned)n2; c0 += 32u * GDB_LGROUPS) {
                 const unsigned c = c0 + lane;
                 const bool live = c < (unsigned)n2;
                 const unsigned d2 = live ? C.deg2[c] : 0u;
                 const unsigned d2s = min(d2, (unsigned)C.D2);
+                const unsigned col_sa = ell_sa + c * (unsigned)sizeof(gdb_ell_t);
                 float acc[NACC];
 #pragma unroll
                 for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
-                for (unsigned t2 = 0; t2 < d2s; ++t2) {
-                    const unsigned j2 = C.ell_col[t2 * n2p + c];
-                    const edge_t e2 = C.ell_e[t2 * n2p + c];
-#pragma unroll
-                    for (int u = 0; u < GDB_LU; ++u) {
-                        if ((unsigned)u < nu) {  // warp-uniform
-                            float pj;
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(base[u] + j2 * 4u));
-                            product(e1r[u], e2, pj, acc);
-                        }
+#pragma unroll 1
+                for (unsigned u = 0; u < u_sh; ++u) {  // warp-uniform trip count
+                    const gdb_ell_t el = gdb_lds_ell(row_sa + u * (unsigned)sizeof(gdb_ell_t));  // broadcast load
+                    unsigned at = col_sa;
+#pragma unroll 2
+                    for (unsigned t2 = 0; t2 < d2s; ++t2, at += ell_stride) {
+                        const gdb_ell_t en = gdb_lds_ell(at);
+                        float pj;
+                        asm("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(el.off + en.off));
+                        product(el.e, en.e, pj, acc);
                     }
-                    // rows of G1 with more than GDB_LU elements (rare): the rest from global memory
-                    for (unsigned k1 = k1beg + GDB_LU; k1 < k1beg + deg1; ++k1)
-                        product(C.g1.edge[C.g1.rowadj[k1] >> 16], e2, C.stage[b][(unsigned)C.g1.tcslot[k1] * n2p + j2], acc);
                 }
-                if (d2 > d2s) {  // rare: neighbours beyond the ELL slots, from global memory
-                    const unsigned kb = C.g2.rowptr[c];
-                    for (unsigned t2 = d2s; t2 < d2; ++t2) {
-                        const unsigned a2 = C.g2.rowadj[kb + t2], j2 = a2 & 0xffffu;
-                        const edge_t e2 = C.g2.edge[a2 >> 16];
-                        for (unsigned k1 = k1beg; k1 < k1beg + deg1; ++k1)
-                            product(C.g1.edge[C.g1.rowadj[k1] >> 16], e2, C.stage[b][(unsigned)C.g1.tcslot[k1] * n2p + j2], acc);
+                if (u_sh < deg1 || d2 > d2s) {  // rare: elements beyond the shared-memory copies
+                    const unsigned kb = C.g2.rowptr[live ? c : 0u];
+                    for (unsigned u = 0; u < deg1; ++u) {
+                        const unsigned k1 = k1beg + u;
+                        const edge_t e1 = C.g1.edge[C.g1.rowadj[k1] >> 16];
+                        const float *row = C.stage[b] + (unsigned)C.g1.tcslot[k1] * n2p;
+                        for (unsigned t2 = (u < u_sh ? d2s : 0u); t2 < d2; ++t2) {
+                            const unsigned a2 = C.g2.rowadj[kb + t2];
+                            product(e1, C.g2.edge[a2 >> 16], row[a2 & 0xffffu], acc);
+                        }
                     }
                 }
                 if (live) {  // own element
@@ -382,25 +413,32 @@ extern "C" __global__ void __cluster_dims__(GDB_CLUSTER, 1, 1) __launch_bounds__
 
         // ---- shared memory: ELL copy of G2 | staging buffers ---------------------------
         C.D2 = min(C.g2.max_degree, GDB_LELL);
+        C.cap = F.pad3;
         unsigned off = 0;
-        C.ell_col = reinterpret_cast<unsigned short *>(gdb_smem);
-        off += (((unsigned)C.D2 * n2p * 2u) + 15u) & ~15u;
-        C.ell_e = reinterpret_cast<edge_t *>(gdb_smem + off);
-        off += (((unsigned)C.D2 * n2p * (unsigned)sizeof(edge_t)) + 15u) & ~15u;
+        C.ell = reinterpret_cast<gdb_ell_t *>(gdb_smem);
+        off += (((unsigned)C.D2 * n2p * (unsigned)sizeof(gdb_ell_t)) + 15u) & ~15u;
         C.deg2 = reinterpret_cast<unsigned short *>(gdb_smem + off);
         off += ((n2p * 2u) + 15u) & ~15u;
+#pragma unroll
+        for (int bb = 0; bb < 2; ++bb) {
+            C.rowel[bb] = reinterpret_cast<gdb_ell_t *>(gdb_smem + off);
+            off += ((C.cap * (unsigned)sizeof(gdb_ell_t)) + 15u) & ~15u;
+        }
         const unsigned buf_bytes = (unsigned)C.g1.max_tc * n2p * 4u;
         C.stage[0] = reinterpret_cast<float *>(gdb_smem + off);
         C.dbl = off + 2u * buf_bytes <= F.smem_bytes;
         C.stage[1] = C.dbl ? reinterpret_cast<float *>(gdb_smem + off + buf_bytes) : C.stage[0];
+        if (!C.dbl) C.rowel[1] = C.rowel[0];
         for (unsigned c = threadIdx.x; c < n2p; c += GDB_LBLOCK)
             C.deg2[c] = c < (unsigned)n2 ? (unsigned short)(C.g2.rowptr[c + 1] - C.g2.rowptr[c]) : (unsigned short)0;
         for (unsigned k2 = threadIdx.x; k2 < (unsigned)C.g2.nnz; k2 += GDB_LBLOCK) {
             const unsigned rp = C.g2.rowpos[k2], c = rp & 0xffffu, t2 = rp >> 16;
             if (t2 < (unsigned)C.D2) {
                 const unsigned a2 = C.g2.rowadj[k2];
-                C.ell_col[t2 * n2p + c] = (unsigned short)(a2 & 0xffffu);
-                C.ell_e[t2 * n2p + c] = C.g2.edge[a2 >> 16];
+                gdb_ell_t en;
+                en.off = (a2 & 0xffffu) * 4u;
+                en.e = C.g2.edge[a2 >> 16];
+                C.ell[t2 * n2p + c] = en;
             }
         }
 

@@ -89,7 +89,7 @@ struct gdb_params_fixed {
     const float *norm_diag;
     const float *norm_ddiag;  // [m * norm_n + graph]
     unsigned blob_slot;       // small kernel: bytes of one blob staging buffer (two graphs)
-    unsigned pad3;
+    unsigned pad3;            // large kernel: elements of a tile row held in shared memory
 };
 
 struct gdb_params {
