@@ -252,7 +252,7 @@ struct gdb_program_s {
     CUfunction fn_large = nullptr;  // mlgk_solve_large: one cluster per pair (graph-level outputs)
     int small_regs = 0, small_static_smem = 0, large_static_smem = 0;
     int cluster = 4, lcpt = 16, lell = 12;
-    uint32_t edge_size = 0, ell_entry = 8, large_block = 1024;
+    uint32_t edge_size = 0, ell_entry = 8, large_block = 1024, large_ltr = 1;
     unsigned layout[8] = {};
     std::string source, log;
     gdb_program_info info{};
@@ -481,12 +481,13 @@ extern "C" int gdb_program_create(gdb_context_t c, const gdb_program_desc *d, gd
         {
             CUdeviceptr ll = 0;
             size_t ll_bytes = 0;
-            unsigned vals[2] = {0, 0};
+            unsigned vals[3] = {0, 0, 0};
             DRV(c, c->cuModuleGetGlobal(&ll, &ll_bytes, p->mod, "gdb_large_layout"));
             if (ll_bytes != sizeof vals) return gdb_fail(GDB_ERR_LAYOUT, "gdb_large_layout has %zu bytes", ll_bytes);
             RT(cudaMemcpy(vals, reinterpret_cast<void *>(ll), sizeof vals, cudaMemcpyDeviceToHost));
             p->ell_entry = vals[0];
             p->large_block = vals[1];
+            p->large_ltr = vals[2];
         }
         int v2 = 0;
         c->cuFuncGetAttribute(&v2, CU_FUNC_ATTRIBUTE_NUM_REGS, p->fn_large);
@@ -844,10 +845,10 @@ static int pick_kernel(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, cons
         const uint64_t n2p = ((uint64_t)gs->max_node[0] + 3) & ~3ull;
         const uint64_t D = std::min<uint64_t>(gs->max_degree, (uint64_t)p->lell);
         const uint64_t ell_entry = p->ell_entry;  // sizeof(gdb_ell_t), read back from the module
-        const uint64_t row_cap = std::min<uint64_t>(gs->max_tile_nnz, 512);
+        const uint64_t row_cap = std::min<uint64_t>((uint64_t)gs->max_tile_nnz * p->large_ltr, 1024);
         const uint64_t ell = ((D * n2p * ell_entry + 15) & ~15ull) + ((n2p * 2 + 15) & ~15ull) +
                              2 * ((row_cap * ell_entry + 15) & ~15ull);
-        const uint64_t buf = (uint64_t)gs->max_tc * n2p * 4;
+        const uint64_t buf = (uint64_t)p->large_ltr * gs->max_tc * n2p * 4;
         const uint64_t lcap = std::min<uint64_t>(cap, (uint64_t)c->prop.sharedMemPerBlockOptin - p->large_static_smem);
         uint64_t need = ell + 2 * buf;
         if (need > lcap) need = ell + buf;  // single staging buffer
@@ -861,7 +862,7 @@ static int pick_kernel(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, cons
             uint64_t clusters = (uint64_t)c->prop.multiProcessorCount * std::max(1, ctas_per_sm) / p->cluster;
             const double mean_n = (double)gs->sum_node / gs->n;
             const double typical = nvecs * mean_n * mean_n * 4.0 * 1.15;
-            double budget = 0.75 * (double)c->prop.l2CacheSize;
+            double budget = 0.95 * (double)c->prop.l2CacheSize;
             if (const char *env = getenv("GDB_L2_BUDGET_MB")) budget = atof(env) * 1048576.0;
             clusters = std::max<uint64_t>(1, std::min<uint64_t>(clusters, (uint64_t)(budget / typical)));
             if (const char *env = getenv("GDB_LARGE_CLUSTERS")) clusters = std::max(1, atoi(env));

@@ -53,7 +53,9 @@
 #ifndef GDB_LBLOCK
 #define GDB_LBLOCK 1024  // 32 warps = (8 rows of a tile row) x (4 groups of columns)
 #endif
-#define GDB_LGROUPS (GDB_LBLOCK / 256)
+#ifndef GDB_LTR
+#define GDB_LTR 2        // tile rows of G1 per staging step
+#endif
 
 #if GDB_NODAL == 0  // graph-level outputs only; nodal outputs run in mlgk_solve
 
@@ -157,7 +159,7 @@ struct __align__(8) gdb_ell_t {
     edge_t e;
 };
 static_assert(sizeof(gdb_ell_t) % 8 == 0, "ELL entries are loaded 8 bytes at a time");
-extern "C" __device__ const unsigned gdb_large_layout[2] = {(unsigned)sizeof(gdb_ell_t), GDB_LBLOCK};
+extern "C" __device__ const unsigned gdb_large_layout[3] = {(unsigned)sizeof(gdb_ell_t), GDB_LBLOCK, GDB_LTR};
 
 // load an entry through its 32-bit shared-window address (always LDS, no generic-address arithmetic)
 __device__ __forceinline__ gdb_ell_t gdb_lds_ell(unsigned addr) {
@@ -185,13 +187,14 @@ struct gdb_large_ctx {
     bool dbl;                     // both staging buffers usable
 };
 
-// cp.async the rows of `vec` that tile row t of G1 touches into staging buffer b,
-// and copy the tile row's elements (edge, staged-row address) next to them
-__device__ __forceinline__ void gdb_large_stage(const gdb_large_ctx &C, const float *vec, int t, int b) {
-    const unsigned c0 = C.g1.tcptr[t], cnt = C.g1.tcptr[t + 1] - c0;
+// cp.async the rows of `vec` that the tile rows [t, t_end) of G1 touch into staging
+// buffer b (one list of rows per tile row, back to back), and copy the elements of
+// those tile rows (edge, address of the staged row it gathers from) next to them
+__device__ __forceinline__ void gdb_large_stage(const gdb_large_ctx &C, const float *vec, int t, int t_end, int b) {
     const unsigned per_row = C.n2p / 4u;  // 16-byte chunks per row
     const unsigned dst0 = gdb_smem_u32(C.stage[b]);
     const unsigned lane = threadIdx.x & 31u;
+    const unsigned c0 = C.g1.tcptr[t], cnt = C.g1.tcptr[t_end] - c0;
     // a warp copies whole rows, its lanes consecutive 16-byte chunks (no index division)
     for (unsigned s = threadIdx.x >> 5; s < cnt; s += GDB_LBLOCK / 32) {
         const float *src = vec + (size_t)C.g1.tccol[c0 + s] * C.n2p;
@@ -199,12 +202,54 @@ __device__ __forceinline__ void gdb_large_stage(const gdb_large_ctx &C, const fl
 #pragma unroll 4
         for (unsigned ch = lane; ch < per_row; ch += 32u) gdb_cp_async16(dst + ch * 16u, src + ch * 4u);
     }
-    const unsigned k0 = C.g1.rowptr[8 * t], k1 = C.g1.rowptr[min(8 * t + 8, C.g1.n)];
+    const unsigned k0 = C.g1.rowptr[8 * t], k1 = C.g1.rowptr[min(8 * t_end, C.g1.n)];
     for (unsigned k = threadIdx.x; k < min(k1 - k0, C.cap); k += GDB_LBLOCK) {
+        const unsigned tile = (C.g1.rowpos[k0 + k] & 0xffffu) >> 3;  // tile row of this element
         gdb_ell_t el;
-        el.off = dst0 + (unsigned)C.g1.tcslot[k0 + k] * C.n2p * 4u;
+        el.off = dst0 + (C.g1.tcptr[tile] - c0 + (unsigned)C.g1.tcslot[k0 + k]) * C.n2p * 4u;
         el.e = C.g1.edge[C.g1.rowadj[k0 + k] >> 16];
         C.rowel[b][k] = el;
+    }
+}
+
+// acc[] += (edge value | edge Jacobian) of (e1, e2) times the staged vector entry
+template<int MODE, int NACC> __device__ __forceinline__ void gdb_large_product(const gdb_params &P, const edge_t &e1,
+                                                                               const edge_t &e2, float pj, float (&acc)[NACC]) {
+    if constexpr (MODE == 0) {
+        acc[0] = fmaf(gdb_edge_value(P, e1, e2), pj, acc[0]);
+    } else {
+#if GDB_NE > 0
+        float de[GDB_NE];
+        P.edge_kernel.jacobian(e1.label, e2.label, de);
+#if GDB_WEIGHTED
+        pj *= e1.weight * e2.weight;
+#endif
+#pragma unroll
+        for (int a = 0; a < GDB_NE; ++a) acc[a] = fmaf(de[a], pj, acc[a]);
+#endif
+    }
+}
+
+// The gathers of one lane's column for a row of G1 with exactly K elements: the row's
+// elements sit in REGISTERS (K is a compile-time constant), the only loop left is the one
+// over the column's slots -- about 8 instructions per product (sub, 2 mul, ex2, fma for a
+// square-exponential edge kernel + 2 LDS + 1 add) instead of 17 with a rolled loop over a
+// handful of elements.
+template<int K, int MODE, int NACC> __device__ __forceinline__ void gdb_large_column(const gdb_params &P, unsigned row_sa,
+                                                                                     unsigned col_sa, unsigned ell_stride,
+                                                                                     unsigned d2s, float (&acc)[NACC]) {
+    gdb_ell_t el[K];
+#pragma unroll
+    for (int u = 0; u < K; ++u) el[u] = gdb_lds_ell(row_sa + (unsigned)u * (unsigned)sizeof(gdb_ell_t));  // broadcast loads
+#pragma unroll 1
+    for (unsigned t2 = 0; t2 < d2s; ++t2, col_sa += ell_stride) {
+        const gdb_ell_t en = gdb_lds_ell(col_sa);
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+            float pj;
+            asm("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(el[u].off + en.off));
+            gdb_large_product<MODE, NACC>(P, el[u].e, en.e, pj, acc);
+        }
     }
 }
 
@@ -218,22 +263,29 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int n1 = C.g1.n, n2 = C.g2.n;
     const unsigned n2p = C.n2p;
+    // a step covers GDB_LTR tile rows: fewer barriers, and 8 GDB_LTR rows x column blocks
+    // deal out evenly over the 32 warps
     if (C.t_lo < C.t_hi) {
-        gdb_large_stage(C, vec, C.t_lo, 0);
+        gdb_large_stage(C, vec, C.t_lo, min(C.t_lo + GDB_LTR, C.t_hi), 0);
         gdb_cp_async_commit();
     }
-    for (int t = C.t_lo; t < C.t_hi; ++t) {
-        const int b = C.dbl ? ((t - C.t_lo) & 1) : 0;
-        if (C.dbl && t + 1 < C.t_hi) {
-            gdb_large_stage(C, vec, t + 1, b ^ 1);
+    for (int t = C.t_lo, step = 0; t < C.t_hi; t += GDB_LTR, ++step) {
+        const int b = C.dbl ? (step & 1) : 0;
+        const int t_end = min(t + GDB_LTR, C.t_hi);
+        if (C.dbl && t_end < C.t_hi) {
+            gdb_large_stage(C, vec, t_end, min(t_end + GDB_LTR, C.t_hi), b ^ 1);
             gdb_cp_async_commit();
             gdb_cp_async_wait<1>();
         } else {
             gdb_cp_async_wait<0>();
         }
-        __syncthreads();  // staged rows of tile row t visible to every warp
-        const int i1 = 8 * t + (int)(warp & 7u);
-        if (i1 < n1) {
+        __syncthreads();  // staged rows of this step visible to every warp
+        const unsigned rows_here = (unsigned)(min(8 * t_end, n1) - 8 * t);
+        const unsigned n_items = rows_here * (((unsigned)n2 + 31u) >> 5);
+#pragma unroll 1
+        for (unsigned item = warp; item < n_items; item += GDB_LBLOCK / 32) {
+            const unsigned cb = item / rows_here;
+            const int i1 = 8 * t + (int)(item - cb * rows_here);
             const unsigned k0 = C.g1.rowptr[8 * t];
             const unsigned k1beg = C.g1.rowptr[i1], deg1 = C.g1.rowptr[i1 + 1] - k1beg;
             // elements of this row that sit in shared memory (the rest, rare, in global memory)
@@ -241,52 +293,62 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
             const unsigned row_sa = gdb_smem_u32(C.rowel[b]) + (k1beg - k0) * (unsigned)sizeof(gdb_ell_t);
             const unsigned ell_sa = gdb_smem_u32(C.ell), ell_stride = n2p * (unsigned)sizeof(gdb_ell_t);
             constexpr int NACC = MODE == 0 ? 1 : (GDB_NE > 0 ? GDB_NE : 1);
-            // acc[] += (edge value | edge Jacobian) of (e1, e2) times the staged vector entry
             auto product = [&](const edge_t &e1, const edge_t &e2, float pj, float (&acc)[NACC]) {
-                if constexpr (MODE == 0) {
-                    acc[0] = fmaf(gdb_edge_value(P, e1, e2), pj, acc[0]);
-                } else {
-#if GDB_NE > 0
-                    float de[GDB_NE];
-                    P.edge_kernel.jacobian(e1.label, e2.label, de);
-#if GDB_WEIGHTED
-                    pj *= e1.weight * e2.weight;
-#endif
-#pragma unroll
-                    for (int a = 0; a < GDB_NE; ++a) acc[a] = fmaf(de[a], pj, acc[a]);
-#endif
-                }
+                gdb_large_product<MODE, NACC>(P, e1, e2, pj, acc);
             };
-            // warps (row, group q) share out the columns in blocks of 32: rolled loops, the
-            // body must stay in the instruction cache
-#pragma unroll 1
-            for (unsigned c0 = 32u * (warp >> 3); c0 < (unsigned)n2; c0 += 32u * GDB_LGROUPS) {
-                const unsigned c = c0 + lane;
+            {
+                const unsigned c = 32u * cb + lane;
                 const bool live = c < (unsigned)n2;
+                // own element: issue its global loads NOW so that their latency hides behind the
+                // gather loops below
+                const size_t i_own = (size_t)i1 * n2p + (live ? c : 0u);
+                float own_v = 0.f, own_d = 0.f;
+                if constexpr (MODE == 0) {
+                    own_v = vec[i_own];
+                    own_d = diag[i_own];
+                } else {
+                    own_v = yv[i_own];
+                }
                 const unsigned d2 = live ? C.deg2[c] : 0u;
                 const unsigned d2s = min(d2, (unsigned)C.D2);
                 const unsigned col_sa = ell_sa + c * (unsigned)sizeof(gdb_ell_t);
                 float acc[NACC];
 #pragma unroll
                 for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
-#pragma unroll 1
-                for (unsigned u = 0; u < u_sh; ++u) {  // warp-uniform trip count
-                    const gdb_ell_t el = gdb_lds_ell(row_sa + u * (unsigned)sizeof(gdb_ell_t));  // broadcast load
+                // rows of 1 .. 8 elements (warp-uniform count): fully unrolled over the elements
+                switch (MODE == 0 ? u_sh : 0u) {
+                case 1: gdb_large_column<1, MODE, NACC>(P, row_sa, col_sa, ell_stride, d2s, acc); break;
+                case 2: gdb_large_column<2, MODE, NACC>(P, row_sa, col_sa, ell_stride, d2s, acc); break;
+                case 3: gdb_large_column<3, MODE, NACC>(P, row_sa, col_sa, ell_stride, d2s, acc); break;
+                case 4: gdb_large_column<4, MODE, NACC>(P, row_sa, col_sa, ell_stride, d2s, acc); break;
+                case 5: gdb_large_column<5, MODE, NACC>(P, row_sa, col_sa, ell_stride, d2s, acc); break;
+                case 6: gdb_large_column<6, MODE, NACC>(P, row_sa, col_sa, ell_stride, d2s, acc); break;
+                case 7: gdb_large_column<7, MODE, NACC>(P, row_sa, col_sa, ell_stride, d2s, acc); break;
+                case 8: gdb_large_column<8, MODE, NACC>(P, row_sa, col_sa, ell_stride, d2s, acc); break;
+                default: {
+                    // any other count (and the Jacobian sweep, once per pair): slots outside,
+                    // elements inside (warp-uniform trip count, broadcast loads)
                     unsigned at = col_sa;
-#pragma unroll 2
+#pragma unroll 1
                     for (unsigned t2 = 0; t2 < d2s; ++t2, at += ell_stride) {
                         const gdb_ell_t en = gdb_lds_ell(at);
-                        float pj;
-                        asm("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(el.off + en.off));
-                        product(el.e, en.e, pj, acc);
+                        unsigned ra = row_sa;
+#pragma unroll 2
+                        for (unsigned u = 0; u < u_sh; ++u, ra += (unsigned)sizeof(gdb_ell_t)) {
+                            const gdb_ell_t el = gdb_lds_ell(ra);
+                            float pj;
+                            asm("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(el.off + en.off));
+                            product(el.e, en.e, pj, acc);
+                        }
                     }
+                }
                 }
                 if (u_sh < deg1 || d2 > d2s) {  // rare: elements beyond the shared-memory copies
                     const unsigned kb = C.g2.rowptr[live ? c : 0u];
                     for (unsigned u = 0; u < deg1; ++u) {
                         const unsigned k1 = k1beg + u;
                         const edge_t e1 = C.g1.edge[C.g1.rowadj[k1] >> 16];
-                        const float *row = C.stage[b] + (unsigned)C.g1.tcslot[k1] * n2p;
+                        const float *row = C.stage[b] + (C.g1.tcptr[i1 >> 3] - C.g1.tcptr[t] + (unsigned)C.g1.tcslot[k1]) * n2p;
                         for (unsigned t2 = (u < u_sh ? d2s : 0u); t2 < d2; ++t2) {
                             const unsigned a2 = C.g2.rowadj[kb + t2];
                             product(e1, C.g2.edge[a2 >> 16], row[a2 & 0xffffu], acc);
@@ -294,23 +356,20 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
                     }
                 }
                 if (live) {  // own element
-                    const size_t i = (size_t)i1 * n2p + c;
                     if constexpr (MODE == 0) {
-                        const float v = vec[i];
-                        const float r = fmaf(diag[i], v, -acc[0]);
-                        out[i] = r;
-                        res[0] = fmaf(v, r, res[0]);
+                        const float r = fmaf(own_d, own_v, -acc[0]);
+                        out[i_own] = r;
+                        res[0] = fmaf(own_v, r, res[0]);
                     } else {
-                        const float yi = yv[i];
 #pragma unroll
-                        for (int a = 0; a < NACC; ++a) res[a] = fmaf(yi, acc[a], res[a]);
+                        for (int a = 0; a < NACC; ++a) res[a] = fmaf(own_v, acc[a], res[a]);
                     }
                 }
             }
         }
         __syncthreads();  // every warp is done with buffer b before it is refilled
-        if (!C.dbl && t + 1 < C.t_hi) {
-            gdb_large_stage(C, vec, t + 1, 0);
+        if (!C.dbl && t_end < C.t_hi) {
+            gdb_large_stage(C, vec, t_end, min(t_end + GDB_LTR, C.t_hi), 0);
             gdb_cp_async_commit();
         }
     }
@@ -424,7 +483,7 @@ extern "C" __global__ void __cluster_dims__(GDB_CLUSTER, 1, 1) __launch_bounds__
             C.rowel[bb] = reinterpret_cast<gdb_ell_t *>(gdb_smem + off);
             off += ((C.cap * (unsigned)sizeof(gdb_ell_t)) + 15u) & ~15u;
         }
-        const unsigned buf_bytes = (unsigned)C.g1.max_tc * n2p * 4u;
+        const unsigned buf_bytes = (unsigned)GDB_LTR * (unsigned)C.g1.max_tc * n2p * 4u;
         C.stage[0] = reinterpret_cast<float *>(gdb_smem + off);
         C.dbl = off + 2u * buf_bytes <= F.smem_bytes;
         C.stage[1] = C.dbl ? reinterpret_cast<float *>(gdb_smem + off + buf_bytes) : C.stage[0];

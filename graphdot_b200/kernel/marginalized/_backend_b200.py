@@ -15,6 +15,7 @@ hyper-parameters) and ``.state`` (matching nested tuple); starting
 probabilities offer ``gen_expr()``, ``.dtype`` and ``.state``.
 """
 import ctypes as C
+import os
 import uuid
 
 import numpy as np
@@ -294,7 +295,9 @@ class B200Backend(Backend):
         self.block_size = block_size
         self.slots_per_lane = slots_per_lane   # 2 / 4 / None = by mean degree
         self.cluster_size = cluster_size       # CTAs per large pair; None = 4
-        self.nvrtc_extra = list(nvrtc_extra)
+        # GDB_NVRTC_EXTRA: tuning hook (e.g. '-DGDB_LBLOCK=512 -DGDB_LTR=1')
+        self.nvrtc_extra = (list(nvrtc_extra)
+                            + os.environ.get('GDB_NVRTC_EXTRA', '').split())
         self._context = None
         self._programs = {}
         self._graphsets = []     # small LRU of (key, GraphSet)

@@ -535,8 +535,15 @@ class SquareExponential(_ScalarKernel):
 
     @staticmethod
     def _cxx(x, y, ls):
+        # exp(-d2 / (2 l^2)) = 2^(d2 * c) with c = -log2(e) / (2 l^2): the
+        # parenthesised factor only depends on the hyper-parameter, so the
+        # compiler hoists it out of the solver's loops and one evaluation is
+        # sub, 2 mul, ex2 (the large-pair kernel evaluates the edge kernel
+        # for every product of every matvec; --use_fast_math does not
+        # re-associate the reference's -0.5F*d2/l^2, which costs 4 mul)
         d2 = f'graphdot::ipow<2>({x} - {y})'
-        f = f'expf(-0.5f * {d2} * graphdot::ripow<2>({ls}))'
+        f = (f'exp2f({d2} * (-0.72134752044448170368f * '
+             f'graphdot::ripow<2>({ls})))')
         return f, [f'({f} * {d2} * graphdot::ripow<3>({ls}))']
 
 
