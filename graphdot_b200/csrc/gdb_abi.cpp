@@ -850,20 +850,26 @@ static int pick_kernel(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, cons
                              2 * ((row_cap * ell_entry + 15) & ~15ull);
         const uint64_t buf = (uint64_t)p->large_ltr * gs->max_tc * n2p * 4;
         const uint64_t lcap = std::min<uint64_t>(cap, (uint64_t)c->prop.sharedMemPerBlockOptin - p->large_static_smem);
+        // staging: double buffered unless that costs a resident CTA per SM (two CTAs of
+        // different pairs hide each other's latency better than a second buffer does)
         uint64_t need = ell + 2 * buf;
-        if (need > lcap) need = ell + buf;  // single staging buffer
+        int ctas_dbl = 0, ctas_sgl = 0;
+        if (need <= lcap) DRV(c, c->cuOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_dbl, p->fn_large, (int)p->large_block, (size_t)need));
+        if (ell + buf <= lcap) DRV(c, c->cuOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_sgl, p->fn_large, (int)p->large_block, (size_t)(ell + buf)));
+        if (ctas_sgl > ctas_dbl || getenv("GDB_LARGE_SINGLE")) need = ell + buf;
         if (need <= lcap) {
-            // clusters in flight: what the device can co-schedule, capped so that the
-            // vectors of all of them stay L2-resident
+            // clusters in flight: what the device can co-schedule (an optional cap keeps
+            // the vectors of all of them L2-resident: GDB_L2_BUDGET_MB)
             const int nvecs = p->eval_gradient ? 6 : 5;
             const uint64_t per_cluster = (uint64_t)nvecs * gs->max_node[0] * n2p * 4;
-            int ctas_per_sm = 0;
-            DRV(c, c->cuOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, p->fn_large, (int)p->large_block, (size_t)need));
-            uint64_t clusters = (uint64_t)c->prop.multiProcessorCount * std::max(1, ctas_per_sm) / p->cluster;
+            const int ctas_per_sm = std::max(ctas_sgl > ctas_dbl ? ctas_sgl : ctas_dbl, 1);
+            uint64_t clusters = (uint64_t)c->prop.multiProcessorCount * ctas_per_sm / p->cluster;
             const double mean_n = (double)gs->sum_node / gs->n;
             const double typical = nvecs * mean_n * mean_n * 4.0 * 1.15;
-            double budget = 0.95 * (double)c->prop.l2CacheSize;
+            double budget = typical * 1e6;  // no cap unless asked for
             if (const char *env = getenv("GDB_L2_BUDGET_MB")) budget = atof(env) * 1048576.0;
+            // the arena must fit in a quarter of the device memory
+            clusters = std::min<uint64_t>(clusters, std::max<uint64_t>(1, c->prop.totalGlobalMem / 4 / per_cluster));
             clusters = std::max<uint64_t>(1, std::min<uint64_t>(clusters, (uint64_t)(budget / typical)));
             if (const char *env = getenv("GDB_LARGE_CLUSTERS")) clusters = std::max(1, atoi(env));
             int rc;

@@ -6,12 +6,11 @@
 // (compute_duo), :806-997 (derivative) and the job loop of reference
 // kernel/marginalized/template.cu:29-475 for pairs in this regime.
 //
-// Why a cluster: the CG vectors of one pair are 5 N floats = 0.8 ... 5 MB.
-// With one CTA per pair, 148+ concurrent pairs stream > 1 GB of vectors through
-// HBM in every iteration (round 1: 16 % of the copy bandwidth, latency bound).
-// With GDB_CLUSTER CTAs per pair only SMs / GDB_CLUSTER pairs are in flight,
-// their vectors stay L2-resident, and every vector pass is split over the
-// cluster's CTAs.
+// Why a cluster: the CG vectors of one pair are 5 N floats = 0.8 ... 5 MB and
+// one matvec is 2e6 gathered products; GDB_CLUSTER CTAs split both, which cuts
+// the latency of a pair and the number of arenas in flight.  (Measured, DESIGN.md
+// section 4.3: the kernel is bound by instruction issue and latency, not by
+// HBM or L2 bandwidth -- two resident CTAs per SM matter more than L2 residency.)
 //
 // Per pair (G1 = rows, G2 = columns, element i = i1 n2p + i2 with the row
 // stride n2p = n2 rounded up to 4):
@@ -22,10 +21,11 @@
 //    columns of that tile row (gdb_pack.cpp: tcptr / tccol / tcslot), about 14
 //    rows for a banded graph instead of the 24 rows of its 3 octiles -- are
 //    staged in shared memory with cp.async (16-byte LDGSTS, L2 -> smem),
-//    DOUBLE BUFFERED: the rows of tile row t + 1 are in flight while tile row
-//    t is computed.  The CTA's 32 warps are (8 rows of the tile row) x (4
-//    groups of columns); a warp's lanes own 32 consecutive columns at a time:
-//    every gather of p is a conflict-free LDS;
+//    double buffered when that does not cost a resident CTA.  The CTA's warps
+//    share out (rows of the tile row) x (blocks of 32 columns); a warp's lanes
+//    own 32 consecutive columns at a time: every gather of p is a
+//    conflict-free LDS.  Rows of 1..8 elements run a gather loop specialised
+//    on the element count, with the row's elements in registers;
 //  * G2 is held per CTA in shared memory in ELL form (slot-major:
 //    ell[t][column] = {neighbour, edge}), so that the lanes' loads are
 //    conflict-free as well; the elements of the tile row of G1 are staged next
@@ -51,10 +51,10 @@
 #define GDB_LELL 12
 #endif
 #ifndef GDB_LBLOCK
-#define GDB_LBLOCK 1024  // 32 warps = (8 rows of a tile row) x (4 groups of columns)
+#define GDB_LBLOCK 512  // 16 warps share out the (rows of a staging step) x (blocks of 32 columns)
 #endif
 #ifndef GDB_LTR
-#define GDB_LTR 2        // tile rows of G1 per staging step
+#define GDB_LTR 1        // tile rows of G1 per staging step
 #endif
 
 #if GDB_NODAL == 0  // graph-level outputs only; nodal outputs run in mlgk_solve
@@ -230,28 +230,9 @@ template<int MODE, int NACC> __device__ __forceinline__ void gdb_large_product(c
     }
 }
 
-// The gathers of one lane's column for a row of G1 with exactly K elements: the row's
-// elements sit in REGISTERS (K is a compile-time constant), the only loop left is the one
-// over the column's slots -- about 8 instructions per product (sub, 2 mul, ex2, fma for a
-// square-exponential edge kernel + 2 LDS + 1 add) instead of 17 with a rolled loop over a
-// handful of elements.
-template<int K, int MODE, int NACC> __device__ __forceinline__ void gdb_large_column(const gdb_params &P, unsigned row_sa,
-                                                                                     unsigned col_sa, unsigned ell_stride,
-                                                                                     unsigned d2s, float (&acc)[NACC]) {
-    gdb_ell_t el[K];
-#pragma unroll
-    for (int u = 0; u < K; ++u) el[u] = gdb_lds_ell(row_sa + (unsigned)u * (unsigned)sizeof(gdb_ell_t));  // broadcast loads
-#pragma unroll 1
-    for (unsigned t2 = 0; t2 < d2s; ++t2, col_sa += ell_stride) {
-        const gdb_ell_t en = gdb_lds_ell(col_sa);
-#pragma unroll
-        for (int u = 0; u < K; ++u) {
-            float pj;
-            asm("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(el[u].off + en.off));
-            gdb_large_product<MODE, NACC>(P, el[u].e, en.e, pj, acc);
-        }
-    }
-}
+template<int V> struct gdb_int {
+    static constexpr int value = V;
+};
 
 // One sweep over this CTA's tile rows with `vec` staged.
 //  MODE 0 (matvec):  out[i] = diag[i] vec[i] - sum_j W_ij vec[j]; returns sum vec[i] out[i] in res[0]
@@ -280,91 +261,105 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
             gdb_cp_async_wait<0>();
         }
         __syncthreads();  // staged rows of this step visible to every warp
+        // warps = (rows of this step) x (groups of column blocks): a warp keeps ONE row -- its
+        // elements stay in registers across all of the warp's column blocks
         const unsigned rows_here = (unsigned)(min(8 * t_end, n1) - 8 * t);
-        const unsigned n_items = rows_here * (((unsigned)n2 + 31u) >> 5);
+        const unsigned groups = max(1u, (unsigned)(GDB_LBLOCK / 32) / rows_here);
+        const unsigned ell_sa = gdb_smem_u32(C.ell), ell_stride = n2p * (unsigned)sizeof(gdb_ell_t);
+        const unsigned k0 = C.g1.rowptr[8 * t];
+        constexpr int NACC = MODE == 0 ? 1 : (GDB_NE > 0 ? GDB_NE : 1);
 #pragma unroll 1
-        for (unsigned item = warp; item < n_items; item += GDB_LBLOCK / 32) {
-            const unsigned cb = item / rows_here;
-            const int i1 = 8 * t + (int)(item - cb * rows_here);
-            const unsigned k0 = C.g1.rowptr[8 * t];
+        for (unsigned wi = warp; wi < rows_here * groups; wi += GDB_LBLOCK / 32) {
+            const unsigned q = wi / rows_here;
+            const int i1 = 8 * t + (int)(wi - q * rows_here);
             const unsigned k1beg = C.g1.rowptr[i1], deg1 = C.g1.rowptr[i1 + 1] - k1beg;
             // elements of this row that sit in shared memory (the rest, rare, in global memory)
             const unsigned u_sh = k1beg - k0 >= C.cap ? 0u : min(deg1, C.cap - (k1beg - k0));
             const unsigned row_sa = gdb_smem_u32(C.rowel[b]) + (k1beg - k0) * (unsigned)sizeof(gdb_ell_t);
-            const unsigned ell_sa = gdb_smem_u32(C.ell), ell_stride = n2p * (unsigned)sizeof(gdb_ell_t);
-            constexpr int NACC = MODE == 0 ? 1 : (GDB_NE > 0 ? GDB_NE : 1);
-            auto product = [&](const edge_t &e1, const edge_t &e2, float pj, float (&acc)[NACC]) {
-                gdb_large_product<MODE, NACC>(P, e1, e2, pj, acc);
-            };
-            {
-                const unsigned c = 32u * cb + lane;
-                const bool live = c < (unsigned)n2;
-                // own element: issue its global loads NOW so that their latency hides behind the
-                // gather loops below
-                const size_t i_own = (size_t)i1 * n2p + (live ? c : 0u);
-                float own_v = 0.f, own_d = 0.f;
-                if constexpr (MODE == 0) {
-                    own_v = vec[i_own];
-                    own_d = diag[i_own];
-                } else {
-                    own_v = yv[i_own];
-                }
-                const unsigned d2 = live ? C.deg2[c] : 0u;
-                const unsigned d2s = min(d2, (unsigned)C.D2);
-                const unsigned col_sa = ell_sa + c * (unsigned)sizeof(gdb_ell_t);
-                float acc[NACC];
+            // K > 0: the row has exactly K elements, held in registers and fully unrolled
+            // (about 8 instructions per product: sub, 2 mul, ex2, fma for a square-exponential
+            // edge kernel + 2 LDS + 1 add, instead of 17 with a rolled loop over a handful of
+            // elements); K = 0: any other count (and the Jacobian sweep, once per pair)
+            auto row_pass = [&](auto kc) {
+                constexpr int K = decltype(kc)::value;
+                gdb_ell_t el[K > 0 ? K : 1];
 #pragma unroll
-                for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
-                // rows of 1 .. 8 elements (warp-uniform count): fully unrolled over the elements
-                switch (MODE == 0 ? u_sh : 0u) {
-                case 1: gdb_large_column<1, MODE, NACC>(P, row_sa, col_sa, ell_stride, d2s, acc); break;
-                case 2: gdb_large_column<2, MODE, NACC>(P, row_sa, col_sa, ell_stride, d2s, acc); break;
-                case 3: gdb_large_column<3, MODE, NACC>(P, row_sa, col_sa, ell_stride, d2s, acc); break;
-                case 4: gdb_large_column<4, MODE, NACC>(P, row_sa, col_sa, ell_stride, d2s, acc); break;
-                case 5: gdb_large_column<5, MODE, NACC>(P, row_sa, col_sa, ell_stride, d2s, acc); break;
-                case 6: gdb_large_column<6, MODE, NACC>(P, row_sa, col_sa, ell_stride, d2s, acc); break;
-                case 7: gdb_large_column<7, MODE, NACC>(P, row_sa, col_sa, ell_stride, d2s, acc); break;
-                case 8: gdb_large_column<8, MODE, NACC>(P, row_sa, col_sa, ell_stride, d2s, acc); break;
-                default: {
-                    // any other count (and the Jacobian sweep, once per pair): slots outside,
-                    // elements inside (warp-uniform trip count, broadcast loads)
-                    unsigned at = col_sa;
+                for (int u = 0; u < K; ++u) el[u] = gdb_lds_ell(row_sa + (unsigned)u * (unsigned)sizeof(gdb_ell_t));  // broadcast loads
 #pragma unroll 1
-                    for (unsigned t2 = 0; t2 < d2s; ++t2, at += ell_stride) {
-                        const gdb_ell_t en = gdb_lds_ell(at);
-                        unsigned ra = row_sa;
-#pragma unroll 2
-                        for (unsigned u = 0; u < u_sh; ++u, ra += (unsigned)sizeof(gdb_ell_t)) {
-                            const gdb_ell_t el = gdb_lds_ell(ra);
-                            float pj;
-                            asm("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(el.off + en.off));
-                            product(el.e, en.e, pj, acc);
-                        }
-                    }
-                }
-                }
-                if (u_sh < deg1 || d2 > d2s) {  // rare: elements beyond the shared-memory copies
-                    const unsigned kb = C.g2.rowptr[live ? c : 0u];
-                    for (unsigned u = 0; u < deg1; ++u) {
-                        const unsigned k1 = k1beg + u;
-                        const edge_t e1 = C.g1.edge[C.g1.rowadj[k1] >> 16];
-                        const float *row = C.stage[b] + (C.g1.tcptr[i1 >> 3] - C.g1.tcptr[t] + (unsigned)C.g1.tcslot[k1]) * n2p;
-                        for (unsigned t2 = (u < u_sh ? d2s : 0u); t2 < d2; ++t2) {
-                            const unsigned a2 = C.g2.rowadj[kb + t2];
-                            product(e1, C.g2.edge[a2 >> 16], row[a2 & 0xffffu], acc);
-                        }
-                    }
-                }
-                if (live) {  // own element
+                for (unsigned c0 = 32u * q; c0 < (unsigned)n2; c0 += 32u * groups) {
+                    const unsigned c = c0 + lane;
+                    const bool live = c < (unsigned)n2;
+                    // own element: its global loads are issued before the gather loop, which
+                    // hides their latency
+                    const size_t i_own = (size_t)i1 * n2p + (live ? c : 0u);
+                    float own_v, own_d = 0.f;
                     if constexpr (MODE == 0) {
-                        const float r = fmaf(own_d, own_v, -acc[0]);
-                        out[i_own] = r;
-                        res[0] = fmaf(own_v, r, res[0]);
+                        own_v = vec[i_own];
+                        own_d = diag[i_own];
                     } else {
+                        own_v = yv[i_own];
+                    }
+                    const unsigned d2 = live ? C.deg2[c] : 0u;
+                    const unsigned d2s = min(d2, (unsigned)C.D2);
+                    unsigned at = ell_sa + c * (unsigned)sizeof(gdb_ell_t);
+                    float acc[NACC];
 #pragma unroll
-                        for (int a = 0; a < NACC; ++a) res[a] = fmaf(own_v, acc[a], res[a]);
+                    for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
+#pragma unroll 1
+                    for (unsigned t2 = 0; t2 < d2s; ++t2, at += ell_stride) {  // slots of this lane's column
+                        const gdb_ell_t en = gdb_lds_ell(at);
+                        if constexpr (K > 0) {
+#pragma unroll
+                            for (int u = 0; u < K; ++u) {
+                                float pj;
+                                asm("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(el[u].off + en.off));
+                                gdb_large_product<MODE, NACC>(P, el[u].e, en.e, pj, acc);
+                            }
+                        } else {
+                            unsigned ra = row_sa;
+#pragma unroll 2
+                            for (unsigned u = 0; u < u_sh; ++u, ra += (unsigned)sizeof(gdb_ell_t)) {  // warp-uniform
+                                const gdb_ell_t e1 = gdb_lds_ell(ra);
+                                float pj;
+                                asm("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(e1.off + en.off));
+                                gdb_large_product<MODE, NACC>(P, e1.e, en.e, pj, acc);
+                            }
+                        }
+                    }
+                    if (u_sh < deg1 || d2 > d2s) {  // rare: elements beyond the shared-memory copies
+                        const unsigned kb = C.g2.rowptr[live ? c : 0u];
+                        for (unsigned u = 0; u < deg1; ++u) {
+                            const unsigned k1 = k1beg + u;
+                            const edge_t e1 = C.g1.edge[C.g1.rowadj[k1] >> 16];
+                            const float *row = C.stage[b] + (C.g1.tcptr[i1 >> 3] - C.g1.tcptr[t] + (unsigned)C.g1.tcslot[k1]) * n2p;
+                            for (unsigned t2 = (u < u_sh ? d2s : 0u); t2 < d2; ++t2) {
+                                const unsigned a2 = C.g2.rowadj[kb + t2];
+                                gdb_large_product<MODE, NACC>(P, e1, C.g2.edge[a2 >> 16], row[a2 & 0xffffu], acc);
+                            }
+                        }
+                    }
+                    if (live) {  // own element
+                        if constexpr (MODE == 0) {
+                            const float r = fmaf(own_d, own_v, -acc[0]);
+                            out[i_own] = r;
+                            res[0] = fmaf(own_v, r, res[0]);
+                        } else {
+#pragma unroll
+                            for (int a = 0; a < NACC; ++a) res[a] = fmaf(own_v, acc[a], res[a]);
+                        }
                     }
                 }
+            };
+            switch (MODE == 0 && u_sh == deg1 ? u_sh : 0u) {
+            case 1: row_pass(gdb_int<1>{}); break;
+            case 2: row_pass(gdb_int<2>{}); break;
+            case 3: row_pass(gdb_int<3>{}); break;
+            case 4: row_pass(gdb_int<4>{}); break;
+            case 5: row_pass(gdb_int<5>{}); break;
+            case 6: row_pass(gdb_int<6>{}); break;
+            case 7: row_pass(gdb_int<7>{}); break;
+            case 8: row_pass(gdb_int<8>{}); break;
+            default: row_pass(gdb_int<0>{}); break;
             }
         }
         __syncthreads();  // every warp is done with buffer b before it is refilled
@@ -428,7 +423,11 @@ __device__ __forceinline__ int gdb_large_pcg(const gdb_params &P, const gdb_larg
     return k;
 }
 
-extern "C" __global__ void __cluster_dims__(GDB_CLUSTER, 1, 1) __launch_bounds__(GDB_LBLOCK, 1)
+#ifndef GDB_LMINB
+#define GDB_LMINB 2  // resident CTAs per SM asked of ptxas: two CTAs (of different pairs) per SM overlap
+                     // each other's latency-bound phases (vector passes, barriers) with gather loops
+#endif
+extern "C" __global__ void __cluster_dims__(GDB_CLUSTER, 1, 1) __launch_bounds__(GDB_LBLOCK, GDB_LMINB)
     mlgk_solve_large(const __grid_constant__ gdb_params P) {
     extern __shared__ __align__(16) unsigned char gdb_smem[];
     __shared__ gdb_large_shared S;

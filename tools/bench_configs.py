@@ -41,6 +41,10 @@ def main():
     ap.add_argument('--c5-graphs', type=int, default=4000)
     ap.add_argument('--only', default='')
     ap.add_argument('--c4-grad', action='store_true')
+    ap.add_argument('--c4-order', default='natural',
+                    choices=['natural', 'rcm', 'random'],
+                    help='node order of the C4 graphs (sensitivity of the '
+                         'large-pair kernel to the tile structure)')
     args = ap.parse_args()
     be = B200Backend()
     rows = []
@@ -78,6 +82,15 @@ def main():
         record('C3', len(G) * (len(G) + 1) // 2, t)
     if not only or 'C4' in only:
         G = make_config_graphs('C4', args.c4_graphs)
+        if args.c4_order != 'natural':
+            from graphdot_b200.reorder import octile_count, rcm
+            rng = np.random.default_rng(0)
+            before = sum(octile_count(g) for g in G)
+            G = [g.permute(rcm(g) if args.c4_order == 'rcm'
+                           else rng.permutation(len(g.nodes))) for g in G]
+            print(json.dumps(dict(order=args.c4_order, octiles_before=before,
+                                  octiles_after=sum(octile_count(g)
+                                                    for g in G))), flush=True)
         k = make_config_kernel('C4', backend=be)
         if args.c4_grad:
             (K, dK), t = timed(lambda: k(G, eval_gradient=True), repeat=1)
@@ -93,6 +106,7 @@ def main():
         gbps = model_bytes / (be.last['kernel_ms'] * 1e-3) / 1e9
         record('C4' + ('+grad' if args.c4_grad else ''),
                len(G) * (len(G) + 1) // 2, t, n_graphs=len(G),
+               order=args.c4_order,
                mean_N=float(np.mean(np.outer(n, n))),
                model_GBps=gbps, hbm_peak_GBps=6551.0,
                hbm_frac=gbps / 6551.0,
