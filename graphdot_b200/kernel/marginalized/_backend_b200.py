@@ -410,12 +410,34 @@ class B200Backend(Backend):
         G = [graphs[k] for k in todo]
         n = len(G)
 
-        def cat(frames, key, counts):
+        try:
+            from ... import _fastcols
+        except ImportError:          # helper not built: plain numpy
+            _fastcols = None
+        own = type(G[0].nodes) is DataFrame
+        nodes = [g.nodes._data if own and type(g.nodes) is DataFrame
+                 else g.nodes for g in G]
+        edges = [g.edges._data if own and type(g.edges) is DataFrame
+                 else g.edges for g in G]
+
+        def count(tables):
+            cnt = np.empty(n, np.int64)
+            if _fastcols is not None:
+                _fastcols.lengths(tables, '!i', cnt)
+            else:
+                cnt[:] = [len(t['!i']) for t in tables]
+            return cnt
+
+        def cat(tables, key, counts, dtype=None):
+            """Concatenation of column ``key`` of all tables."""
             try:
-                if all(type(f) is DataFrame for f in frames[:1]):
-                    a = np.concatenate([f._data[key] for f in frames])
-                else:
-                    a = np.concatenate([f[key] for f in frames])
+                if dtype is None:
+                    dtype = np.asarray(tables[0][key]).dtype
+                if _fastcols is not None and dtype.kind != 'O':
+                    a = np.empty(int(counts.sum()), dtype=dtype)
+                    _fastcols.gather(tables, key, a, counts, dtype.itemsize)
+                    return a
+                a = np.concatenate([t[key] for t in tables])
             except KeyError:
                 raise TypeError(f'attribute {key!r} missing in a graph: all '
                                 'nodes/edges must be of the same type')
@@ -423,10 +445,7 @@ class B200Backend(Backend):
                 raise TypeError(f'attribute {key!r}: column length mismatch')
             return a
 
-        nodes = [g.nodes for g in G]
-        edges = [g.edges for g in G]
-        ncnt = np.fromiter((len(f['!i']) for f in nodes), np.int64, n)
-        ecnt = np.fromiter((len(f['!i']) for f in edges), np.int64, n)
+        ncnt, ecnt = count(nodes), count(edges)
         if not ncnt.all():
             raise ValueError('graph without nodes')
         noff = np.zeros(n + 1, np.uint64)
