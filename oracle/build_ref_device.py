@@ -97,6 +97,9 @@ def build(name, config, n_graphs, traits_kw):
         kedge = mk.TensorProduct(length=mk.SquareExponential(0.1))
     elif config == 'C1':
         knode, kedge = mk.Constant(1.0), mk.Constant(1.0)
+    elif config == 'C4':
+        knode = mk.TensorProduct(feat=mk.Convolution(mk.SquareExponential(1.0)))
+        kedge = mk.TensorProduct(length=mk.SquareExponential(0.2))
     else:
         raise KeyError(config)
     p = Uniform(1.0)
@@ -137,11 +140,32 @@ def build(name, config, n_graphs, traits_kw):
     # ---- graphs in the reference's device layout (pointers -> offsets) -----
     node_off, oct_off, edge_off = [0], [0], [0]
     degree, nodes, edges = [], [], []
+    # variable-length node features (reference _octilegraph.py:45-88): node_t
+    # holds frozen_array{ptr, size}; the host pointers of the build container
+    # become offsets into one saved feature pool that the launcher relocates
+    ptr_fields = [(k, node_t.fields[k][1]) for k in node_t.names
+                  if node_t.fields[k][0].names == ('ptr', 'size')]
+    pool, pool_at = [], 0
     octs = {k: [] for k in ('elements', 'nzmask', 'nzmask_r', 'upper', 'left')}
     for og in ogs:
         assert og.node_t == node_t and og.edge_t == edge_t
         degree.append(np.asarray(og.degree))
-        nodes.append(np.asarray(og.nodes_aos).view(np.uint8).reshape(-1))
+        aos = np.array(og.nodes_aos)            # private copy
+        for key, _ in ptr_fields:
+            ptrs = aos[key]['ptr'].astype(np.int64)
+            sizes = aos[key]['size'].astype(np.int64)
+            inner = np.dtype(key.rsplit('::', 1)[1])
+            base = int(ptrs.min())
+            nbytes = int((ptrs - base).max()
+                         + sizes[np.argmax(ptrs)] * inner.itemsize)
+            raw = np.frombuffer(ctypes.string_at(base, nbytes), np.uint8)
+            pad = (-pool_at) % 16
+            pool.append(np.zeros(pad, np.uint8))
+            pool_at += pad
+            aos[key]['ptr'] = ptrs - base + pool_at
+            pool.append(raw)
+            pool_at += nbytes
+        nodes.append(aos.view(np.uint8).reshape(-1))
         edges.append(np.asarray(og.edges_aos).view(np.uint8).reshape(-1))
         base = int(og.edges_aos.base)
         o = og.octiles
@@ -156,6 +180,7 @@ def build(name, config, n_graphs, traits_kw):
              node_off=np.array(node_off), oct_off=np.array(oct_off),
              degree=np.concatenate(degree), nodes=np.concatenate(nodes),
              edges=np.concatenate(edges),
+             pool=(np.concatenate(pool) if pool else np.zeros(0, np.uint8)),
              **{'oct_' + k: np.concatenate(v) for k, v in octs.items()})
 
     def state(obj):
@@ -166,6 +191,8 @@ def build(name, config, n_graphs, traits_kw):
         name=name, config=config, n_graphs=n_graphs, traits=traits_kw,
         weighted=bool(weighted), node_size=node_t.itemsize,
         edge_size=edge_t.itemsize,
+        node_ptr_offsets=[int(off + node_t.fields[k][0].fields['ptr'][1])
+                          for k, off in ptr_fields],
         n_jac=len(p.theta) + 1 + sum(1 for _ in _flat(knode.theta))
         + sum(1 for _ in _flat(kedge.theta)),
         theta={'node_kernel': state(knode), 'edge_kernel': state(kedge_dev),
@@ -192,6 +219,8 @@ def main():
     build('c2_gram', 'C2', n, dict(symmetric=True))
     build('c3_grad', 'C2', n, dict(symmetric=True, eval_gradient=True))
     build('c1_gram', 'C1', 100, dict(symmetric=True))
+    build('c4_gram', 'C4', int(os.environ.get('GDB_REF_C4_GRAPHS', 60)),
+          dict(symmetric=True))
 
 
 if __name__ == '__main__':

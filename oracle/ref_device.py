@@ -93,7 +93,16 @@ class RefDeviceSolver:
         self.n_graphs = len(node_off) - 1
         self.sizes = np.diff(node_off)
         self.d_degree = self._dev(z['degree'].astype(np.float32))
-        self.d_nodes = self._dev(z['nodes'])
+        nodes = np.array(z['nodes'])
+        if m.get('node_ptr_offsets'):
+            # frozen_array data pointers: pool-relative offsets -> device addresses
+            self.d_pool = self._dev(z['pool'])
+            rows = nodes.reshape(-1, m['node_size'])
+            for off in m['node_ptr_offsets']:
+                ptr = rows[:, off:off + 8].copy().view(np.uint64)
+                ptr += np.uint64(self.d_pool.data_ptr())
+                rows[:, off:off + 8] = ptr.view(np.uint8)
+        self.d_nodes = self._dev(nodes)
         self.d_edges = self._dev(z['edges'])
         # octile_t {edge_t* elements; u64 nzmask; u64 nzmask_r; int upper, left}
         oct_dt = np.dtype([('elements', '<u8'), ('nzmask', '<u8'),

@@ -58,3 +58,20 @@ def test_unlabeled_closed_form_reference_device_code():
     kernel = make_config_kernel('C1', backend=B200Backend())
     K = kernel(make_config_graphs('C1', n))
     assert np.allclose(K, Kr, rtol=1e-5)
+
+
+def test_c4_large_pairs_match_reference_device_code():
+    """BASELINE config C4 (200-500 nodes, Convolution over variable-length
+    node features): the cluster kernel against the reference's own device
+    code on the same graphs."""
+    _need('c4_gram')
+    n = 6
+    ref = ref_device.RefDeviceSolver('c4_gram')
+    assert ref.sizes[:n].min() >= 200
+    Kr, _, ms = ref.solve(ref_device.triu_jobs(n), q=0.05, n=n)
+    be = B200Backend()
+    kernel = make_config_kernel('C4', backend=be)
+    K = kernel(make_config_graphs('C4', n))
+    assert be.last['kernel'] == 'mlgk_solve_large'
+    assert np.allclose(K, Kr, rtol=1e-5), np.abs(K / Kr - 1).max()
+    assert np.count_nonzero(K - K.T) == 0

@@ -112,6 +112,24 @@ def main():
                hbm_frac=gbps / 6551.0,
                products_per_s=be.last['matvec_products']
                / (be.last['kernel_ms'] * 1e-3))
+    if only and 'C4ref' in only:
+        # the reference's own device code on the same C4 graphs (oracle/_ref/c4_gram)
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from oracle import ref_device
+        ref = ref_device.RefDeviceSolver('c4_gram')
+        n = min(args.c4_graphs, ref.n_graphs)
+        jobs = ref_device.triu_jobs(n)
+        ref.solve(ref_device.triu_jobs(4), 0.05, n=n)
+        Kr, _, ms = ref.solve(jobs, 0.05, n=n)
+        G = make_config_graphs('C4', n)
+        K = make_config_kernel('C4', backend=be)(G)
+        row = dict(config='C4 reference device code', pairs=len(jobs),
+                   kernel_ms=ms, pairs_per_s=len(jobs) / (ms * 1e-3),
+                   ours_kernel_ms=be.last['kernel_ms'],
+                   ours_pairs_per_s=len(jobs) / (be.last['kernel_ms'] * 1e-3),
+                   max_rel_diff=float(np.abs(K / Kr - 1).max()), n_graphs=n)
+        rows.append(row)
+        print(json.dumps(row), flush=True)
     if not only or 'C5' in only:
         G = make_config_graphs('C5', args.c5_graphs)
         h = len(G) // 2
