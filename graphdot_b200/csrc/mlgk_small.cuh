@@ -35,6 +35,11 @@
 //    load feed two FMAs.  Each system has its own CG scalars and convergence
 //    flag (the reference shares alpha/beta between the stacked systems,
 //    marginalized_kernel.h:721-772).
+//  * measured and rejected in round 2: a software-
+//    pipelined element loop (+0.4 %, within noise) and the symmetrically scaled
+//    unit-diagonal system (-2.6 %: the scaling of W and the extra shared-memory
+//    vector cost more than the divisions they save, and diag^-1/2 does not exist
+//    for the negative degrees that the reference's tests allow);
 //  * three barriers per CG iteration (two reductions + publish p); the K dot
 //    products of a reduction share one shuffle butterfly and are joined through
 //    a double-buffered shared-memory slot.
@@ -65,9 +70,6 @@
 #endif
 #define GDB_PRAGMA_(x) _Pragma(#x)
 #define GDB_UNROLL(n) GDB_PRAGMA_(unroll n)
-#ifndef GDB_K1_PIPELINE
-#define GDB_K1_PIPELINE 0  // 1: software-pipelined element loop (experimental, unmeasured)
-#endif
 #ifndef GDB_ROLL_ROWS
 #define GDB_ROLL_ROWS 0  // 1: matvec rolled over the rows, W p handed over through shared memory
 #endif
@@ -658,44 +660,6 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll
                 for (int s = 0; s < GDB_WPT; ++s) acc[s] = gv_make(0.f, 0.f);
                 const uint2 row = gdb_lds_u2(w_rtsa + (unsigned)(i1 - w_row0) * 8u);  // steps of this row
-#if GDB_K1_PIPELINE
-                // EXPERIMENTAL (not measured yet): software pipeline --
-                // the step-table entry of step k + 1 is loaded before the gathers of step k,
-                // so that only one of the two dependent shared-memory latencies is exposed
-                if (row.x != row.y) {
-                    uint2 step = gdb_lds_u2(row.x);
-                    unsigned ka = row.x + 8u;
-#pragma unroll 1
-                    while (true) {
-                        const bool more = ka != row.y;
-                        const uint2 next = gdb_lds_u2(more ? ka : row.x);  // always a valid entry
-#pragma unroll
-                        for (int s = 0; s < GDB_WPT; ++s) {
-#if GDB_ADJ == 2
-                            const float2 w2 = gdb_lds_f2(step.x + w_woff[s]);
-                            const gv_t p0 = gdb_lds_gv(step.y + w_xoff[s][0]);
-                            const gv_t p1 = gdb_lds_gv(step.y + w_xoff[s][1]);
-                            acc[s] = gv_fma(w2.x, p0, acc[s]);
-                            acc[s] = gv_fma(w2.y, p1, acc[s]);
-#else
-                            const float4 w4 = gdb_lds_f4(step.x + w_woff[s]);
-                            const gv_t p0 = gdb_lds_gv(step.y + w_xoff[s][0]);
-                            const gv_t p1 = gdb_lds_gv(step.y + w_xoff[s][1]);
-                            const gv_t p2 = gdb_lds_gv(step.y + w_xoff[s][2]);
-                            const gv_t p3 = gdb_lds_gv(step.y + w_xoff[s][3]);
-                            acc[s] = gv_fma(w4.x, p0, acc[s]);
-                            acc[s] = gv_fma(w4.y, p1, acc[s]);
-                            acc[s] = gv_fma(w4.z, p2, acc[s]);
-                            acc[s] = gv_fma(w4.w, p3, acc[s]);
-#endif
-                        }
-                        if (!more) break;
-                        step = next;
-                        ka += 8u;
-                    }
-                }
-                if (false)
-#endif
                 GDB_UNROLL(GDB_K1_UNROLL)  // the body is replicated per row already: keep the code in the instruction cache
                 for (unsigned ka = row.x; ka != row.y; ka += 8u) {  // warp-uniform trip count
                     const uint2 step = gdb_lds_u2(ka);  // (W row, p row)
