@@ -464,14 +464,22 @@ def run_gpu(args, rank, world, local_rank):
                                                 for p in packed)
             buf = (np.asarray(base) if same_buf
                    else np.concatenate([p.blob for p in packed]))
-            payload = [(buf.tobytes(), cuts, [p.n_node for p in packed],
+            payload = [(len(buf), cuts, [p.n_node for p in packed],
                         packed[0].key, B200Backend._layouts(G[0]))]
         if world > 1:
+            # the packed set travels once over NVLink: metadata as a small
+            # object, the blobs as one byte tensor (NCCL broadcast)
             t0 = time.perf_counter()
             dist.broadcast_object_list(payload, src=0)
+            nbytes = payload[0][0]
+            blob_t = (torch.from_numpy(buf).cuda() if rank == 0 else
+                      torch.empty(nbytes, dtype=torch.uint8, device='cuda'))
+            dist.broadcast(blob_t, src=0)
+            if rank != 0:
+                buf = blob_t.cpu().numpy()
+            del blob_t
             first_call['broadcast_ms'] = (time.perf_counter() - t0) * 1e3
-        raw, cuts, n_nodes, key, layouts = payload[0]
-        buf = np.frombuffer(raw, dtype=np.uint8)
+        _, cuts, n_nodes, key, layouts = payload[0]
         packed = [PackedGraph(buf[a:b], nn, key)
                   for a, b, nn in zip(cuts[:-1], cuts[1:], n_nodes)]
         t0 = time.perf_counter()

@@ -627,7 +627,7 @@ class B200Backend(Backend):
     def __call__(self, graphs, node_kernel, edge_kernel, p, q, eps, ftol,
                  gtol, jobs, starts, gramian, gradient, nX, nY, nJ, traits,
                  timer, stream=None, keep_on_device=False, store_diag=False,
-                 normalize=False, **launch_options):
+                 normalize=False, resend=True, **launch_options):
         """The reference's 17-argument back-end call (reference
         _backend_cuda.py:247-248).  Keyword extras (all optional, this
         package's front end uses them): ``collect=Collect(...)`` fuses the
@@ -647,7 +647,8 @@ class B200Backend(Backend):
                         gtol, jobs, starts, gramian, gradient, nX, nY, nJ,
                         stream=stream, keep_on_device=keep_on_device,
                         store_diag=store_diag, normalize=normalize,
-                        upload=self.resend_graphs, **launch_options)
+                        upload=self.resend_graphs and resend,
+                        **launch_options)
         timer.toc('GPU kernel execution')
         return a
 

@@ -250,6 +250,7 @@ class MarginalizedGraphKernel:
                     timer, store_diag=True, keep_on_device=True,
                     stream=extra.get('stream'))
             extra['normalize'] = True   # ... and scale the main solve
+            extra['resend'] = False     # the graphs were (re-)sent just now
         backend(graphs, self.node_kernel, self.edge_kernel, self.p, self.q,
                 self.eps, self.ftol, self.gtol, jobs, starts, gramian,
                 gradient, rows, cols, self.n_dims, traits, timer, **extra)

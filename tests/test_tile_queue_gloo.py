@@ -73,3 +73,51 @@ def test_tiles_cover_the_upper_triangle_exactly_once():
         total += len(jobs)
     assert total == n * (n + 1) // 2
     assert np.array_equal(seen, np.triu(np.ones((n, n), dtype=int)))
+
+
+def _rank_shared(rank, world, port, nx, ny, cols, path, out_dir):
+    """The C5 arrangement of bench.py on CPU: rank 0 'packs' and broadcasts a
+    payload, both ranks pull COLUMN tiles of the X-by-Y rectangle from the
+    store counter and write them straight into ONE shared host matrix (a
+    memory-mapped file); rank 0 then holds the assembled result."""
+    from graphdot_b200.kernel.marginalized._tiles import col_tiles
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port),
+                      RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    store = dist.distributed_c10d._get_default_store()
+    payload = [dict(blob=b'x' * 1000, cuts=list(range(5)))
+               if rank == 0 else None]
+    dist.broadcast_object_list(payload, src=0)
+    assert payload[0]['cuts'] == list(range(5))
+    if rank == 0:
+        with open(path, 'wb') as f:
+            f.truncate(nx * ny * 4)
+    dist.barrier()
+    K = np.memmap(path, dtype=np.float32, mode='r+').reshape((nx, ny),
+                                                              order='F')
+    done = 0
+    for j0, j1 in StoreTileQueue(store, col_tiles(ny, cols), 'c5'):
+        jobs = np.asarray(PairJobs.rect(0, nx, nx + j0, nx + j1))
+        assert len(jobs) == nx * (j1 - j0)
+        # stand-in for the solve: entry (i, j) = 1000 i + j
+        K[jobs['i'], jobs['j'] - nx] = 1000.0 * jobs['i'] + (jobs['j'] - nx)
+        done += len(jobs)
+    K.flush()
+    total = torch.tensor([float(done)], dtype=torch.float64)
+    dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    dist.barrier()
+    if rank == 0:
+        np.save(os.path.join(out_dir, 'total.npy'), np.array([total.item()]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_column_tiles_fill_one_shared_host_matrix(tmp_path):
+    nx, ny, cols, world = 19, 23, 4, 2
+    path = str(tmp_path / 'gram.bin')
+    mp.spawn(_rank_shared, args=(world, _free_port(), nx, ny, cols, path,
+                                 str(tmp_path)), nprocs=world, join=True)
+    K = np.fromfile(path, dtype=np.float32).reshape((nx, ny), order='F')
+    want = 1000.0 * np.arange(nx)[:, None] + np.arange(ny)[None, :]
+    assert np.array_equal(K, want)
+    assert np.load(tmp_path / 'total.npy')[0] == nx * ny

@@ -29,3 +29,25 @@ for slots in (2, 4):
     Kd = kernel(G[:4], nodal=True)
     print(slots, float(np.abs(K - K2).max()), K.shape, dK.shape, Kd.shape)
 print('sanitize target done')
+
+# round 2: the large-pair (cluster) kernel, forced onto mid-size graphs by a
+# small shared-memory cap so that the sanitizer finishes quickly; Gram +
+# Jacobian, symmetric and X-by-Y, against the general kernel
+if '--large' in sys.argv:
+    from graphdot_b200.synthetic import newman_watts_strogatz
+    os.environ['GDB_SMEM_CAP'] = '40000'
+    G = [newman_watts_strogatz(np.random.default_rng(s), n) for s, n in
+         ((1, 41), (2, 56), (3, 64))]
+    be = B200Backend()
+    kernel = make_config_kernel('C4', backend=be)
+    K, dK = kernel(G, eval_gradient=True)
+    print('large:', be.last['kernel'], be.last['grid'], be.last['smem_bytes'])
+    assert be.last['kernel'] == 'mlgk_solve_large'
+    Kxy = kernel(G[:2], G[1:])
+    os.environ['GDB_FORCE_GENERAL'] = '1'
+    be2 = B200Backend()
+    K2, dK2 = make_config_kernel('C4', backend=be2)(G, eval_gradient=True)
+    assert be2.last['kernel'] == 'mlgk_solve'
+    print('large vs general:', float(np.abs(K / K2 - 1).max()),
+          float(np.abs(dK - dK2).max() / np.abs(dK2).max()))
+    print('sanitize large target done')
