@@ -846,7 +846,7 @@ static int pick_kernel(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, cons
         const uint64_t D = std::min<uint64_t>(gs->max_degree, (uint64_t)p->lell);
         const uint64_t ell_entry = p->ell_entry;  // sizeof(gdb_ell_t), read back from the module
         const uint64_t row_cap = std::min<uint64_t>((uint64_t)gs->max_tile_nnz * p->large_ltr, 1024);
-        const uint64_t ell = ((D * n2p * ell_entry + 15) & ~15ull) + ((n2p * 2 + 15) & ~15ull) +
+        const uint64_t ell = ((D * n2p * ell_entry + 15) & ~15ull) + ((n2p * 4 + 15) & ~15ull) +
                              2 * ((row_cap * ell_entry + 15) & ~15ull);
         const uint64_t buf = (uint64_t)p->large_ltr * gs->max_tc * n2p * 4;
         const uint64_t lcap = std::min<uint64_t>(cap, (uint64_t)c->prop.sharedMemPerBlockOptin - p->large_static_smem);

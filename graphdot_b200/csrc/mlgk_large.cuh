@@ -27,8 +27,9 @@
 //    conflict-free LDS.  Rows of 1..8 elements run a gather loop specialised
 //    on the element count, with the row's elements in registers;
 //  * G2 is held per CTA in shared memory in ELL form (slot-major:
-//    ell[t][column] = {neighbour, edge}), so that the lanes' loads are
-//    conflict-free as well; the elements of the tile row of G1 are staged next
+//    ell[t][position] = {neighbour, edge}, positions = columns sorted by
+//    decreasing degree so that the lanes of a warp run the same number of
+//    slots), so that the lanes' loads are conflict-free as well; the elements of the tile row of G1 are staged next
 //    to the rows they gather from and read by broadcast loads;
 //    the edge microkernel is evaluated on the fly (nnz1 nnz2 = 2e6 products
 //    per matvec do not fit on chip);
@@ -127,7 +128,7 @@ struct gdb_large_graph {
     const float *degree;
     const node_t *node;
     const edge_t *edge;
-    const unsigned *rowptr, *rowadj, *rowpos, *tcptr;
+    const unsigned *rowptr, *rowadj, *rowpos, *tcptr, *lanemap;
     const unsigned short *tccol, *tcslot;
     int n, nnz, n_tile, max_degree, max_tc;
 };
@@ -142,6 +143,7 @@ __device__ __forceinline__ gdb_large_graph gdb_large_view(const unsigned char *b
     v.rowadj = reinterpret_cast<const unsigned *>(base + h->off_rowadj);
     v.rowpos = reinterpret_cast<const unsigned *>(base + h->off_ellslot);
     v.tcptr = reinterpret_cast<const unsigned *>(base + h->off_tcptr);
+    v.lanemap = reinterpret_cast<const unsigned *>(base + h->off_lanemap);
     v.tccol = reinterpret_cast<const unsigned short *>(base + h->off_tccol);
     v.tcslot = reinterpret_cast<const unsigned short *>(base + h->off_tcslot);
     v.n = h->n_node;
@@ -177,8 +179,8 @@ struct gdb_large_ctx {
     gdb_large_graph g1, g2;
     unsigned n2p;                 // row stride of the vectors (floats)
     int t_lo, t_hi;               // this CTA's tile rows of G1
-    gdb_ell_t *ell;               // [D2][n2p] slot t of column c of G2
-    unsigned short *deg2;         // [n2p] stored elements of column c (0 for pad columns)
+    gdb_ell_t *ell;               // [D2][n2p] slot t of the column at position p of G2
+    unsigned *colinfo;            // [n2p] position p (columns sorted by decreasing degree) -> column | degree << 16
     int D2;                       // ELL slots in shared memory
     float *stage[2];              // staged rows of the gathered vector
     gdb_ell_t *rowel[2];          // elements of the tile row of G1 (CSR order): {shared-window address of the
@@ -287,8 +289,14 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
                 for (int u = 0; u < K; ++u) el[u] = gdb_lds_ell(row_sa + (unsigned)u * (unsigned)sizeof(gdb_ell_t));  // broadcast loads
 #pragma unroll 1
                 for (unsigned c0 = 32u * q; c0 < (unsigned)n2; c0 += 32u * groups) {
-                    const unsigned c = c0 + lane;
-                    const bool live = c < (unsigned)n2;
+                    // lanes take 32 consecutive POSITIONS of the degree-sorted column order (the
+                    // packer's lane map, stable within a degree): the lanes of a warp then have
+                    // (almost) the same number of slots -- in node order the per-lane trip count
+                    // of the slot loop left 28 % of the lanes idle
+                    const unsigned pos = c0 + lane;
+                    const bool live = pos < (unsigned)n2;
+                    const unsigned ci = live ? C.colinfo[pos] : 0u;
+                    const unsigned c = ci & 0xffffu;
                     // own element: its global loads are issued before the gather loop, which
                     // hides their latency
                     const size_t i_own = (size_t)i1 * n2p + (live ? c : 0u);
@@ -299,9 +307,9 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
                     } else {
                         own_v = yv[i_own];
                     }
-                    const unsigned d2 = live ? C.deg2[c] : 0u;
+                    const unsigned d2 = ci >> 16;
                     const unsigned d2s = min(d2, (unsigned)C.D2);
-                    unsigned at = ell_sa + c * (unsigned)sizeof(gdb_ell_t);
+                    unsigned at = ell_sa + pos * (unsigned)sizeof(gdb_ell_t);
                     float acc[NACC];
 #pragma unroll
                     for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
@@ -327,7 +335,7 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
                         }
                     }
                     if (u_sh < deg1 || d2 > d2s) {  // rare: elements beyond the shared-memory copies
-                        const unsigned kb = C.g2.rowptr[live ? c : 0u];
+                        const unsigned kb = C.g2.rowptr[c];
                         for (unsigned u = 0; u < deg1; ++u) {
                             const unsigned k1 = k1beg + u;
                             const edge_t e1 = C.g1.edge[C.g1.rowadj[k1] >> 16];
@@ -475,8 +483,8 @@ extern "C" __global__ void __cluster_dims__(GDB_CLUSTER, 1, 1) __launch_bounds__
         unsigned off = 0;
         C.ell = reinterpret_cast<gdb_ell_t *>(gdb_smem);
         off += (((unsigned)C.D2 * n2p * (unsigned)sizeof(gdb_ell_t)) + 15u) & ~15u;
-        C.deg2 = reinterpret_cast<unsigned short *>(gdb_smem + off);
-        off += ((n2p * 2u) + 15u) & ~15u;
+        C.colinfo = reinterpret_cast<unsigned *>(gdb_smem + off);
+        off += ((n2p * 4u) + 15u) & ~15u;
 #pragma unroll
         for (int bb = 0; bb < 2; ++bb) {
             C.rowel[bb] = reinterpret_cast<gdb_ell_t *>(gdb_smem + off);
@@ -487,8 +495,14 @@ extern "C" __global__ void __cluster_dims__(GDB_CLUSTER, 1, 1) __launch_bounds__
         C.dbl = off + 2u * buf_bytes <= F.smem_bytes;
         C.stage[1] = C.dbl ? reinterpret_cast<float *>(gdb_smem + off + buf_bytes) : C.stage[0];
         if (!C.dbl) C.rowel[1] = C.rowel[0];
-        for (unsigned c = threadIdx.x; c < n2p; c += GDB_LBLOCK)
-            C.deg2[c] = c < (unsigned)n2 ? (unsigned short)(C.g2.rowptr[c + 1] - C.g2.rowptr[c]) : (unsigned short)0;
+        for (unsigned ps = threadIdx.x; ps < n2p; ps += GDB_LBLOCK) {
+            unsigned ci = 0u;
+            if (ps < (unsigned)n2) {
+                const unsigned c = C.g2.lanemap[ps] & 0xffffu;
+                ci = c | ((C.g2.rowptr[c + 1] - C.g2.rowptr[c]) << 16);
+            }
+            C.colinfo[ps] = ci;
+        }
         for (unsigned k2 = threadIdx.x; k2 < (unsigned)C.g2.nnz; k2 += GDB_LBLOCK) {
             const unsigned rp = C.g2.rowpos[k2], c = rp & 0xffffu, t2 = rp >> 16;
             if (t2 < (unsigned)C.D2) {
@@ -496,7 +510,7 @@ extern "C" __global__ void __cluster_dims__(GDB_CLUSTER, 1, 1) __launch_bounds__
                 gdb_ell_t en;
                 en.off = (a2 & 0xffffu) * 4u;
                 en.e = C.g2.edge[a2 >> 16];
-                C.ell[t2 * n2p + c] = en;
+                C.ell[t2 * n2p + (C.g2.lanemap[c] >> 16)] = en;
             }
         }
 

