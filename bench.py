@@ -433,7 +433,7 @@ def run_gpu(args, rank, world, local_rank):
                       'eval_gradient=True): 1 diagonal launch + 1 launch of '
                       'all 2 001 000 pairs, result in torch CUDA tensors',
                       e2e_path='Normalization(kernel)(G, eval_gradient=True)'
-                      ': graphs H2D, diagonal launch, 8 pipelined row-block '
+                      ': graphs H2D, diagonal launch, 4 pipelined row-block '
                       'launches, column blocks D2H + float64 collection '
                       'overlapped with the next launch')
 

@@ -278,3 +278,53 @@ def test_c4_symmetric_gram_small_set(backend):
     assert np.array_equal(K, K.T)
     Kn = Normalization(kernel)(G)
     assert np.allclose(np.diag(Kn), 1.0, atol=2e-7)
+
+
+@pytest.mark.parametrize('p_edge, grad', [(0.08, True), (0.3, False),
+                                          (0.3, True)])
+def test_large_pair_kernel_rare_paths_vs_general_kernel(monkeypatch, p_edge,
+                                                        grad):
+    """The cluster kernel on inputs unlike C4: weighted molecular-style graphs
+    (8-byte edge type) of 70-110 nodes, dense enough (degree up to ~40) that
+    rows have more than 8 elements (generic gather loop), columns more than
+    16 neighbours (ELL overflow read from global memory) and tile rows touch
+    most columns; X-by-Y with different sizes.  Forced by a small
+    shared-memory cap; compared with the general kernel and the oracle."""
+    from graphdot_b200.synthetic import random_labeled_graph
+    rng = np.random.default_rng(11)
+    G = [random_labeled_graph(rng, n, p_edge) for n in (71, 96, 110, 83)]
+    monkeypatch.setenv('GDB_SMEM_CAP', '120000')
+    be = B200Backend()
+    kernel = make_config_kernel('C3', backend=be)
+    out = kernel(G[:2], G[2:], eval_gradient=grad)
+    assert be.last['kernel'] == 'mlgk_solve_large'
+    sym = kernel(G, eval_gradient=grad)
+    assert be.last['kernel'] == 'mlgk_solve_large'
+    monkeypatch.setenv('GDB_FORCE_GENERAL', '1')
+    be2 = B200Backend()
+    kernel2 = make_config_kernel('C3', backend=be2)
+    ref = kernel2(G[:2], G[2:], eval_gradient=grad)
+    assert be2.last['kernel'] == 'mlgk_solve'
+    sym2 = kernel2(G, eval_gradient=grad)
+    if grad:
+        assert rel_err(out[0], ref[0]) < 2e-6
+        assert rel_err(sym[0], sym2[0]) < 2e-6
+        for m in range(5):
+            assert rel_err(out[1][:, :, m], ref[1][:, :, m]) < 2e-5
+            assert rel_err(sym[1][:, :, m], sym2[1][:, :, m]) < 2e-5
+        K = sym[0]
+    else:
+        assert rel_err(out, ref) < 2e-6
+        assert rel_err(sym, sym2) < 2e-6
+        K = sym
+    assert np.array_equal(K, K.T)
+    if p_edge > 0.1:      # the dense oracle is slow on 10^6 edge pairs
+        return
+    # one pair against the float64 oracle
+    _, ko, go = oracle.solve_pair(G[0], G[3], kernel.node_kernel,
+                                  kernel.edge_kernel, kernel.q, kernel.p,
+                                  eval_gradient=True)
+    assert K[0, 3] == pytest.approx(ko, rel=GRAM_RTOL)
+    if grad:
+        assert np.allclose(sym[1][0, 3], go, rtol=GRAD_RTOL,
+                           atol=GRAD_RTOL * np.abs(go).max())

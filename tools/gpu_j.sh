@@ -10,5 +10,6 @@ for n in 4 6 12; do
 import sys,json
 d=json.loads(sys.stdin.read()); print('launches $n: value %.4g e2e %.4g e2e_ms %.2f' % (d['value'], d['e2e']['value'], d['e2e']['ms_per_step']))"
 done
+timeout 120 python tools/e2e_breakdown.py > $O/e2e_breakdown.txt 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:mlgk_solve -s 1 -c 1 -f -o $O/prof_c4 python tools/profile_c4.py --n-graphs 24 > $O/ncu_c4.log 2>&1
 echo "ncu c4 rc=$?"
