@@ -285,7 +285,7 @@ static int pick_wpt(const gdb_program_desc *d) { return d->workers_per_thread <=
 static int pick_rpw(const gdb_program_desc *d) { return d->rows_per_warp <= 0 ? 8 : d->rows_per_warp; }
 static int pick_adj(const gdb_program_desc *d) { return d->slots_per_lane <= 0 ? 4 : d->slots_per_lane; }
 static int pick_cluster(const gdb_program_desc *d) {
-    int c = d->cluster_size <= 0 ? 4 : d->cluster_size;
+    int c = d->cluster_size <= 0 ? 2 : d->cluster_size;
     if (const char *env = getenv("GDB_CLUSTER")) c = atoi(env);  // tuning hook
     return c;
 }
@@ -845,18 +845,25 @@ static int pick_kernel(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, cons
         const uint64_t n2p = ((uint64_t)gs->max_node[0] + 3) & ~3ull;
         const uint64_t D = std::min<uint64_t>(gs->max_degree, (uint64_t)p->lell);
         const uint64_t ell_entry = p->ell_entry;  // sizeof(gdb_ell_t), read back from the module
-        const uint64_t row_cap = std::min<uint64_t>((uint64_t)gs->max_tile_nnz * p->large_ltr, 1024);
+        // elements of one CTA's rows of the first graph: at most its share of the tile rows
+        const uint64_t tiles_per_cta = (((uint64_t)gs->max_node[0] + 7) / 8 + p->cluster - 1) / p->cluster;
+        const uint64_t row_cap = std::min<uint64_t>((uint64_t)gs->max_tile_nnz * tiles_per_cta, 6144);
         const uint64_t ell = ((D * n2p * ell_entry + 15) & ~15ull) + ((n2p * 4 + 15) & ~15ull) +
-                             2 * ((row_cap * ell_entry + 15) & ~15ull);
+                             ((row_cap * ell_entry + 15) & ~15ull);
         const uint64_t buf = (uint64_t)p->large_ltr * gs->max_tc * n2p * 4;
         const uint64_t lcap = std::min<uint64_t>(cap, (uint64_t)c->prop.sharedMemPerBlockOptin - p->large_static_smem);
-        // staging: double buffered unless that costs a resident CTA per SM (two CTAs of
-        // different pairs hide each other's latency better than a second buffer does)
-        uint64_t need = ell + 2 * buf;
+        // staging: ONE buffer.  Two resident CTAs of different pairs per SM hide the staging
+        // latency of each other, and the shared memory a second buffer would take is worth
+        // more as L1 (the node-kernel set-up re-reads the feature pools of both graphs; measured
+        // on C4: 2 x 115 KB double buffered 32.5 k pairs/s, 2 x 80 KB single buffered 42.9 k).
+        // GDB_LARGE_DOUBLE=1 forces double buffering (A-B hook).
+        uint64_t need = ell + buf;
         int ctas_dbl = 0, ctas_sgl = 0;
-        if (need <= lcap) DRV(c, c->cuOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_dbl, p->fn_large, (int)p->large_block, (size_t)need));
-        if (ell + buf <= lcap) DRV(c, c->cuOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_sgl, p->fn_large, (int)p->large_block, (size_t)(ell + buf)));
-        if (ctas_sgl > ctas_dbl || getenv("GDB_LARGE_SINGLE")) need = ell + buf;
+        if (need <= lcap) DRV(c, c->cuOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_sgl, p->fn_large, (int)p->large_block, (size_t)need));
+        if (getenv("GDB_LARGE_DOUBLE") && ell + 2 * buf <= lcap) {
+            need = ell + 2 * buf;
+            DRV(c, c->cuOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_dbl, p->fn_large, (int)p->large_block, (size_t)need));
+        }
         if (need <= lcap) {
             // clusters in flight: what the device can co-schedule (an optional cap keeps
             // the vectors of all of them L2-resident: GDB_L2_BUDGET_MB)

@@ -20,8 +20,10 @@
 //    row's elements touch -- the packer's sorted list of distinct neighbour
 //    columns of that tile row (gdb_pack.cpp: tcptr / tccol / tcslot), about 14
 //    rows for a banded graph instead of the 24 rows of its 3 octiles -- are
-//    staged in shared memory with cp.async (16-byte LDGSTS, L2 -> smem),
-//    double buffered when that does not cost a resident CTA.  The CTA's warps
+//    staged in shared memory with cp.async (16-byte LDGSTS, L2 -> smem) into ONE
+//    buffer: the second resident CTA of the SM (another pair) covers the
+//    staging latency, and the shared memory a second buffer would take is
+//    worth more as L1 (32.5 k vs 42.9 k pairs/s on C4).  The CTA's warps
 //    share out (rows of the tile row) x (blocks of 32 columns); a warp's lanes
 //    own 32 consecutive columns at a time: every gather of p is a
 //    conflict-free LDS.  Rows of 1..8 elements run a gather loop specialised
@@ -46,7 +48,7 @@
 #pragma once
 
 #ifndef GDB_CLUSTER
-#define GDB_CLUSTER 4
+#define GDB_CLUSTER 2
 #endif
 #ifndef GDB_LELL
 #define GDB_LELL 12
@@ -183,15 +185,16 @@ struct gdb_large_ctx {
     unsigned *colinfo;            // [n2p] position p (columns sorted by decreasing degree) -> column | degree << 16
     int D2;                       // ELL slots in shared memory
     float *stage[2];              // staged rows of the gathered vector
-    gdb_ell_t *rowel[2];          // elements of the tile row of G1 (CSR order): {shared-window address of the
-                                  // staged row the element gathers from, edge}
-    unsigned cap;                 // elements per tile row held in shared memory
+    gdb_ell_t *rowel;             // elements of ALL of this CTA's rows of G1 (CSR order), filled once per pair:
+                                  // {byte offset, inside a staging buffer, of the staged row the element
+                                  // gathers from; edge}
+    unsigned k_lo;                // CSR position of the first of them
+    unsigned cap;                 // elements held in shared memory
     bool dbl;                     // both staging buffers usable
 };
 
 // cp.async the rows of `vec` that the tile rows [t, t_end) of G1 touch into staging
-// buffer b (one list of rows per tile row, back to back), and copy the elements of
-// those tile rows (edge, address of the staged row it gathers from) next to them
+// buffer b (one list of rows per tile row, back to back)
 __device__ __forceinline__ void gdb_large_stage(const gdb_large_ctx &C, const float *vec, int t, int t_end, int b) {
     const unsigned per_row = C.n2p / 4u;  // 16-byte chunks per row
     const unsigned dst0 = gdb_smem_u32(C.stage[b]);
@@ -203,14 +206,6 @@ __device__ __forceinline__ void gdb_large_stage(const gdb_large_ctx &C, const fl
         const unsigned dst = dst0 + s * C.n2p * 4u;
 #pragma unroll 4
         for (unsigned ch = lane; ch < per_row; ch += 32u) gdb_cp_async16(dst + ch * 16u, src + ch * 4u);
-    }
-    const unsigned k0 = C.g1.rowptr[8 * t], k1 = C.g1.rowptr[min(8 * t_end, C.g1.n)];
-    for (unsigned k = threadIdx.x; k < min(k1 - k0, C.cap); k += GDB_LBLOCK) {
-        const unsigned tile = (C.g1.rowpos[k0 + k] & 0xffffu) >> 3;  // tile row of this element
-        gdb_ell_t el;
-        el.off = dst0 + (C.g1.tcptr[tile] - c0 + (unsigned)C.g1.tcslot[k0 + k]) * C.n2p * 4u;
-        el.e = C.g1.edge[C.g1.rowadj[k0 + k] >> 16];
-        C.rowel[b][k] = el;
     }
 }
 
@@ -268,7 +263,7 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
         const unsigned rows_here = (unsigned)(min(8 * t_end, n1) - 8 * t);
         const unsigned groups = max(1u, (unsigned)(GDB_LBLOCK / 32) / rows_here);
         const unsigned ell_sa = gdb_smem_u32(C.ell), ell_stride = n2p * (unsigned)sizeof(gdb_ell_t);
-        const unsigned k0 = C.g1.rowptr[8 * t];
+        const unsigned stage_sa = gdb_smem_u32(C.stage[b]);
         constexpr int NACC = MODE == 0 ? 1 : (GDB_NE > 0 ? GDB_NE : 1);
 #pragma unroll 1
         for (unsigned wi = warp; wi < rows_here * groups; wi += GDB_LBLOCK / 32) {
@@ -276,8 +271,8 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
             const int i1 = 8 * t + (int)(wi - q * rows_here);
             const unsigned k1beg = C.g1.rowptr[i1], deg1 = C.g1.rowptr[i1 + 1] - k1beg;
             // elements of this row that sit in shared memory (the rest, rare, in global memory)
-            const unsigned u_sh = k1beg - k0 >= C.cap ? 0u : min(deg1, C.cap - (k1beg - k0));
-            const unsigned row_sa = gdb_smem_u32(C.rowel[b]) + (k1beg - k0) * (unsigned)sizeof(gdb_ell_t);
+            const unsigned u_sh = k1beg - C.k_lo >= C.cap ? 0u : min(deg1, C.cap - (k1beg - C.k_lo));
+            const unsigned row_sa = gdb_smem_u32(C.rowel) + (k1beg - C.k_lo) * (unsigned)sizeof(gdb_ell_t);
             // K > 0: the row has exactly K elements, held in registers and fully unrolled
             // (about 8 instructions per product: sub, 2 mul, ex2, fma for a square-exponential
             // edge kernel + 2 LDS + 1 add, instead of 17 with a rolled loop over a handful of
@@ -286,7 +281,10 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
                 constexpr int K = decltype(kc)::value;
                 gdb_ell_t el[K > 0 ? K : 1];
 #pragma unroll
-                for (int u = 0; u < K; ++u) el[u] = gdb_lds_ell(row_sa + (unsigned)u * (unsigned)sizeof(gdb_ell_t));  // broadcast loads
+                for (int u = 0; u < K; ++u) {
+                    el[u] = gdb_lds_ell(row_sa + (unsigned)u * (unsigned)sizeof(gdb_ell_t));  // broadcast loads
+                    el[u].off += stage_sa;  // offset inside a staging buffer -> shared-window address
+                }
 #pragma unroll 1
                 for (unsigned c0 = 32u * q; c0 < (unsigned)n2; c0 += 32u * groups) {
                     // lanes take 32 consecutive POSITIONS of the degree-sorted column order (the
@@ -329,7 +327,7 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
                             for (unsigned u = 0; u < u_sh; ++u, ra += (unsigned)sizeof(gdb_ell_t)) {  // warp-uniform
                                 const gdb_ell_t e1 = gdb_lds_ell(ra);
                                 float pj;
-                                asm("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(e1.off + en.off));
+                                asm("ld.shared.f32 %0, [%1];" : "=f"(pj) : "r"(stage_sa + e1.off + en.off));
                                 gdb_large_product<MODE, NACC>(P, e1.e, en.e, pj, acc);
                             }
                         }
@@ -485,16 +483,24 @@ extern "C" __global__ void __cluster_dims__(GDB_CLUSTER, 1, 1) __launch_bounds__
         off += (((unsigned)C.D2 * n2p * (unsigned)sizeof(gdb_ell_t)) + 15u) & ~15u;
         C.colinfo = reinterpret_cast<unsigned *>(gdb_smem + off);
         off += ((n2p * 4u) + 15u) & ~15u;
-#pragma unroll
-        for (int bb = 0; bb < 2; ++bb) {
-            C.rowel[bb] = reinterpret_cast<gdb_ell_t *>(gdb_smem + off);
-            off += ((C.cap * (unsigned)sizeof(gdb_ell_t)) + 15u) & ~15u;
-        }
+        C.rowel = reinterpret_cast<gdb_ell_t *>(gdb_smem + off);
+        off += ((C.cap * (unsigned)sizeof(gdb_ell_t)) + 15u) & ~15u;
         const unsigned buf_bytes = (unsigned)GDB_LTR * (unsigned)C.g1.max_tc * n2p * 4u;
         C.stage[0] = reinterpret_cast<float *>(gdb_smem + off);
         C.dbl = off + 2u * buf_bytes <= F.smem_bytes;
         C.stage[1] = C.dbl ? reinterpret_cast<float *>(gdb_smem + off + buf_bytes) : C.stage[0];
-        if (!C.dbl) C.rowel[1] = C.rowel[0];
+        // the elements of this CTA's rows of G1, once per pair (the staging steps of every
+        // matvec then issue cp.async only)
+        C.k_lo = C.g1.rowptr[row_lo];
+        for (unsigned k = threadIdx.x; k < min(C.g1.rowptr[row_hi] - C.k_lo, C.cap); k += GDB_LBLOCK) {
+            const unsigned kk = C.k_lo + k;
+            const unsigned tile = (C.g1.rowpos[kk] & 0xffffu) >> 3;  // tile row of this element
+            const unsigned first = (unsigned)C.t_lo + (tile - (unsigned)C.t_lo) / GDB_LTR * GDB_LTR;  // first tile row of its step
+            gdb_ell_t el;
+            el.off = (C.g1.tcptr[tile] - C.g1.tcptr[first] + (unsigned)C.g1.tcslot[kk]) * n2p * 4u;
+            el.e = C.g1.edge[C.g1.rowadj[kk] >> 16];
+            C.rowel[k] = el;
+        }
         for (unsigned ps = threadIdx.x; ps < n2p; ps += GDB_LBLOCK) {
             unsigned ci = 0u;
             if (ps < (unsigned)n2) {

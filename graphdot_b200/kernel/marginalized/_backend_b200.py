@@ -294,7 +294,7 @@ class B200Backend(Backend):
         self.device = device
         self.block_size = block_size
         self.slots_per_lane = slots_per_lane   # 2 / 4 / None = by mean degree
-        self.cluster_size = cluster_size       # CTAs per large pair; None = 4
+        self.cluster_size = cluster_size       # CTAs per large pair; None = 2
         # GDB_NVRTC_EXTRA: tuning hook (e.g. '-DGDB_LBLOCK=512 -DGDB_LTR=1')
         self.nvrtc_extra = (list(nvrtc_extra)
                             + os.environ.get('GDB_NVRTC_EXTRA', '').split())

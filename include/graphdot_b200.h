@@ -118,7 +118,7 @@ typedef struct gdb_program_desc {
     const char *extra_options; /* extra NVRTC options, space separated     */
     /* large-pair kernel (one thread-block cluster per pair; used when the CG
      * vectors of the largest pair do not fit in shared memory)            */
-    int32_t cluster_size;    /* CTAs per pair: 1, 2, 4 or 8; 0 = 4          */
+    int32_t cluster_size;    /* CTAs per pair: 1, 2, 4 or 8; 0 = 2          */
     int32_t cols_per_lane;   /* columns of the second graph per lane, 1..32;
                                 32 * cols_per_lane >= nodes; 0 = 16          */
     int32_t ell_slots;       /* neighbours per column of the second graph
