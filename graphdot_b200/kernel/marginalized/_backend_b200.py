@@ -306,6 +306,7 @@ class B200Backend(Backend):
         self.resend_graphs = False   # True: every call re-sends the packed
         #                              graphs host -> device (end-to-end timing)
         self._inflight = []      # host inputs of asynchronous solves
+        self._memo = None        # (list object, len, first, last, graph set)
         self.totals = {}         # running sums over all solves (bench)
         self.reset_totals()
         native.load()            # fail loudly if the library is missing
@@ -635,7 +636,19 @@ class B200Backend(Backend):
         pipelines the solve in row / column blocks, ``gramian_dev=`` /
         ``gradient_dev=`` leave the results in caller-owned device memory."""
         timer.tic('transferring graphs to GPU')
-        gs = self.graphset(list(graphs))
+        # the front end hands the SAME list object to the diagonal solve and to
+        # the main solve of one public call: skip the second cache walk
+        memo = self._memo
+        if (type(graphs) is list and memo is not None and memo[0] is graphs
+                and len(graphs) == memo[1] and graphs[0] is memo[2]
+                and graphs[-1] is memo[3]
+                and graphs[0].cookie.get(self.uuid) is memo[4].packed[0]
+                and graphs[-1].cookie.get(self.uuid) is memo[4].packed[-1]):
+            gs = memo[4]
+        else:
+            glist = graphs if type(graphs) is list else list(graphs)
+            gs = self.graphset(glist)
+            self._memo = (graphs, len(glist), glist[0], glist[-1], gs)
         timer.toc('transferring graphs to GPU')
 
         timer.tic('code generation + JIT')
