@@ -827,13 +827,15 @@ static int pick_kernel(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, cons
         // one warp per tile row of G1, lanes (x workers per thread) over the columns of G2
         const bool mapped = (uint64_t)gs->max_node[0] <= (uint64_t)p->rpw * (uint64_t)(block / 32) &&
                             (uint64_t)gs->max_node[0] <= 32ull * p->wpt;
-        // nodal Jacobians (forward sensitivities) are implemented by the general kernel only
+        // nodal Jacobians (forward sensitivities): a second W-shaped buffer for dW, x by node
+        // and the right-hand sides of a round
         const bool nodal_grad = p->eval_gradient && p->nodal != GDB_NODAL_NONE;
-        if (gs->index16 && small_need <= small_cap && mapped && wmax < (1u << 24) && !nodal_grad &&
+        const uint64_t ng_need = nodal_grad ? (((wmax + 3) & ~3ull) * 2 - wmax) * 4 + maxNpad * 4 + maxNpad * 8 + 64 : 0;
+        if (gs->index16 && small_need + ng_need <= small_cap && mapped && wmax < (1u << 24) &&
             !getenv("GDB_FORCE_GENERAL")) {
             k.fn = p->fn_small;
             k.kind = 1;
-            smem = small_need;
+            smem = small_need + ng_need;
             spill = false;
         }
     }

@@ -103,6 +103,18 @@ __device__ __forceinline__ gv_t gv_add(gv_t a, gv_t b) { return a + b; }
 __device__ __forceinline__ float gv_get(gv_t a, int) { return a; }
 #endif
 
+// nodal Jacobians (forward sensitivities) run extra solve rounds
+#define GDB_NGRAD (GDB_GRADIENT && GDB_NODAL != 0)
+// byte offset added to the W-row addresses of a matvec: a compile-time zero for the CG
+// matvec, the distance to the dW buffer for the right-hand sides of edge sensitivities
+struct gdb_wzero {
+    __device__ __forceinline__ unsigned operator()() const { return 0u; }
+};
+struct gdb_wdelta {
+    unsigned bytes;
+    __device__ __forceinline__ unsigned operator()() const { return bytes; }
+};
+
 // ---- mbarrier / TMA bulk copy (cp.async.bulk) helpers --------------------------
 __device__ __forceinline__ unsigned gdb_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void gdb_mbar_init(unsigned long long *bar, unsigned count) {
@@ -536,7 +548,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
                 const int i2 = (int)(g2.lanemap[pos] & 0xffffu);
                 const node_t &u2 = g2.node[i2];
                 const float d2 = g2.degree[i2] * Q2;
-#if GDB_GRADIENT
+#if GDB_GRADIENT && !GDB_NGRAD
                 const float p2 = P.p_start(u2);
 #endif
 #pragma unroll 1
@@ -545,7 +557,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
                     const float dx = g1.degree[i1] * d2;
                     // diagonal Dx / Vx in the first float of p, rhs in the W p slot
                     pbuf[i1 * n2 + pos] = gv_make(__fdividef(dx, P.node_kernel(u1, u2)), 0.f);
-#if GDB_GRADIENT
+#if GDB_GRADIENT && !GDB_NGRAD
                     wpbuf[i1 * n2 + pos] = gv_make(dx, P.p_start(u1) * p2);
 #else
                     wpbuf[i1 * n2 + pos] = gv_make(dx, 0.f);
@@ -644,77 +656,237 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
         }
         gdb_group_sync();  // W, the step table and p complete
 
+        // matvec: W p of every owned element, one row of G1 at a time
+        auto row_wp = [&](int i1, gv_t (&acc)[GDB_WPT], auto wd) {
+#pragma unroll
+            for (int s = 0; s < GDB_WPT; ++s) acc[s] = gv_make(0.f, 0.f);
+            const uint2 row = gdb_lds_u2(w_rtsa + (unsigned)(i1 - w_row0) * 8u);  // steps of this row
+            GDB_UNROLL(GDB_K1_UNROLL)  // the body is replicated per row already: keep the code in the instruction cache
+            for (unsigned ka = row.x; ka != row.y; ka += 8u) {  // warp-uniform trip count
+                const uint2 step = gdb_lds_u2(ka);  // (W row, p row)
+#pragma unroll
+                for (int s = 0; s < GDB_WPT; ++s) {
+                    // All lanes load: empty slots hold W = 0 and point at position 0
+                    // of the p row, unused lanes read lane 0's slots.
+#if GDB_ADJ == 2
+                    const float2 w2 = gdb_lds_f2(step.x + w_woff[s] + wd());
+                    const gv_t p0 = gdb_lds_gv(step.y + w_xoff[s][0]);
+                    const gv_t p1 = gdb_lds_gv(step.y + w_xoff[s][1]);
+                    acc[s] = gv_fma(w2.x, p0, acc[s]);
+                    acc[s] = gv_fma(w2.y, p1, acc[s]);
+#else
+                    const float4 w4 = gdb_lds_f4(step.x + w_woff[s] + wd());
+                    const gv_t p0 = gdb_lds_gv(step.y + w_xoff[s][0]);
+                    const gv_t p1 = gdb_lds_gv(step.y + w_xoff[s][1]);
+                    const gv_t p2 = gdb_lds_gv(step.y + w_xoff[s][2]);
+                    const gv_t p3 = gdb_lds_gv(step.y + w_xoff[s][3]);
+                    acc[s] = gv_fma(w4.x, p0, acc[s]);
+                    acc[s] = gv_fma(w4.y, p1, acc[s]);
+                    acc[s] = gv_fma(w4.z, p2, acc[s]);
+                    acc[s] = gv_fma(w4.w, p3, acc[s]);
+#endif
+                }
+            }
+            // helpers hand their partial sums to the owning lane (fixed order).  The first
+            // exchange is unconditional -- lanes without a helper add nothing -- so that the
+            // common case of molecular graphs (one helper at most, no overflow) is straight-line
+#pragma unroll
+            for (int s = 0; s < GDB_WPT; ++s) {
+                const gv_t t = gdb_shfl_vlane(acc, w_help[s] & 0xffffu);
+                if (w_help[s] >> 16) acc[s] = gv_add(acc[s], t);
+            }
+            if (w_rare) {  // uniform per pair: more helpers per column, or slots without a lane
+#pragma unroll 1
+                for (unsigned h = 1; h < w_most; ++h) {
+#pragma unroll
+                    for (int s = 0; s < GDB_WPT; ++s) {
+                        const unsigned src = (w_help[s] & 0xffffu) + h;
+                        const gv_t t = gdb_shfl_vlane(acc, src);
+                        if (h < (w_help[s] >> 16)) acc[s] = gv_add(acc[s], t);
+                    }
+                }
+                if (w_ovf) {
+#pragma unroll
+                    for (int s = 0; s < GDB_WPT; ++s)
+                        if (GDB_LIVE(s))
+                            acc[s] = gv_add(acc[s], gdb_small_overflow(g1.rowadj, g2.rowptr, g2.rowadj, g2.lanemap, vovf, W + wd() / 4u, pbuf,
+                                                                       g1.rowptr[i1], g1.rowptr[i1 + 1], (unsigned)wstride, ovf0, (unsigned)n2,
+                                                                       (unsigned)GDB_POS(s),
+                                                                       (1u + (w_help[s] >> 16)) * (unsigned)GDB_ADJ));
+                }
+            }
+        };
+
+#if GDB_NGRAD
+        // ---- nodal Jacobian by forward sensitivities (reference template.cu:226-418 re-solves
+        //      twice per hyper-parameter for a central difference): R_i = xs_i p1 p2; d/dp_m is
+        //      explicit; for q, node and edge parameters  dx/dt = A^-1 (db/dt - dA/dt x)  is one
+        //      more solve with the SAME cached operator W -- two parameters per round on the
+        //      two float2 lanes:
+        //        q:      rhs = 2Q Dx (1 - x / Vx)
+        //        node m: rhs = Dx / Vx^2 dVx_m x          (+ lmin: R -= dVx_m p1 p2)
+        //        edge m: rhs = (dW_m) x: dW_m is cached like W in a second buffer and applied
+        //                with the matvec of the CG loop
+        constexpr int NG_SENS = GDB_NJ - GDB_NP;
+        constexpr int NG_ROUNDS = 1 + (NG_SENS + 1) / 2;
+        const unsigned w_floats = ((unsigned)(nnz1 * wstride) + 3u) & ~3u;
+        float *W2 = W + w_floats;                     // dW_m, same layout as W
+        float *Xb = W2 + w_floats;                    // x of the value solve, by node
+        gv_t *rhsb = reinterpret_cast<gv_t *>(Xb + ((N + 3) & ~3));  // right-hand sides, by lane position
+        const unsigned ngI1 = F.starts[ja] - F.row0, ngI2 = F.starts[jb] - F.col0;
+        const unsigned long long ngplane = (unsigned long long)F.nX * F.nY;
+        (void)ngI2;
+        (void)ngplane;
+        auto write_nodal = [&](int i1, int i2, int m, float val) {
+#if GDB_NODAL == 2
+            F.grad[(unsigned long long)(ngI1 + i1 + i2 * n1) + (unsigned long long)m * F.nX] = val;
+#elif GDB_DIAGONAL
+            if (i1 == i2) F.grad[(unsigned long long)(ngI1 + i1) + (unsigned long long)m * F.nX] = val;
+#else
+            F.grad[(unsigned long long)(ngI1 + i1) + (unsigned long long)(ngI2 + i2) * F.nX + m * ngplane] = val;
+#if GDB_SYMMETRIC
+            if (!same) F.grad[(unsigned long long)(ngI2 + i2) + (unsigned long long)(ngI1 + i1) * F.nX + m * ngplane] = val;
+#endif
+#endif
+        };
+        bool w2_clean = false;
+        int iters = 0;  // summed over all rounds
+#pragma unroll 1
+        for (int round = 0; round < NG_ROUNDS; ++round) {
+        const int ng_m0 = GDB_NP + 2 * (round - 1);  // Jacobian index of lane 0 of this round (lane 1: + 1)
+        if (round > 0) {
+            gdb_group_sync();  // the outputs of the previous round have been read from p
+#if GDB_NE > 0
+            const bool any_edge = ng_m0 + 1 >= GDB_NP + 1 + GDB_NV;  // uniform
+            if (any_edge) {  // p := (x, x) by lane position: what the dW matvec gathers
+#pragma unroll
+                for (int s = 0; s < GDB_WPT; ++s)
+                    if (GDB_LIVE(s)) {
+                        const int i2 = (int)(g2.lanemap[GDB_POS(s)] & 0xffffu);
+#pragma unroll 1
+                        for (int i1 = w_row0; i1 < w_row1; ++i1) {
+                            const float xi = Xb[i1 * n2 + i2];
+                            pbuf[i1 * n2 + GDB_POS(s)] = gv_make(xi, xi);
+                        }
+                    }
+            }
+#endif
+            // element-wise right-hand sides (q and node parameters); edge parameters start at 0
+#pragma unroll
+            for (int s = 0; s < GDB_WPT; ++s)
+                if (GDB_LIVE(s)) {
+                    const int i2 = (int)(g2.lanemap[GDB_POS(s)] & 0xffffu);
+                    const node_t &u2 = g2.node[i2];
+                    const float d2 = g2.degree[i2] * Q2;
+#pragma unroll 1
+                    for (int i1 = w_row0; i1 < w_row1; ++i1) {
+                        const node_t &u1 = g1.node[i1];
+                        const float dx = g1.degree[i1] * d2;
+                        const float v = P.node_kernel(u1, u2);
+                        const float xi = Xb[i1 * n2 + i2];
+                        float comp[2] = {0.f, 0.f};
+#if GDB_NV > 0
+                        float dv[GDB_NV];
+                        P.node_kernel.jacobian(u1, u2, dv);
+#endif
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const int m = ng_m0 + c;
+                            if (m == GDB_NP) comp[c] = 2.f * Q * dx * (1.f - __fdividef(xi, v));
+#if GDB_NV > 0
+                            else if (m < GDB_NP + 1 + GDB_NV) {
+                                float dvm = 0.f;
+#pragma unroll
+                                for (int k = 0; k < GDB_NV; ++k) dvm = (k == m - GDB_NP - 1) ? dv[k] : dvm;
+                                comp[c] = __fdividef(dx, v * v) * dvm * xi;
+                            }
+#endif
+                        }
+                        rhsb[i1 * n2 + GDB_POS(s)] = gv_make(comp[0], comp[1]);
+                    }
+                }
+#if GDB_NE > 0
+            // edge parameters: dW_m into the second buffer (zero pattern as W), then one matvec
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                const int m = ng_m0 + c;
+                if (m < GDB_NP + 1 + GDB_NV || m >= GDB_NJ) continue;  // uniform
+                const int ke = m - (GDB_NP + 1 + GDB_NV);
+                if (!w2_clean) {
+                    float4 *W4 = reinterpret_cast<float4 *>(W2);
+                    for (int idx = threadIdx.x; idx < (int)(w_floats / 4u); idx += GDB_BLOCK) W4[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    w2_clean = true;
+                }
+                gdb_group_sync();  // zero fill / the previous use of W2 is over; p = (x, x) and rhsb visible
+                for (unsigned k2 = ep_lane; k2 < (unsigned)nnz2; k2 += ep_gs) {
+                    const edge_t e2 = g2.edge[g2.rowadj[k2] >> 16];
+                    float *Wk = W2 + wslot[k2];
+                    for (unsigned k1 = ep_grp; k1 < (unsigned)nnz1; k1 += ep_ng) {
+                        const edge_t &e1 = g1.edge[g1.rowadj[k1] >> 16];
+                        float de[GDB_NE];
+                        P.edge_kernel.jacobian(e1.label, e2.label, de);
+                        float dem = 0.f;
+#pragma unroll
+                        for (int k = 0; k < GDB_NE; ++k) dem = (k == ke) ? de[k] : dem;
+#if GDB_WEIGHTED
+                        dem *= e1.weight * e2.weight;
+#endif
+                        Wk[k1 * (unsigned)wstride] = dem;
+                    }
+                }
+                gdb_group_sync();
+#pragma unroll 1
+                for (int i1 = w_row0; i1 < w_row1; ++i1) {
+                    gv_t acc[GDB_WPT];
+                    row_wp(i1, acc, gdb_wdelta{w_floats * 4u});
+#pragma unroll
+                    for (int s = 0; s < GDB_WPT; ++s)
+                        if (GDB_LIVE(s)) {
+                            gv_t cur = rhsb[i1 * n2 + GDB_POS(s)];
+                            if (c == 0) cur.x = acc[s].x; else cur.y = acc[s].y;
+                            rhsb[i1 * n2 + GDB_POS(s)] = cur;
+                        }
+                }
+            }
+#endif
+            gdb_group_sync();  // every read of p = (x, x) is done, rhsb complete
+            // row registers of this round: r = rhs, z = r / diag, p = z, x = 0
+#pragma unroll
+            for (int k = 0; k < GV_N; ++k) rho[k] = 0.f;
+#pragma unroll
+            for (int s = 0; s < GDB_WPT; ++s) {
+#pragma unroll
+                for (int r = 0; r < GDB_RPW; ++r) {
+                    const int i1 = w_row0 + r;
+                    xv[s][r] = gv_make(0.f, 0.f);
+                    rv[s][r] = gv_make(0.f, 0.f);
+                    apv[s][r] = gv_make(0.f, 0.f);
+                    if (GDB_LIVE(s) && i1 < w_row1) {
+                        const gv_t ri = rhsb[i1 * n2 + GDB_POS(s)];
+                        const gv_t z = gv_scale(__fdividef(1.0f, diag[s][r]), ri);
+                        rv[s][r] = ri;
+                        pbuf[i1 * n2 + GDB_POS(s)] = z;
+#pragma unroll
+                        for (int k = 0; k < GV_N; ++k) rho[k] = fmaf(gv_get(ri, k), gv_get(z, k), rho[k]);
+                    }
+                }
+            }
+            gdb_group_sum_n(rho, s_red, flip);  // barrier: p complete
+        }
+#endif
         // ---- Jacobi-PCG, both systems at once ---------------------------------------
         // stop when sqrt(r.r) < ftol N  <=>  r.r < (ftol N)^2; bit k of `active`: system k runs
         const float thresh2 = (F.ftol * (float)N) * (F.ftol * (float)N);
         unsigned active = 0u;
 #pragma unroll
         for (int k = 0; k < GV_N; ++k) active |= (rho[k] != 0.f ? 1u : 0u) << k;
+#if !GDB_NGRAD
         int iters = 0;  // summed over the systems that were still active
+#endif
         for (int it = 0; it < N; ++it) {
             if (active == 0u) break;
             iters += __popc(active);
 
-            // matvec: W p of every owned element, one row of G1 at a time
-            auto row_wp = [&](int i1, gv_t (&acc)[GDB_WPT]) {
-#pragma unroll
-                for (int s = 0; s < GDB_WPT; ++s) acc[s] = gv_make(0.f, 0.f);
-                const uint2 row = gdb_lds_u2(w_rtsa + (unsigned)(i1 - w_row0) * 8u);  // steps of this row
-                GDB_UNROLL(GDB_K1_UNROLL)  // the body is replicated per row already: keep the code in the instruction cache
-                for (unsigned ka = row.x; ka != row.y; ka += 8u) {  // warp-uniform trip count
-                    const uint2 step = gdb_lds_u2(ka);  // (W row, p row)
-#pragma unroll
-                    for (int s = 0; s < GDB_WPT; ++s) {
-                        // All lanes load: empty slots hold W = 0 and point at position 0
-                        // of the p row, unused lanes read lane 0's slots.
-#if GDB_ADJ == 2
-                        const float2 w2 = gdb_lds_f2(step.x + w_woff[s]);
-                        const gv_t p0 = gdb_lds_gv(step.y + w_xoff[s][0]);
-                        const gv_t p1 = gdb_lds_gv(step.y + w_xoff[s][1]);
-                        acc[s] = gv_fma(w2.x, p0, acc[s]);
-                        acc[s] = gv_fma(w2.y, p1, acc[s]);
-#else
-                        const float4 w4 = gdb_lds_f4(step.x + w_woff[s]);
-                        const gv_t p0 = gdb_lds_gv(step.y + w_xoff[s][0]);
-                        const gv_t p1 = gdb_lds_gv(step.y + w_xoff[s][1]);
-                        const gv_t p2 = gdb_lds_gv(step.y + w_xoff[s][2]);
-                        const gv_t p3 = gdb_lds_gv(step.y + w_xoff[s][3]);
-                        acc[s] = gv_fma(w4.x, p0, acc[s]);
-                        acc[s] = gv_fma(w4.y, p1, acc[s]);
-                        acc[s] = gv_fma(w4.z, p2, acc[s]);
-                        acc[s] = gv_fma(w4.w, p3, acc[s]);
-#endif
-                    }
-                }
-                // helpers hand their partial sums to the owning lane (fixed order).  The first
-                // exchange is unconditional -- lanes without a helper add nothing -- so that the
-                // common case of molecular graphs (one helper at most, no overflow) is straight-line
-#pragma unroll
-                for (int s = 0; s < GDB_WPT; ++s) {
-                    const gv_t t = gdb_shfl_vlane(acc, w_help[s] & 0xffffu);
-                    if (w_help[s] >> 16) acc[s] = gv_add(acc[s], t);
-                }
-                if (w_rare) {  // uniform per pair: more helpers per column, or slots without a lane
-#pragma unroll 1
-                    for (unsigned h = 1; h < w_most; ++h) {
-#pragma unroll
-                        for (int s = 0; s < GDB_WPT; ++s) {
-                            const unsigned src = (w_help[s] & 0xffffu) + h;
-                            const gv_t t = gdb_shfl_vlane(acc, src);
-                            if (h < (w_help[s] >> 16)) acc[s] = gv_add(acc[s], t);
-                        }
-                    }
-                    if (w_ovf) {
-#pragma unroll
-                        for (int s = 0; s < GDB_WPT; ++s)
-                            if (GDB_LIVE(s))
-                                acc[s] = gv_add(acc[s], gdb_small_overflow(g1.rowadj, g2.rowptr, g2.rowadj, g2.lanemap, vovf, W, pbuf,
-                                                                           g1.rowptr[i1], g1.rowptr[i1 + 1], (unsigned)wstride, ovf0, (unsigned)n2,
-                                                                           (unsigned)GDB_POS(s),
-                                                                           (1u + (w_help[s] >> 16)) * (unsigned)GDB_ADJ));
-                    }
-                }
-            };
             float pAp[GV_N];
 #pragma unroll
             for (int k = 0; k < GV_N; ++k) pAp[k] = 0.f;
@@ -723,7 +895,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #pragma unroll 1
             for (int i1 = w_row0; i1 < w_row1; ++i1) {
                 gv_t acc[GDB_WPT];
-                row_wp(i1, acc);
+                row_wp(i1, acc, gdb_wzero{});
 #pragma unroll
                 for (int s = 0; s < GDB_WPT; ++s)
                     if (GDB_LIVE(s)) wpbuf[i1 * n2 + GDB_POS(s)] = acc[s];
@@ -736,7 +908,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
                 if (i1 < w_row1) {  // warp-uniform
 #if !GDB_ROLL_ROWS
                     gv_t acc[GDB_WPT];
-                    row_wp(i1, acc);
+                    row_wp(i1, acc, gdb_wzero{});
 #endif
 #pragma unroll
                     for (int s = 0; s < GDB_WPT; ++s) {
@@ -814,12 +986,87 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             gdb_group_sync();  // p complete before the next matvec
         }
 
+#if GDB_NGRAD
+        // publish this round's solutions by node (p is free now) and write the outputs
+        gdb_group_sync();
+        {
+            gv_t *ys = pbuf;
+#pragma unroll
+            for (int s = 0; s < GDB_WPT; ++s) {
+#pragma unroll
+                for (int r = 0; r < GDB_RPW; ++r) {
+                    const int i1 = w_row0 + r;
+                    if (i1 < w_row1 && GDB_LIVE(s)) ys[i1 * n2 + (int)(g2.lanemap[GDB_POS(s)] & 0xffffu)] = xv[s][r];
+                }
+            }
+            gdb_group_sync();
+            for (int i = threadIdx.x; i < N; i += GDB_BLOCK) {
+                const int i1 = i / n2, i2 = i - i1 * n2;
+                const node_t &u1 = g1.node[i1];
+                const node_t &u2 = g2.node[i2];
+                const float p1 = P.p_start(u1), p2 = P.p_start(u2);
+#if GDB_NODAL == 2 || GDB_SYMMETRIC
+                const bool sym = same;  // self pair: bit-exact symmetry of the output
+#else
+                const bool sym = false;
+#endif
+                if (round == 0) {
+                    // the value solve: nodal Gram entries (as the epilogue of the other programs),
+                    // x kept for the sensitivity rounds, explicit d/dp planes
+                    const float xraw = gv_get(ys[i], 0);
+                    Xb[i] = xraw;
+                    float xi = sym ? 0.5f * (xraw + gv_get(ys[i2 * n2 + i1], 0)) : xraw;
+#if GDB_LMIN == 1
+                    xi -= P.node_kernel(u1, u2);
+#endif
+#if GDB_NODAL == 2
+                    F.gram[ngI1 + i1 + i2 * n1] = xi * p1 * p2;
+#elif GDB_DIAGONAL
+                    if (i1 == i2) F.gram[ngI1 + i1] = xi * p1 * p2;
+#else
+                    F.gram[(unsigned long long)(ngI1 + i1) + (unsigned long long)(ngI2 + i2) * F.nX] = xi * p1 * p2;
+#if GDB_SYMMETRIC
+                    if (!same) F.gram[(unsigned long long)(ngI2 + i2) + (unsigned long long)(ngI1 + i1) * F.nX] = xi * p1 * p2;
+#endif
+#endif
+#if GDB_NP > 0
+                    float d1[GDB_NP], d2[GDB_NP];
+                    P.p_start.jacobian(u1, d1);
+                    P.p_start.jacobian(u2, d2);
+#pragma unroll
+                    for (int m = 0; m < GDB_NP; ++m)
+                        write_nodal(i1, i2, m, xi * __fadd_rn(__fmul_rn(d1[m], p2), __fmul_rn(p1, d2[m])));  // no FMA: symmetric under swap
+#endif
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int m = ng_m0 + c;
+                        if (m >= GDB_NJ) continue;
+                        float val = gv_get(ys[i], c);
+                        if (sym) val = 0.5f * (val + gv_get(ys[i2 * n2 + i1], c));
+#if GDB_LMIN == 1 && GDB_NV > 0
+                        if (m > GDB_NP && m < GDB_NP + 1 + GDB_NV) {
+                            float dv[GDB_NV];
+                            P.node_kernel.jacobian(u1, u2, dv);
+#pragma unroll
+                            for (int k = 0; k < GDB_NV; ++k) val -= (k == m - GDB_NP - 1) ? dv[k] : 0.f;
+                        }
+#endif
+                        write_nodal(i1, i2, m, val * p1 * p2);
+                    }
+                }
+            }
+        }
+        }  // rounds
+#endif
+
         if (threadIdx.x == 0) {
             atomicAdd(F.counters + 1, (unsigned long long)iters);
             atomicAdd(F.counters + 2, (unsigned long long)iters * (unsigned long long)nnz1 * (unsigned long long)nnz2);
             atomicAdd(F.counters + 3, (unsigned long long)iters * (unsigned long long)N);
         }
 
+#if !GDB_NGRAD
         const unsigned I1 = F.starts[ja] - F.row0, I2 = F.starts[jb] - F.col0;
         const unsigned long long plane = (unsigned long long)F.nX * F.nY;
         (void)plane;
@@ -1028,6 +1275,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
             }
         }
 #endif
+#endif  // !GDB_NGRAD
     }
 }
 #undef GDB_POS

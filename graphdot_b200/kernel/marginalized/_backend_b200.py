@@ -835,6 +835,10 @@ def preset_sources():
         'c4_convolution': ('C4', conv, T(symmetric=True), (256, 1)),
         'c5_offdiag': ('C2', mol, T(), (128, 1, 6, 2)),
         'c2_nodal': ('C2', mol, T(symmetric=True, nodal=True), (128, 1, 6, 2)),
+        'c2_nodal_grad': ('C2', mol, T(symmetric=True, nodal=True,
+                                       eval_gradient=True), (128, 1, 6, 2)),
+        'c2_nodal_diag_grad': ('C2', mol, T(diagonal=True, nodal=True, lmin=1,
+                                            eval_gradient=True), (128, 1, 6, 2)),
         'c2_wpt2': ('C2', mol, T(symmetric=True), (128, 2)),
     }
     out = {}

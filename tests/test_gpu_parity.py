@@ -153,6 +153,8 @@ def test_nodal_gradient_vs_oracle(mlgk_golden, backend, name, lmin):
     mlgk = MarginalizedGraphKernel(knode, kedge, q=q, p=Uniform(pv),
                                    backend=backend)
     R, dR = mlgk(G, nodal=True, eval_gradient=True, lmin=lmin)
+    # round 2: the sensitivity solves run in the small-pair kernel on the cached W
+    assert backend.last['small_kernel']
     assert dR.shape == (*R.shape, mlgk.active_theta_mask.sum())
     assert np.count_nonzero(dR - dR.transpose(1, 0, 2)) == 0
 
@@ -189,6 +191,33 @@ def test_nodal_gradient_vs_oracle(mlgk_golden, backend, name, lmin):
     D, dD = mlgk.diag(G, nodal=True, eval_gradient=True, lmin=lmin)
     assert np.allclose(D, np.diag(R), rtol=1e-6)
     assert np.allclose(dD, np.einsum('iik->ik', dR), rtol=1e-4, atol=1e-6)
+
+
+def test_nodal_gradient_small_kernel_matches_general_kernel(monkeypatch):
+    """The same nodal Jacobian from the two kernels that implement it: the
+    small-pair kernel (sensitivity rounds on the cached W, two parameters per
+    round) and the general kernel, on molecular graphs incl. nodal='block'."""
+    G = make_config_graphs('C2', 10)
+    be = B200Backend()
+    k1 = make_config_kernel('C3', backend=be)
+    R1, dR1 = k1(G, nodal=True, eval_gradient=True)
+    assert be.last['small_kernel']
+    B1 = k1.diag(G[:4], nodal='block', eval_gradient=False)
+    monkeypatch.setenv('GDB_FORCE_GENERAL', '1')
+    be2 = B200Backend()
+    k2 = make_config_kernel('C3', backend=be2)
+    R2, dR2 = k2(G, nodal=True, eval_gradient=True)
+    assert not be2.last['small_kernel']
+    assert rel_err(R1, R2) < 2e-6
+    for m in range(dR1.shape[2]):
+        assert rel_err(dR1[:, :, m], dR2[:, :, m]) < 2e-5, m
+    B2 = k2.diag(G[:4], nodal='block', eval_gradient=False)
+    assert all(rel_err(a, b) < 2e-6 for a, b in zip(B1, B2))
+    X1, dX1 = k1(G[:3], G[3:7], nodal=True, eval_gradient=True, lmin=1)
+    X2, dX2 = k2(G[:3], G[3:7], nodal=True, eval_gradient=True, lmin=1)
+    assert rel_err(X1, X2) < 2e-6
+    for m in range(dX1.shape[2]):
+        assert rel_err(dX1[:, :, m], dX2[:, :, m]) < 2e-5, m
 
 
 @pytest.mark.parametrize('name', CASES)

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 final single-GPU batch: tests, benches, profiles
-O=gpurun_out/final; mkdir -p $O
+O=gpurun_out/final2; mkdir -p $O
 timeout 1800 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1
 echo "gpu tests rc=$?" | tee $O/status.txt; tail -n 3 $O/pytest_gpu.log
 timeout 600 python bench.py --steps 20 --warmup 3 > $O/bench_n1.json 2> $O/bench_n1.err
