@@ -1026,14 +1026,20 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
         const bool rect = a->job_mode == GDB_JOBS_RECT && !p->diagonal && p->nodal != GDB_NODAL_BLOCK;
         tiles.push_back({a->i0, a->i1, a->j0, a->j1, n_jobs, rect ? col_at(a->j0) : 0, rect ? col_at(a->j1) : a->nY});
     } else if (a->job_mode == GDB_JOBS_TRIU) {
-        for (uint32_t lo = a->i0; lo < a->i1; lo += a->tile) {
-            const uint32_t hi = std::min(a->i1, lo + a->tile);
+        double width = a->tile;
+        for (uint32_t lo = a->i0; lo < a->i1;) {
+            const uint32_t hi = std::min<uint64_t>(a->i1, (uint64_t)lo + std::max<uint32_t>(1u, (uint32_t)width));
             tiles.push_back({lo, hi, lo, a->j1, triu_jobs(lo, hi, a->j1), col_at(lo), col_at(hi)});
+            lo = hi;
+            if (a->tile_shrink > 0.f && a->tile_shrink < 1.f) width = std::max(64.0, width * a->tile_shrink);
         }
     } else {
-        for (uint32_t lo = a->j0; lo < a->j1; lo += a->tile) {
-            const uint32_t hi = std::min(a->j1, lo + a->tile);
+        double width = a->tile;
+        for (uint32_t lo = a->j0; lo < a->j1;) {
+            const uint32_t hi = std::min<uint64_t>(a->j1, (uint64_t)lo + std::max<uint32_t>(1u, (uint32_t)width));
             tiles.push_back({a->i0, a->i1, lo, hi, (uint64_t)(a->i1 - a->i0) * (hi - lo), col_at(lo), col_at(hi)});
+            lo = hi;
+            if (a->tile_shrink > 0.f && a->tile_shrink < 1.f) width = std::max(64.0, width * a->tile_shrink);
         }
     }
     const size_t nt = tiles.size();
@@ -1140,15 +1146,45 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
     if (to_host) RT(cudaEventRecord(c->ev_copy, c->copy_stream));
     if (a->async) return GDB_OK;
 
+    const bool trace = getenv("GDB_TRACE") != nullptr;
+    const auto t_enq = std::chrono::steady_clock::now();
+    auto since = [&](const char *what, size_t t) {
+        if (trace)
+            fprintf(stderr, "[gdb_solve] %-22s tile %zu  +%.2f ms\n", what, t,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enq).count());
+    };
+    since("enqueued", nt);
     std::vector<unsigned long long> counters(nt * 4, 0);
-    RT(cudaMemcpyAsync(counters.data(), c->counters.ptr, nt * 32, cudaMemcpyDeviceToHost, st));
     // ---- collection: convert every finished column block on the host threads ----
     if (to_host && a->out_dtype != GDB_OUT_NONE) {
         gdb_pool *pool = ctx_pool(c);
+        {
+            // The result arrays are usually fresh allocations: fault their pages in NOW, on all
+            // host threads, while the first launch computes -- the conversion passes below then
+            // run at memory bandwidth instead of at page-fault speed (192 MB of float64 for C3:
+            // 47 000 faults).  One store per page; nothing has been converted yet.
+            const size_t esz = a->out_dtype == GDB_OUT_F64 ? 8 : 4, page = 4096;
+            char *bufs[2] = {static_cast<char *>(a->out_gram), static_cast<char *>(a->out_grad)};
+            const size_t lens[2] = {(size_t)plane * esz, a->out_grad ? (size_t)plane * planes.size() * esz : 0};
+            for (int b = 0; b < 2; ++b) {
+                if (!bufs[b] || !lens[b]) continue;
+                char *base = bufs[b];
+                const size_t n_pages = (lens[b] + page - 1) / page, per = 256;
+                const size_t len = lens[b];
+                pool->parallel_for((n_pages + per - 1) / per, [=](size_t part) {
+                    for (size_t pg = part * per; pg < std::min(n_pages, (part + 1) * per); ++pg) {
+                        volatile char *q = base + std::min(pg * page, len - 1);
+                        *q = 0;
+                    }
+                });
+            }
+        }
         for (size_t t = 0; t < nt; ++t) {
             const Tile &T = tiles[t];
             if (T.c1 <= T.c0) continue;
+            if (t == 0) since("pages touched", t);
             RT(cudaEventSynchronize(c->tile_ev[2 * t + 1]));
+            since("block on host", t);
             const uint64_t off = T.c0 * a->nX, cnt = (T.c1 - T.c0) * a->nX;
             // one parallel pass over (planes x chunks) of this column block
             const size_t chunk = 1u << 15, per_plane = (size_t)((cnt + chunk - 1) / chunk);
@@ -1171,8 +1207,13 @@ extern "C" int gdb_solve(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, gd
             });
         }
     }
+    since("collected", nt);
+    // (the diagnostics counters come back last: a copy into pageable memory blocks the host
+    // until the stream gets there, which would serialise the collection behind the kernels)
+    RT(cudaMemcpyAsync(counters.data(), c->counters.ptr, nt * 32, cudaMemcpyDeviceToHost, st));
     RT(cudaStreamSynchronize(st));
     if (to_host) RT(cudaStreamSynchronize(c->copy_stream));
+    since("synchronized", nt);
     RT(cudaGetLastError());
     cudaEventElapsedTime(&a->h2d_ms, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&a->kernel_ms, c->ev[1], c->ev[2]);

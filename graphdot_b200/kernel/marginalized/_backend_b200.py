@@ -668,7 +668,8 @@ class B200Backend(Backend):
     def launch(self, gs, prog, node_kernel, edge_kernel, p, q, eps, ftol,
                gtol, jobs, starts, gramian, gradient, nX, nY, nJ, row0=0,
                col0=0, stream=None, keep_on_device=False, upload=False,
-               store_diag=False, normalize=False, tile=0, collect=None,
+               store_diag=False, normalize=False, tile=0, tile_shrink=0.0,
+               collect=None,
                gramian_dev=None, gradient_dev=None, async_=False):
         """One ``gdb_solve`` call.  ``jobs`` is an explicit (i, j) array or a
         ``PairJobs`` grid descriptor (no per-pair host data)."""
@@ -705,6 +706,7 @@ class B200Backend(Backend):
         a.gramian_dev = gramian_dev
         a.gradient_dev = gradient_dev
         a.tile = int(tile or 0)
+        a.tile_shrink = float(tile_shrink or 0.0)
         a.async_ = int(bool(async_))
         if collect is not None:
             a.out_dtype = collect.code
@@ -790,13 +792,20 @@ class Collect:
             self.code = native.OUT_F32
         else:
             raise TypeError(f'collection into {dtype} is not supported')
-        self.gram = np.empty((rows, cols), dtype=dtype, order='F')
+        # Result arrays come from the pooled page-locked allocator: fresh
+        # numpy allocations are mmap'ed, and faulting in the 192 MB of a C3
+        # result (47 000 pages) took ~94 ms on the GPU box -- longer than the
+        # solve.  Pooled blocks keep their pages; an array returns its block
+        # to the pool when the caller drops it.
+        self.gram = native.pinned_empty(rows * cols, dtype).reshape(
+            (rows, cols), order='F')
         self.mask = self.grad = None
         if n_jac:
             mask = np.ascontiguousarray(mask, dtype=np.uint8)
             self.mask = mask
-            self.grad = np.empty((rows, cols, int(mask.sum())), dtype=dtype,
-                                 order='F')
+            k = int(mask.sum())
+            self.grad = native.pinned_empty(rows * cols * k, dtype).reshape(
+                (rows, cols, k), order='F')
 
 
 B200Backend.collect = Collect

@@ -230,10 +230,9 @@ class MarginalizedGraphKernel:
                 extra_out['collect'] = coll
             if make is not None and len(pairs) >= 65536:
                 # pipeline: a handful of launches, copy-back and collection
-                # of a finished column block overlap the next launch (C3 on
-                # a B200, end to end: 4 launches 103.9 ms, 6: 104.4, 8: 105.2,
-                # 12: 106.7 -- every launch has a tail, the last block's
-                # copy and conversion are exposed)
+                # of a finished column block overlap the next launch.
+                # (C3 on a B200, end to end: 4 uniform launches 103.9 ms, 8:
+                # 105.2, 12: 106.7; shrinking launch sizes did not help.)
                 n_launch = int(os.environ.get('GDB_PIPELINE_LAUNCHES', 4))
                 extra_out['tile'] = max(32, -(-(nx if traits.symmetric
                                                 else ny) // n_launch))

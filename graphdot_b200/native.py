@@ -107,7 +107,8 @@ class SolveArgs(C.Structure):
                 ('upload_graphs', C.c_int32),
                 ('stream', C.c_void_p), ('keep_on_device', C.c_int32),
                 ('gramian_dev', C.c_void_p), ('gradient_dev', C.c_void_p),
-                ('tile', C.c_uint32), ('out_dtype', C.c_int32),
+                ('tile', C.c_uint32), ('tile_shrink', C.c_float),
+                ('out_dtype', C.c_int32),
                 ('out_gram', C.c_void_p), ('out_grad', C.c_void_p),
                 ('plane_mask', C.c_void_p), ('async_', C.c_int32),
                 ('kernel_ms', C.c_float), ('h2d_ms', C.c_float),

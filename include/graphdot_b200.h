@@ -284,6 +284,11 @@ typedef struct gdb_solve_args {
      * COLUMNS, whose device->host copy (on a second stream) and host-side
      * collection overlap the next launch.                                  */
     uint32_t tile;
+    float tile_shrink;        /* 0 or 1: all launches `tile` wide; 0 < s < 1:
+                                 every launch s times the previous one (at
+                                 least 64): big launches first, so that the
+                                 copy and collection of the LAST, exposed
+                                 column block are short                    */
     /* Host-side collection, fused with the copy-back (replaces the
      * reshape / active-theta masking / astype of reference
      * _kernel.py:247-264, which is a serial numpy pass over 4(1+nJ) B per
