@@ -130,6 +130,13 @@ def pair_system(g1, g2, knode, kedge, q, jac=False, sparse=False):
     return out
 
 
+def _unit_start(nodes):
+    """Default starting probability p = 1 on every node (reference
+    starting_probability.py:80-81): value and d/dp, evaluated here so that the
+    oracle does not lean on the product's implementation."""
+    return np.ones(len(nodes)), np.ones((1, len(nodes)))
+
+
 def _start_prob(p, g):
     vals, dvals = p(g.nodes)
     order = np.argsort(np.asarray(g.nodes['!i']))
@@ -144,8 +151,7 @@ def solve_pair(g1, g2, knode, kedge, q, p=None, lmin=0,
     """Nodal solution matrix R (n1, n2) with starting probabilities applied,
     graph-level K = R.sum(), and with ``eval_gradient`` the Jacobian of K in
     the order [p..., q, node..., edge...]."""
-    from graphdot_b200.kernel.marginalized.starting_probability import Uniform
-    p = Uniform(1.0) if p is None else p
+    p = _unit_start if p is None else p
     if sparse is None:
         sparse = len(g1.nodes) * len(g2.nodes) > 3000
     s = pair_system(g1, g2, knode, kedge, q, jac=eval_gradient, sparse=sparse)

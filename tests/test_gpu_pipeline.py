@@ -328,3 +328,41 @@ def test_large_pair_kernel_rare_paths_vs_general_kernel(monkeypatch, p_edge,
     if grad:
         assert np.allclose(sym[1][0, 3], go, rtol=GRAD_RTOL,
                            atol=GRAD_RTOL * np.abs(go).max())
+
+
+def test_large_pair_kernel_mixed_sizes_and_isolated_nodes(monkeypatch):
+    """One graph set with 5 ... 260 nodes (fewer tile rows than CTAs in a
+    cluster, sizes that are no multiple of 8 or 32) and a graph with isolated
+    nodes (degree 0 -> 1, reference _octilegraph.py:139; rows and columns
+    without elements): the cluster kernel equals the general kernel."""
+    from graphdot_b200.graph import DataFrame
+    from graphdot_b200.synthetic import newman_watts_strogatz
+    G = [newman_watts_strogatz(np.random.default_rng(s), n)
+         for s, n in ((1, 5), (2, 9), (3, 33), (4, 260), (5, 203))]
+    # append three isolated nodes to the 33-node graph
+    g = G[2]
+    n = len(g.nodes)
+    feat = np.empty(n + 3, dtype=object)
+    for i in range(n):
+        feat[i] = np.asarray(g.nodes['feat'][i])
+    for i in range(3):
+        feat[n + i] = np.full(8, 0.1 * (i + 1), dtype=np.float32)
+    nodes = DataFrame()
+    nodes['!i'] = np.arange(n + 3, dtype=np.uint32)
+    nodes['feat'] = feat
+    G[2] = type(g)(nodes, g.edges, title='isolated')
+    be = B200Backend()
+    kernel = make_config_kernel('C4', backend=be)
+    K, dK = kernel(G, eval_gradient=True)
+    assert be.last['kernel'] == 'mlgk_solve_large'
+    Kxy = kernel(G[:2], G[2:])
+    monkeypatch.setenv('GDB_FORCE_GENERAL', '1')
+    be2 = B200Backend()
+    kernel2 = make_config_kernel('C4', backend=be2)
+    K2, dK2 = kernel2(G, eval_gradient=True)
+    assert be2.last['kernel'] == 'mlgk_solve'
+    assert np.allclose(K, K2, rtol=5e-6)
+    for m in range(dK.shape[2]):
+        assert rel_err(dK[:, :, m], dK2[:, :, m]) < 2e-5
+    assert np.allclose(Kxy, kernel2(G[:2], G[2:]), rtol=5e-6)
+    assert np.array_equal(K, K.T)
