@@ -350,3 +350,165 @@ extern "C" int gdb_graphs_pack_batch(const gdb_layout *L, const gdb_batch_src *s
         return gdb_graph_pack(L, &s, static_cast<uint8_t *>(blobs) + blob_off[g], blob_off[g + 1] - blob_off[g]);
     });
 }
+
+// ---------------------------------------------------------------------------
+// node reordering (host): permutations for Graph.permute that shrink the tile
+// footprint of a graph.  Replaces reference graphdot/graph/reorder/rcm.py:7-22
+// (scipy) and plays the role of reference graphdot/graph/reorder/pbr (a
+// hypergraph partitioner around kahypar that minimises non-empty 8 x 8 tiles,
+// pbr/mnom.py:11-24) with a native greedy tile-growing partition.
+// ---------------------------------------------------------------------------
+namespace {
+
+struct Csr {
+    std::vector<uint32_t> ptr, adj;
+};
+
+bool build_csr(uint32_t n, uint32_t m, const uint32_t *ei, const uint32_t *ej, Csr &g) {
+    g.ptr.assign(n + 1, 0);
+    for (uint32_t k = 0; k < m; ++k) {
+        if (ei[k] >= n || ej[k] >= n) return false;
+        if (ei[k] == ej[k]) continue;
+        g.ptr[ei[k] + 1]++;
+        g.ptr[ej[k] + 1]++;
+    }
+    for (uint32_t i = 0; i < n; ++i) g.ptr[i + 1] += g.ptr[i];
+    g.adj.resize(g.ptr[n]);
+    std::vector<uint32_t> fill(g.ptr.begin(), g.ptr.end() - 1);
+    for (uint32_t k = 0; k < m; ++k) {
+        if (ei[k] == ej[k]) continue;
+        g.adj[fill[ei[k]]++] = ej[k];
+        g.adj[fill[ej[k]]++] = ei[k];
+    }
+    return true;
+}
+
+// reverse Cuthill-McKee: BFS from a low-degree node of every component, neighbours by
+// increasing degree, order reversed
+void order_rcm(uint32_t n, const Csr &g, uint32_t *perm) {
+    auto deg = [&](uint32_t v) { return g.ptr[v + 1] - g.ptr[v]; };
+    std::vector<uint32_t> by_degree(n), order;
+    std::vector<char> seen(n, 0);
+    for (uint32_t i = 0; i < n; ++i) by_degree[i] = i;
+    std::stable_sort(by_degree.begin(), by_degree.end(), [&](uint32_t a, uint32_t b) { return deg(a) < deg(b); });
+    order.reserve(n);
+    std::vector<uint32_t> nb;
+    for (uint32_t s : by_degree) {
+        if (seen[s]) continue;
+        seen[s] = 1;
+        size_t head = order.size();
+        order.push_back(s);
+        while (head < order.size()) {
+            const uint32_t v = order[head++];
+            nb.clear();
+            for (uint32_t k = g.ptr[v]; k < g.ptr[v + 1]; ++k)
+                if (!seen[g.adj[k]]) {
+                    seen[g.adj[k]] = 1;
+                    nb.push_back(g.adj[k]);
+                }
+            std::stable_sort(nb.begin(), nb.end(), [&](uint32_t a, uint32_t b) { return deg(a) < deg(b); });
+            order.insert(order.end(), nb.begin(), nb.end());
+        }
+    }
+    for (uint32_t k = 0; k < n; ++k) perm[k] = order[n - 1 - k];
+}
+
+// greedy tile growing: fill one block of 8 nodes at a time with the unassigned node that
+// has the most neighbours in the block (ties: in the previous block, then the smaller
+// degree); a new block is seeded next to the previous one.  Neighbourhoods end up inside
+// a tile row / the adjacent one, i.e. few non-empty 8 x 8 tiles.
+void order_tiles(uint32_t n, const Csr &g, uint32_t *perm) {
+    auto deg = [&](uint32_t v) { return g.ptr[v + 1] - g.ptr[v]; };
+    std::vector<int> in_cur(n, 0), in_prev(n, 0);  // neighbours in the current / previous block
+    std::vector<char> done(n, 0);
+    std::vector<uint32_t> touched, prev_block, block;
+    uint32_t placed = 0;
+    while (placed < n) {
+        block.clear();
+        for (int slot = 0; slot < 8 && placed < n; ++slot) {
+            // candidates: unassigned nodes adjacent to the current or the previous block
+            long best = -1;
+            long best_key = -1;
+            for (uint32_t v : touched) {
+                if (done[v]) continue;
+                const long key = (long)in_cur[v] * 4096 * 64 + (long)in_prev[v] * 4096 + (4095 - (long)std::min<uint32_t>(deg(v), 4095));
+                if (key > best_key) {
+                    best_key = key;
+                    best = v;
+                }
+            }
+            if (best < 0) {  // nothing adjacent: the unassigned node of smallest degree
+                uint32_t bd = ~0u;
+                for (uint32_t v = 0; v < n; ++v)
+                    if (!done[v] && deg(v) < bd) {
+                        bd = deg(v);
+                        best = v;
+                    }
+            }
+            const uint32_t v = (uint32_t)best;
+            done[v] = 1;
+            perm[placed++] = v;
+            block.push_back(v);
+            for (uint32_t k = g.ptr[v]; k < g.ptr[v + 1]; ++k) {
+                const uint32_t u = g.adj[k];
+                if (!in_cur[u] && !in_prev[u]) touched.push_back(u);
+                in_cur[u]++;
+            }
+        }
+        // the finished block becomes the previous one
+        for (uint32_t v : prev_block)
+            for (uint32_t k = g.ptr[v]; k < g.ptr[v + 1]; ++k) in_prev[g.adj[k]]--;
+        for (uint32_t v : block)
+            for (uint32_t k = g.ptr[v]; k < g.ptr[v + 1]; ++k) {
+                in_cur[g.adj[k]]--;
+                in_prev[g.adj[k]]++;
+            }
+        prev_block = block;
+        std::vector<uint32_t> keep;
+        for (uint32_t u : touched)
+            if (!done[u] && (in_cur[u] || in_prev[u])) keep.push_back(u);
+        std::sort(keep.begin(), keep.end());
+        keep.erase(std::unique(keep.begin(), keep.end()), keep.end());
+        touched.swap(keep);
+    }
+}
+
+}  // namespace
+
+extern "C" int gdb_graph_reorder(uint32_t n_node, uint32_t n_edge, const uint32_t *edge_i, const uint32_t *edge_j,
+                                 int32_t method, uint32_t *perm) {
+    if (!n_node || !perm || (n_edge && (!edge_i || !edge_j))) return gdb_fail(GDB_ERR_INVALID, "gdb_graph_reorder: null argument");
+    Csr g;
+    if (!build_csr(n_node, n_edge, edge_i, edge_j, g)) return gdb_fail(GDB_ERR_INVALID, "edge end point out of range");
+    if (method == GDB_REORDER_RCM)
+        order_rcm(n_node, g, perm);
+    else if (method == GDB_REORDER_TILES)
+        order_tiles(n_node, g, perm);
+    else
+        return gdb_fail(GDB_ERR_INVALID, "unknown reordering method %d", method);
+    return GDB_OK;
+}
+
+extern "C" int gdb_graph_count_tiles(uint32_t n_node, uint32_t n_edge, const uint32_t *edge_i, const uint32_t *edge_j,
+                                     const uint32_t *perm, uint64_t *n_tiles) {
+    if (!n_tiles || (n_edge && (!edge_i || !edge_j))) return gdb_fail(GDB_ERR_INVALID, "gdb_graph_count_tiles: null argument");
+    std::vector<uint32_t> inv;
+    if (perm) {
+        inv.resize(n_node);
+        for (uint32_t k = 0; k < n_node; ++k) {
+            if (perm[k] >= n_node) return gdb_fail(GDB_ERR_INVALID, "perm is not a permutation");
+            inv[perm[k]] = k;  // new index of old node perm[k] is k (Graph.permute)
+        }
+    }
+    std::vector<uint64_t> keys;
+    keys.reserve(2 * (size_t)n_edge);
+    for (uint32_t k = 0; k < n_edge; ++k) {
+        if (edge_i[k] >= n_node || edge_j[k] >= n_node) return gdb_fail(GDB_ERR_INVALID, "edge end point out of range");
+        const uint64_t i = perm ? inv[edge_i[k]] : edge_i[k], j = perm ? inv[edge_j[k]] : edge_j[k];
+        keys.push_back((i >> 3) << 32 | (j >> 3));
+        keys.push_back((j >> 3) << 32 | (i >> 3));
+    }
+    std::sort(keys.begin(), keys.end());
+    *n_tiles = (uint64_t)(std::unique(keys.begin(), keys.end()) - keys.begin());
+    return GDB_OK;
+}

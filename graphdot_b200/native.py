@@ -150,6 +150,10 @@ SYMBOLS = [
                                  C.c_uint64]),
     ('gdb_graphs_pack_batch', C.c_int, [C.POINTER(Layout), C.POINTER(BatchSrc),
                                         _P, _P, C.c_uint64, C.c_int32]),
+    ('gdb_graph_reorder', C.c_int, [C.c_uint32, C.c_uint32, _P, _P, C.c_int32,
+                                    _P]),
+    ('gdb_graph_count_tiles', C.c_int, [C.c_uint32, C.c_uint32, _P, _P, _P,
+                                        C.POINTER(C.c_uint64)]),
     ('gdb_graphset_create', C.c_int, [_P, C.POINTER(Layout), C.c_uint32,
                                       C.POINTER(_P), C.POINTER(C.c_uint64),
                                       C.POINTER(_P)]),

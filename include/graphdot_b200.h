@@ -221,6 +221,23 @@ int gdb_graphs_pack_batch(const gdb_layout *layout, const gdb_batch_src *src,
                           uint64_t *blob_off, void *blobs, uint64_t capacity,
                           int32_t n_threads);
 
+/* Node reordering (pure host): a permutation for Graph.permute -- new index
+ * of old node perm[k] is k -- that shrinks the tile footprint of a graph.
+ * GDB_REORDER_RCM: reverse Cuthill-McKee (replaces reference
+ * graphdot/graph/reorder/rcm.py:7-22).  GDB_REORDER_TILES: greedy growth of
+ * 8-node blocks, the role of the reference's partition-based reordering
+ * (graphdot/graph/reorder/pbr, which minimises non-empty 8 x 8 tiles with a
+ * hypergraph partitioner, pbr/mnom.py:11-24).  gdb_graph_count_tiles counts
+ * the non-empty 8 x 8 tiles of the symmetric adjacency, optionally after a
+ * permutation (perm may be NULL). */
+#define GDB_REORDER_RCM 0
+#define GDB_REORDER_TILES 1
+int gdb_graph_reorder(uint32_t n_node, uint32_t n_edge, const uint32_t *edge_i,
+                      const uint32_t *edge_j, int32_t method, uint32_t *perm);
+int gdb_graph_count_tiles(uint32_t n_node, uint32_t n_edge,
+                          const uint32_t *edge_i, const uint32_t *edge_j,
+                          const uint32_t *perm, uint64_t *n_tiles);
+
 /* Assemble packed blobs into one device-resident graph set. */
 int gdb_graphset_create(gdb_context_t ctx, const gdb_layout *layout,
                         uint32_t n_graphs, const void *const *blobs,

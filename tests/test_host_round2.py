@@ -245,3 +245,56 @@ def test_tf32_separable_study_conclusion():
     # operands that ARE representable (0/1 adjacency, constant vectors of the
     # closed-form C1 solution) hide the problem: no evidence either way
     assert mod.study(n_pairs=8, q=0.05)['tf32x1']['within_1e5']
+
+
+def test_native_reorderings_are_permutations_and_shrink_the_tile_count():
+    """reference graph/reorder/rcm.py:7-22 and graph/reorder/pbr/__init__.py:
+    11-33: both return a permutation for Graph.permute.  On shuffled C4-like
+    small-world graphs the tile-growing order brings the number of non-empty
+    8 x 8 tiles back to (at most 5 % above) the generator's natural ring order
+    and beats RCM; the native RCM is as good as scipy's; the native tile count
+    agrees with packing the permuted graph."""
+    import scipy.sparse.csgraph
+    from graphdot_b200.reorder import octile_count, pbr, rcm
+    from graphdot_b200.synthetic import make_config_graphs
+    rng = np.random.default_rng(3)
+    natural = make_config_graphs('C4', 6)
+    shuffled = [g.permute(rng.permutation(len(g.nodes))) for g in natural]
+    n_nat = sum(octile_count(g) for g in natural)
+    n_shuf = sum(octile_count(g) for g in shuffled)
+    n_rcm = n_pbr = n_scipy = 0
+    for g in shuffled:
+        n = len(g.nodes)
+        pr, pp = rcm(g), pbr(g)
+        assert sorted(pr.tolist()) == list(range(n))
+        assert sorted(pp.tolist()) == list(range(n))
+        n_rcm += octile_count(g, pr)
+        n_pbr += octile_count(g, pp)
+        n_scipy += octile_count(g, scipy.sparse.csgraph.reverse_cuthill_mckee(
+            g.adjacency_matrix.tocsr(), symmetric_mode=True))
+        assert octile_count(g.permute(pp)) == octile_count(g, pp)
+    assert n_rcm <= 1.05 * n_scipy
+    assert n_pbr <= 1.05 * n_nat
+    assert n_pbr < n_rcm < 0.5 * n_shuf
+
+
+def test_reorder_rejects_bad_input_and_handles_isolated_nodes():
+    from graphdot_b200 import native
+    from graphdot_b200.reorder import octile_count, pbr, rcm
+    from graphdot_b200.graph import Graph
+    import pandas as pd
+    g = Graph(nodes=pd.DataFrame({'!i': np.arange(11), 'f': np.zeros(11)}),
+              edges=pd.DataFrame({'!i': [0, 9], '!j': [9, 3],
+                                  '!w': [1.0, 1.0]}))
+    for f in (rcm, pbr):
+        p = f(g)
+        assert sorted(p.tolist()) == list(range(11))
+        assert octile_count(g, p) <= octile_count(g)
+    lib = native.load()
+    ei = np.array([0, 20], dtype=np.uint32)
+    ej = np.array([1, 2], dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    assert lib.gdb_graph_reorder(4, 2, ei.ctypes.data, ej.ctypes.data, 0,
+                                 out.ctypes.data) != 0
+    assert lib.gdb_graph_reorder(4, 1, ei.ctypes.data, ej.ctypes.data, 7,
+                                 out.ctypes.data) != 0

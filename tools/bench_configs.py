@@ -42,7 +42,8 @@ def main():
     ap.add_argument('--only', default='')
     ap.add_argument('--c4-grad', action='store_true')
     ap.add_argument('--c4-order', default='natural',
-                    choices=['natural', 'rcm', 'random'],
+                    choices=['natural', 'rcm', 'random', 'random+rcm',
+                             'random+pbr'],
                     help='node order of the C4 graphs (sensitivity of the '
                          'large-pair kernel to the tile structure)')
     args = ap.parse_args()
@@ -83,11 +84,17 @@ def main():
     if not only or 'C4' in only:
         G = make_config_graphs('C4', args.c4_graphs)
         if args.c4_order != 'natural':
-            from graphdot_b200.reorder import octile_count, rcm
+            from graphdot_b200.reorder import octile_count, pbr, rcm
             rng = np.random.default_rng(0)
             before = sum(octile_count(g) for g in G)
-            G = [g.permute(rcm(g) if args.c4_order == 'rcm'
-                           else rng.permutation(len(g.nodes))) for g in G]
+            if args.c4_order == 'rcm':
+                G = [g.permute(rcm(g)) for g in G]
+            else:
+                G = [g.permute(rng.permutation(len(g.nodes))) for g in G]
+                if args.c4_order.endswith('+rcm'):
+                    G = [g.permute(rcm(g)) for g in G]
+                elif args.c4_order.endswith('+pbr'):
+                    G = [g.permute(pbr(g)) for g in G]
             print(json.dumps(dict(order=args.c4_order, octiles_before=before,
                                   octiles_after=sum(octile_count(g)
                                                     for g in G))), flush=True)
