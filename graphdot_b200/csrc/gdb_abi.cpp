@@ -246,7 +246,13 @@ extern "C" int gdb_host_unregister(void *p) {
 // ---------------------------------------------------------------------------
 struct gdb_program_s {
     gdb_context_t ctx = nullptr;
-    CUmodule mod = nullptr;
+    // one NVRTC module per kernel: the general and the small-pair kernel are compiled
+    // concurrently when the program is created; the large-pair kernel (80 % of the
+    // compile time of the whole template) only when a graph set first needs it
+    CUmodule mod = nullptr, mod_small = nullptr, mod_large = nullptr;
+    std::string extra;
+    std::mutex large_mu;
+    bool large_tried = false;
     CUfunction fn = nullptr;        // mlgk_solve: any pair size
     CUfunction fn_small = nullptr;  // mlgk_solve_small: pair resident in shared memory
     CUfunction fn_large = nullptr;  // mlgk_solve_large: one cluster per pair (graph-level outputs)
@@ -370,12 +376,13 @@ extern "C" int gdb_render_source(const gdb_program_desc *d, char **out) {
     return GDB_OK;
 }
 
-static int compile_cubin(const std::string &src, const char *extra, std::vector<char> &cubin, std::string &log) {
+static int compile_cubin(const std::string &src, const char *extra, int mask, std::vector<char> &cubin, std::string &log) {
     nvrtcProgram prog;
     nvrtcResult r = nvrtcCreateProgram(&prog, src.c_str(), "mlgk_solver.cu", 0, nullptr, nullptr);
     if (r != NVRTC_SUCCESS) return gdb_fail(GDB_ERR_COMPILE, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "--use_fast_math", "-lineinfo",
                                      "-default-device", "--extra-device-vectorization"};
+    opts.push_back("-DGDB_BUILD_MASK=" + std::to_string(mask));
     if (extra) {
         std::istringstream is(extra);
         std::string tok;
@@ -400,13 +407,31 @@ static int compile_cubin(const std::string &src, const char *extra, std::vector<
     return GDB_OK;
 }
 
+// kernels 0..n-1 (masks 1, 2, 4) compiled on their own threads; the error text of a thread
+// is carried back explicitly because gdb_last_error is per thread
+static void compile_parallel(const std::string &src, const char *extra, int n, std::vector<char> *cubin,
+                             std::string *logs, int *rcs, std::string *errs) {
+    std::vector<std::thread> th;
+    for (int k = 0; k < n; ++k)
+        th.emplace_back([&, k] {
+            rcs[k] = compile_cubin(src, extra, 1 << k, cubin[k], logs[k]);
+            if (rcs[k]) errs[k] = gdb_last_error();
+        });
+    for (auto &t : th) t.join();
+}
+
 extern "C" int gdb_program_compile_only(const gdb_program_desc *d, uint64_t *cubin_bytes) {
     std::string src, log;
     int rc = render(d, src);
     if (rc) return rc;
-    std::vector<char> cubin;
-    if ((rc = compile_cubin(src, d->extra_options, cubin, log))) return rc;
-    if (cubin_bytes) *cubin_bytes = cubin.size();
+    std::vector<char> cubin[3];
+    std::string logs[3], errs[3];
+    int rcs[3] = {0, 0, 0};
+    const int n = d->nodal == GDB_NODAL_NONE ? 3 : 2;
+    compile_parallel(src, d->extra_options, n, cubin, logs, rcs, errs);
+    for (int k = 0; k < n; ++k)
+        if (rcs[k]) return gdb_fail(rcs[k], "%s", errs[k].c_str());
+    if (cubin_bytes) *cubin_bytes = cubin[0].size() + cubin[1].size() + cubin[2].size();
     return GDB_OK;
 }
 
@@ -428,13 +453,17 @@ extern "C" int gdb_program_create(gdb_context_t c, const gdb_program_desc *d, gd
     }
     RT(cudaSetDevice(c->device));
     auto t0 = std::chrono::steady_clock::now();
-    std::vector<char> cubin;
-    std::string log;
-    if ((rc = compile_cubin(src, d->extra_options, cubin, log))) return rc;
+    std::vector<char> cubin[2];
+    std::string logs[2], errs[2];
+    int rcs[2] = {0, 0};
+    compile_parallel(src, d->extra_options, 2, cubin, logs, rcs, errs);
+    for (int k = 0; k < 2; ++k)
+        if (rcs[k]) return gdb_fail(rcs[k], "%s", errs[k].c_str());
     gdb_program_s *p = new gdb_program_s;
     p->ctx = c;
     p->source = src;
-    p->log = log;
+    p->extra = d->extra_options ? d->extra_options : "";
+    p->log = logs[0] + logs[1];
     p->eval_gradient = d->eval_gradient;
     p->nodal = d->nodal;
     p->symmetric = d->symmetric ? 1 : 0;
@@ -445,7 +474,8 @@ extern "C" int gdb_program_create(gdb_context_t c, const gdb_program_desc *d, gd
     p->theta_size[0] = d->node_kernel.theta_size;
     p->theta_size[1] = d->edge_kernel.theta_size;
     p->theta_size[2] = d->p_start.theta_size;
-    DRV(c, c->cuModuleLoadData(&p->mod, cubin.data()));
+    DRV(c, c->cuModuleLoadData(&p->mod, cubin[0].data()));
+    DRV(c, c->cuModuleLoadData(&p->mod_small, cubin[1].data()));
     DRV(c, c->cuModuleGetFunction(&p->fn, p->mod, "mlgk_solve"));
     CUdeviceptr lay = 0;
     size_t lay_bytes = 0;
@@ -466,7 +496,7 @@ extern "C" int gdb_program_create(gdb_context_t c, const gdb_program_desc *d, gd
     p->info.local_bytes = v;
     p->info.max_dynamic_smem = (int)c->prop.sharedMemPerBlockOptin - p->info.static_smem;
     DRV(c, c->cuFuncSetAttribute(p->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, p->info.max_dynamic_smem));
-    DRV(c, c->cuModuleGetFunction(&p->fn_small, p->mod, "mlgk_solve_small"));
+    DRV(c, c->cuModuleGetFunction(&p->fn_small, p->mod_small, "mlgk_solve_small"));
     c->cuFuncGetAttribute(&p->small_regs, CU_FUNC_ATTRIBUTE_NUM_REGS, p->fn_small);
     c->cuFuncGetAttribute(&p->small_static_smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, p->fn_small);
     DRV(c, c->cuFuncSetAttribute(p->fn_small, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
@@ -476,26 +506,6 @@ extern "C" int gdb_program_create(gdb_context_t c, const gdb_program_desc *d, gd
     p->lcpt = pick_lcpt(d);
     p->lell = pick_lell(d);
     p->edge_size = p->layout[6];
-    if (d->nodal == GDB_NODAL_NONE) {
-        DRV(c, c->cuModuleGetFunction(&p->fn_large, p->mod, "mlgk_solve_large"));
-        {
-            CUdeviceptr ll = 0;
-            size_t ll_bytes = 0;
-            unsigned vals[3] = {0, 0, 0};
-            DRV(c, c->cuModuleGetGlobal(&ll, &ll_bytes, p->mod, "gdb_large_layout"));
-            if (ll_bytes != sizeof vals) return gdb_fail(GDB_ERR_LAYOUT, "gdb_large_layout has %zu bytes", ll_bytes);
-            RT(cudaMemcpy(vals, reinterpret_cast<void *>(ll), sizeof vals, cudaMemcpyDeviceToHost));
-            p->ell_entry = vals[0];
-            p->large_block = vals[1];
-            p->large_ltr = vals[2];
-        }
-        int v2 = 0;
-        c->cuFuncGetAttribute(&v2, CU_FUNC_ATTRIBUTE_NUM_REGS, p->fn_large);
-        p->info.num_regs_large = v2;
-        c->cuFuncGetAttribute(&p->large_static_smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, p->fn_large);
-        DRV(c, c->cuFuncSetAttribute(p->fn_large, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
-                                     (int)c->prop.sharedMemPerBlockOptin - p->large_static_smem));
-    }
     p->info.n_jac = (int)p->layout[7];
     p->info.from_cache = 0;
     p->info.compile_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -519,7 +529,8 @@ extern "C" const char *gdb_program_source(gdb_program_t p) { return p ? p->sourc
 extern "C" int gdb_program_destroy(gdb_program_t p) {
     if (!p) return GDB_OK;
     if (--p->refcount > 0) return GDB_OK;
-    if (p->mod && p->ctx) p->ctx->cuModuleUnload(p->mod);
+    for (CUmodule m : {p->mod, p->mod_small, p->mod_large})
+        if (m && p->ctx) p->ctx->cuModuleUnload(m);
     delete p;
     return GDB_OK;
 }
@@ -781,6 +792,42 @@ uint64_t triu_jobs(uint64_t lo, uint64_t hi, uint64_t j1) {
 
 }  // namespace
 
+// compile and load the large-pair kernel the first time a graph set needs it (graph-level
+// outputs only).  A failure is reported once; later solves fall back to the general kernel.
+static int ensure_large(gdb_context_t c, gdb_program_t p) {
+    if (p->nodal != GDB_NODAL_NONE) return GDB_OK;
+    std::lock_guard<std::mutex> lk(p->large_mu);
+    if (p->large_tried) return GDB_OK;
+    p->large_tried = true;
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<char> cubin;
+    std::string log;
+    int rc = compile_cubin(p->source, p->extra.empty() ? nullptr : p->extra.c_str(), 4, cubin, log);
+    if (rc) return rc;
+    p->log += log;
+    CUfunction fn = nullptr;
+    DRV(c, c->cuModuleLoadData(&p->mod_large, cubin.data()));
+    DRV(c, c->cuModuleGetFunction(&fn, p->mod_large, "mlgk_solve_large"));
+    CUdeviceptr ll = 0;
+    size_t ll_bytes = 0;
+    unsigned vals[3] = {0, 0, 0};
+    DRV(c, c->cuModuleGetGlobal(&ll, &ll_bytes, p->mod_large, "gdb_large_layout"));
+    if (ll_bytes != sizeof vals) return gdb_fail(GDB_ERR_LAYOUT, "gdb_large_layout has %zu bytes", ll_bytes);
+    RT(cudaMemcpy(vals, reinterpret_cast<void *>(ll), sizeof vals, cudaMemcpyDeviceToHost));
+    p->ell_entry = vals[0];
+    p->large_block = vals[1];
+    p->large_ltr = vals[2];
+    int v = 0;
+    c->cuFuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_NUM_REGS, fn);
+    p->info.num_regs_large = v;
+    c->cuFuncGetAttribute(&p->large_static_smem, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, fn);
+    DRV(c, c->cuFuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                 (int)c->prop.sharedMemPerBlockOptin - p->large_static_smem));
+    p->fn_large = fn;
+    p->info.compile_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return GDB_OK;
+}
+
 static int pick_kernel(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, const gdb_solve_args *a, LaunchCfg &k) {
     const int block = p->info.block_size;
     const int nvec = p->eval_gradient ? 6 : 5;
@@ -842,8 +889,13 @@ static int pick_kernel(gdb_context_t c, gdb_program_t p, gdb_graphset_t gs, cons
     (void)a;
     // large-pair kernel: one cluster per pair, when the vectors of the largest pair would
     // otherwise live in a per-CTA arena (graph-level outputs; 16-bit row index)
-    if (spill && k.kind == 0 && p->fn_large && gs->index16 && !getenv("GDB_FORCE_GENERAL") &&
-        (uint64_t)gs->max_node[0] <= 32ull * p->lcpt) {
+    const bool large_fits = spill && k.kind == 0 && p->nodal == GDB_NODAL_NONE && gs->index16 &&
+                            !getenv("GDB_FORCE_GENERAL") && (uint64_t)gs->max_node[0] <= 32ull * p->lcpt;
+    if (large_fits) {
+        int rc = ensure_large(c, p);
+        if (rc) return rc;
+    }
+    if (large_fits && p->fn_large) {
         const uint64_t n2p = ((uint64_t)gs->max_node[0] + 3) & ~3ull;
         const uint64_t D = std::min<uint64_t>(gs->max_degree, (uint64_t)p->lell);
         const uint64_t ell_entry = p->ell_entry;  // sizeof(gdb_ell_t), read back from the module

@@ -60,7 +60,7 @@
 #define GDB_LTR 1        // tile rows of G1 per staging step
 #endif
 
-#if GDB_NODAL == 0  // graph-level outputs only; nodal outputs run in mlgk_solve
+#if GDB_NODAL == 0 && (GDB_BUILD_MASK & 4)  // graph-level outputs only; nodal outputs run in mlgk_solve
 
 __device__ __forceinline__ unsigned gdb_cluster_rank() {
     unsigned r;

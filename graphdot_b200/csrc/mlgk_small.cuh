@@ -328,6 +328,7 @@ __device__ __forceinline__ gdb_small_graph gdb_small_view(const unsigned char *b
     return v;
 }
 
+#if GDB_BUILD_MASK & 2
 extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
     mlgk_solve_small(const __grid_constant__ gdb_params P) {
     extern __shared__ __align__(16) unsigned char gdb_smem[];
@@ -1281,3 +1282,4 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS_SMALL)
 #undef GDB_POS
 #undef GDB_LIVE
 #undef GDB_VCOLS
+#endif  // GDB_BUILD_MASK & 2

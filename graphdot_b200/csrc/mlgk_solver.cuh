@@ -108,6 +108,11 @@ static_assert(alignof(node_kernel_t) <= 16 && alignof(edge_kernel_t) <= 16 && al
               "hyper-parameter structs must not be over-aligned");
 static_assert(sizeof(gdb_params) == gdb_up16(GDB_OFF_P + (unsigned)sizeof(p_start_t)), "parameter block layout");
 
+// which kernels this translation unit holds: 1 mlgk_solve, 2 mlgk_solve_small, 4 mlgk_solve_large.
+// The host library compiles one NVRTC module per kernel, concurrently (gdb_abi.cpp).
+#ifndef GDB_BUILD_MASK
+#define GDB_BUILD_MASK 7
+#endif
 extern "C" __device__ const unsigned gdb_param_layout[8] = {
     (unsigned)sizeof(gdb_params), GDB_OFF_V, GDB_OFF_E, GDB_OFF_P,
     (unsigned)sizeof(gdb_params_fixed), (unsigned)sizeof(node_t), (unsigned)sizeof(edge_t), (unsigned)GDB_NJ};
@@ -404,6 +409,7 @@ __device__ __forceinline__ void gdb_copy16(void *dst, const void *src, unsigned 
     for (unsigned k = threadIdx.x; k < bytes / 16; k += GDB_BLOCK) d[k] = s[k];
 }
 
+#if GDB_BUILD_MASK & 1
 extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
     mlgk_solve(const __grid_constant__ gdb_params P) {
     extern __shared__ __align__(16) unsigned char gdb_smem[];
@@ -821,3 +827,4 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
         (void)plane;
     }
 }
+#endif  // GDB_BUILD_MASK & 1

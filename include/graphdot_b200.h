@@ -129,7 +129,9 @@ typedef struct gdb_program_info {
     int32_t block_size;
     int32_t num_regs;        /* general kernel (mlgk_solve)                */
     int32_t num_regs_small;  /* shared-memory kernel (mlgk_solve_small)    */
-    int32_t num_regs_large;  /* cluster kernel (mlgk_solve_large), 0 = none */
+    int32_t num_regs_large;  /* cluster kernel (mlgk_solve_large); 0 = none, or not
+                              * compiled yet: its NVRTC module is built when a
+                              * graph set first needs it */
     int32_t static_smem;
     int32_t local_bytes;     /* spill / stack per thread                   */
     int32_t max_dynamic_smem;

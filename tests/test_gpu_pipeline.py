@@ -366,3 +366,26 @@ def test_large_pair_kernel_mixed_sizes_and_isolated_nodes(monkeypatch):
         assert rel_err(dK[:, :, m], dK2[:, :, m]) < 2e-5
     assert np.allclose(Kxy, kernel2(G[:2], G[2:]), rtol=5e-6)
     assert np.array_equal(K, K.T)
+
+
+def test_large_pair_kernel_module_is_compiled_on_first_need():
+    """The cluster kernel is 80 % of the NVRTC time of the template: a program
+    that only ever sees small pairs never compiles it (num_regs_large stays 0);
+    the first graph set with large pairs compiles and uses it, and the small
+    pairs keep their kernel and their results."""
+    be = B200Backend()
+    kernel = make_config_kernel('C4', backend=be)
+    from graphdot_b200.synthetic import newman_watts_strogatz
+    small = [newman_watts_strogatz(np.random.default_rng(s), 12 + s)
+             for s in range(6)]
+    K_small = kernel(small)
+    assert be.last['kernel'] == 'mlgk_solve_small'
+    progs = list(be._programs.values())
+    assert progs and all(be.program_info(p).num_regs_large == 0 for p in progs)
+    large = make_config_graphs('C4', 3)
+    K_large = kernel(large)
+    assert be.last['kernel'] == 'mlgk_solve_large'
+    assert any(be.program_info(p).num_regs_large > 0
+               for p in be._programs.values())
+    assert np.array_equal(kernel(small), K_small)
+    assert np.all(np.isfinite(K_large)) and np.array_equal(K_large, K_large.T)
