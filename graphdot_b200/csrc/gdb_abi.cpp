@@ -326,7 +326,8 @@ static int render(const gdb_program_desc *d, std::string &src) {
         // registers, no spills) instead of 512.  Measured on the C3 workload
         // (M pairs/s): block 96 / 8 rows / 128 regs 12.4; 128 / 6 / 96 regs 17.6;
         // 128 / 6 / 80 regs (A p spilled) 17.6; 72 regs 11.6.
-        const int threads = (pick_wpt(d) == 1 && pick_rpw(d) <= 6) ? 640 : 512;
+        int threads = (pick_wpt(d) == 1 && pick_rpw(d) <= 6) ? 640 : 512;
+        if (const char *env = getenv("GDB_SMALL_THREADS")) threads = atoi(env);  // tuning hook
         o << "#define GDB_MIN_BLOCKS_SMALL " << std::max(1, threads / block) << "\n";
     }
     o << "#define GDB_WPT " << pick_wpt(d) << "\n";
