@@ -204,26 +204,48 @@ def test_struct_decl_and_state_bytes():
 CASES = ['unlabeled', 'labeled', 'weighted', 'vario-features', 'molecular']
 
 
-@pytest.mark.parametrize('name', CASES)
-@pytest.mark.parametrize('traits', [
+TRAITS = [
     dict(symmetric=True), dict(symmetric=True, eval_gradient=True),
     dict(diagonal=True, nodal=True), dict(nodal=True, lmin=1),
     dict(diagonal=True, nodal='block'), dict(diagonal=True, eval_gradient=True,
                                              lmin=1),
-    dict(symmetric=True, nodal=True, eval_gradient=True)])
-def test_nvrtc_compiles_fixture_kernels_for_sm100a(mlgk_golden, name, traits):
+    dict(symmetric=True, nodal=True, eval_gradient=True)]
+_COMPILED = {}
+
+
+def _compile_fixture_kernels(golden):
+    """NVRTC-compile every (fixture, traits) program once, four at a time on
+    host threads (ctypes releases the GIL; each compile runs its kernels'
+    modules on threads of its own)."""
+    if _COMPILED:
+        return _COMPILED
+    from concurrent.futures import ThreadPoolExecutor
     lib = native.load()
-    G = golden_graphs(mlgk_golden['cases'][name])
-    knode, kedge = golden_kernels(name)
-    nl, el, weighted = B200Backend._layouts(G[0])
-    for block in ((96, 1),):
+
+    def one(job):
+        name, t = job
+        G = golden_graphs(golden['cases'][name])
+        knode, kedge = golden_kernels(name)
+        nl, el, weighted = B200Backend._layouts(G[0])
         d, keep, _ = B200Backend._desc(
             nl, el, weighted, knode, kedge, Uniform(1.0),
-            MarginalizedGraphKernel.traits(**traits), block, ())
+            MarginalizedGraphKernel.traits(**TRAITS[t]), (96, 1), ())
         size = C.c_uint64()
         rc = lib.gdb_program_compile_only(C.byref(d), C.byref(size))
-        assert rc == 0, lib.gdb_last_error().decode()
-        assert size.value > 1000
+        return job, (rc, size.value, lib.gdb_last_error().decode())
+
+    jobs = [(name, t) for name in CASES for t in range(len(TRAITS))]
+    with ThreadPoolExecutor(4) as pool:
+        _COMPILED.update(pool.map(one, jobs))
+    return _COMPILED
+
+
+@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('t', range(len(TRAITS)))
+def test_nvrtc_compiles_fixture_kernels_for_sm100a(mlgk_golden, name, t):
+    rc, size, err = _compile_fixture_kernels(mlgk_golden)[(name, t)]
+    assert rc == 0, err
+    assert size > 1000
 
 
 def test_compile_errors_are_reported():
