@@ -289,7 +289,18 @@ class B200Backend(Backend):
         return native.pinned_empty(size, dtype)
 
     def __init__(self, device=0, block_size=None, nvrtc_extra=(),
-                 graphset_cache=4, slots_per_lane=None, cluster_size=None):
+                 graphset_cache=4, slots_per_lane=None, cluster_size=None,
+                 reorder=None, reorder_min_nodes=64):
+        if reorder not in (None, 'rcm', 'pbr'):
+            raise ValueError(f"reorder must be None, 'rcm' or 'pbr', got "
+                             f'{reorder!r}')
+        # relabel the nodes of graphs with >= reorder_min_nodes nodes when they
+        # are packed (graphdot_b200.reorder; the large-pair kernel's staging
+        # follows the locality of the node order).  Graph-level
+        # results do not depend on the labelling; nodal outputs are indexed by
+        # node and are refused on a re-ordering back end.
+        self.reorder = reorder
+        self.reorder_min_nodes = int(reorder_min_nodes)
         self.uuid = uuid.uuid4()
         self.device = device
         self.block_size = block_size
@@ -368,6 +379,13 @@ class B200Backend(Backend):
         L = self._layout_c(nl, el, weighted)
         n = len(graph.nodes)
         order = np.argsort(np.asarray(graph.nodes['!i']), kind='stable')
+        relabel = None
+        if self.reorder and n >= self.reorder_min_nodes:
+            from ... import reorder as _reorder
+            perm = getattr(_reorder, self.reorder)(graph)
+            order = order[perm]              # new node k is old node perm[k]
+            relabel = np.empty(n, dtype=np.uint32)
+            relabel[perm] = np.arange(n, dtype=np.uint32)
         pool = []
         nodes, pb = nl.fill(graph.nodes, order, pool, 0)
         ne = len(graph.edges)
@@ -375,6 +393,8 @@ class B200Backend(Backend):
         pool_bytes = b''.join(pool)
         ei = np.ascontiguousarray(graph.edges['!i'], dtype=np.uint32)
         ej = np.ascontiguousarray(graph.edges['!j'], dtype=np.uint32)
+        if relabel is not None:
+            ei, ej = relabel[ei], relabel[ej]
         ew = (np.ascontiguousarray(graph.edges['!w'], dtype=np.float32)
               if weighted else None)
         pool_arr = np.frombuffer(pool_bytes, dtype=np.uint8)
@@ -399,6 +419,10 @@ class B200Backend(Backend):
         (``gdb_graphs_pack_batch``); graphs with variable-length features take
         the per-graph path."""
         out = [g.cookie.get(self.uuid) for g in graphs]
+        if self.reorder:                      # re-ordered graphs: per-graph path
+            for k, g in enumerate(graphs):
+                if out[k] is None and len(g.nodes) >= self.reorder_min_nodes:
+                    out[k] = self.pack_graph(g)
         todo = [k for k, p in enumerate(out) if p is None]
         if not todo:
             return out
@@ -598,6 +622,9 @@ class B200Backend(Backend):
     def program(self, gs, node_kernel, edge_kernel, p, traits):
         if traits.lmin not in (0, 1):
             raise ValueError(f'lmin must be 0 or 1, got {traits.lmin}')
+        if self.reorder and traits.nodal is not False:
+            raise ValueError('nodal outputs are indexed by node: use a '
+                             'B200Backend without reorder=')
         nl, el, weighted = gs.layouts
         block = self._pick_block(gs.sizes, traits.eval_gradient is True,
                                  gs.mean_degree)

@@ -389,3 +389,33 @@ def test_large_pair_kernel_module_is_compiled_on_first_need():
                for p in be._programs.values())
     assert np.array_equal(kernel(small), K_small)
     assert np.all(np.isfinite(K_large)) and np.array_equal(K_large, K_large.T)
+
+
+def test_backend_reorder_option_restores_the_tile_footprint():
+    """B200Backend(reorder='pbr') relabels large graphs when it packs them:
+    shuffled C4 graphs give the Gram matrix of the un-shuffled ones (graph-level
+    results do not depend on the labelling) with the shared-memory footprint of
+    the natural order; nodal outputs are refused."""
+    rng = np.random.default_rng(11)
+    natural = make_config_graphs('C4', 4)
+    shuffled = [g.permute(rng.permutation(len(g.nodes))) for g in natural]
+    be_nat, be_shuf, be_pbr = (B200Backend(), B200Backend(),
+                               B200Backend(reorder='pbr'))
+    K_nat = make_config_kernel('C4', backend=be_nat)(natural)
+    smem_nat = be_nat.last['smem_bytes']
+    K_shuf = make_config_kernel('C4', backend=be_shuf)(shuffled)
+    smem_shuf = be_shuf.last['smem_bytes']
+    kernel = make_config_kernel('C4', backend=be_pbr)
+    K_pbr, dK_pbr = kernel(shuffled, eval_gradient=True)
+    assert be_pbr.last['kernel'] == 'mlgk_solve_large'
+    assert np.allclose(K_shuf, K_nat, rtol=5e-6)
+    assert np.allclose(K_pbr, K_nat, rtol=5e-6)
+    assert be_pbr.last['smem_bytes'] <= 1.1 * smem_nat < smem_shuf
+    _, dK_nat = make_config_kernel('C4', backend=be_nat)(natural,
+                                                         eval_gradient=True)
+    for m in range(dK_nat.shape[2]):
+        assert rel_err(dK_pbr[:, :, m], dK_nat[:, :, m]) < 2e-5
+    with pytest.raises(ValueError, match='nodal'):
+        kernel(shuffled, nodal=True)
+    with pytest.raises(ValueError):
+        B200Backend(reorder='metis')

@@ -298,3 +298,24 @@ def test_reorder_rejects_bad_input_and_handles_isolated_nodes():
                                  out.ctypes.data) != 0
     assert lib.gdb_graph_reorder(4, 1, ei.ctypes.data, ej.ctypes.data, 7,
                                  out.ctypes.data) != 0
+
+
+def test_backend_reorder_option_packs_the_permuted_graph():
+    """B200Backend(reorder=...) packs exactly what packing g.permute(perm)
+    would; small graphs are left alone."""
+    from graphdot_b200.kernel.marginalized._backend_b200 import B200Backend
+    from graphdot_b200.reorder import pbr, rcm
+    from graphdot_b200.synthetic import make_config_graphs
+    rng = np.random.default_rng(0)
+    g = make_config_graphs('C4', 1)[0]
+    s = g.permute(rng.permutation(len(g.nodes)))
+    for name, f in (('pbr', pbr), ('rcm', rcm)):
+        a = B200Backend(reorder=name).pack_graph(s).blob
+        b = B200Backend().pack_graph(s.permute(f(s))).blob
+        assert np.array_equal(a, b)
+    mols = make_config_graphs('C2', 20)
+    a = B200Backend(reorder='pbr').pack_graphs(mols)
+    b = B200Backend().pack_graphs(mols)
+    assert all(np.array_equal(x.blob, y.blob) for x, y in zip(a, b))
+    with pytest.raises(ValueError):
+        B200Backend(reorder='metis')
