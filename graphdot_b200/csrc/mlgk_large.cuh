@@ -54,7 +54,13 @@
 #define GDB_LELL 12
 #endif
 #ifndef GDB_LBLOCK
-#define GDB_LBLOCK 512  // 16 warps share out the (rows of a staging step) x (blocks of 32 columns)
+// 8 warps share out the (rows of a staging step) x (blocks of 32 columns).  Two resident CTAs
+// of 256 threads leave ptxas 128 registers per thread: no spills in the gather loops, and 16
+// warps per SM then do what 32 warps at the 64-register cap of 512 threads do with 316 B of
+// spill stores / 596 B of spill loads per thread.  All 500 C4 graphs: 256 threads 46.8 k pairs/s,
+// 512 threads 43.5 k; with the Jacobian 22.4 k / 22.0 k.  (When a badly ordered graph set leaves
+// room for ONE CTA per SM only, 512 threads are better, 29.1 k vs 26.7 k: reorder the graphs.)
+#define GDB_LBLOCK 256
 #endif
 #ifndef GDB_LTR
 #define GDB_LTR 1        // tile rows of G1 per staging step
@@ -261,7 +267,19 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
         // warps = (rows of this step) x (groups of column blocks): a warp keeps ONE row -- its
         // elements stay in registers across all of the warp's column blocks
         const unsigned rows_here = (unsigned)(min(8 * t_end, n1) - 8 * t);
-        const unsigned groups = max(1u, (unsigned)(GDB_LBLOCK / 32) / rows_here);
+        // groups of column blocks per row so that rows x groups deals out evenly over the
+        // warps: warps / gcd(rows, warps) (= warps / rows when that divides, e.g. 16 / 8)
+        unsigned groups;
+        {
+            constexpr unsigned NW = GDB_LBLOCK / 32;
+            unsigned a = rows_here, b = NW;
+            while (b) {
+                const unsigned r = a % b;
+                a = b;
+                b = r;
+            }
+            groups = NW / a;
+        }
         const unsigned ell_sa = gdb_smem_u32(C.ell), ell_stride = n2p * (unsigned)sizeof(gdb_ell_t);
         const unsigned stage_sa = gdb_smem_u32(C.stage[b]);
         constexpr int NACC = MODE == 0 ? 1 : (GDB_NE > 0 ? GDB_NE : 1);
