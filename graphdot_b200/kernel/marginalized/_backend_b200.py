@@ -317,7 +317,7 @@ class B200Backend(Backend):
         self.resend_graphs = False   # True: every call re-sends the packed
         #                              graphs host -> device (end-to-end timing)
         self._inflight = []      # host inputs of asynchronous solves
-        self._memo = None        # (list object, len, first, last, graph set)
+        self._memo = None        # (ids of the graphs, the graphs, graph set)
         self.totals = {}         # running sums over all solves (bench)
         self.reset_totals()
         native.load()            # fail loudly if the library is missing
@@ -663,19 +663,20 @@ class B200Backend(Backend):
         pipelines the solve in row / column blocks, ``gramian_dev=`` /
         ``gradient_dev=`` leave the results in caller-owned device memory."""
         timer.tic('transferring graphs to GPU')
-        # the front end hands the SAME list object to the diagonal solve and to
-        # the main solve of one public call: skip the second cache walk
+        # the same graph OBJECTS as in the previous call (the diagonal and the
+        # main solve of one public call; every step of a training loop): skip
+        # the walk over the graphs' caches.  The memo keeps the list alive, so
+        # an id cannot be recycled while it is compared.
+        glist = graphs if type(graphs) is list else list(graphs)
+        ids = tuple(map(id, glist))
         memo = self._memo
-        if (type(graphs) is list and memo is not None and memo[0] is graphs
-                and len(graphs) == memo[1] and graphs[0] is memo[2]
-                and graphs[-1] is memo[3]
-                and graphs[0].cookie.get(self.uuid) is memo[4].packed[0]
-                and graphs[-1].cookie.get(self.uuid) is memo[4].packed[-1]):
-            gs = memo[4]
+        if (memo is not None and memo[0] == ids
+                and glist[0].cookie.get(self.uuid) is memo[2].packed[0]
+                and glist[-1].cookie.get(self.uuid) is memo[2].packed[-1]):
+            gs = memo[2]
         else:
-            glist = graphs if type(graphs) is list else list(graphs)
             gs = self.graphset(glist)
-            self._memo = (graphs, len(glist), glist[0], glist[-1], gs)
+            self._memo = (ids, glist, gs)
         timer.toc('transferring graphs to GPU')
 
         timer.tic('code generation + JIT')

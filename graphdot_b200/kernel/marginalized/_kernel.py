@@ -160,7 +160,13 @@ class MarginalizedGraphKernel:
         traits = self.traits(symmetric=Y is None, nodal=nodal, lmin=lmin,
                              eval_gradient=eval_gradient)
         graphs = list(X) if Y is None else list(it.chain(X, Y))
-        self._check_types(graphs)
+        # the type check walks every graph (2 ms for 2000): once per set of
+        # graph objects, not once per call (training loops)
+        ids = tuple(map(id, graphs))
+        checked = getattr(self, '_types_checked', None)
+        if checked is None or checked[0] != ids:
+            self._check_types(graphs)
+            self._types_checked = (ids, graphs)
         nx, ny = len(X), (len(X) if Y is None else len(Y))
 
         timer.tic('generating jobs')
@@ -418,6 +424,11 @@ class MarginalizedGraphKernel:
         return np.log(self._flat_bounds()[self.active_theta_mask, :])
 
     def clone_with_theta(self, theta):
-        clone = copy.deepcopy(self)
+        checked, self._types_checked = getattr(self, '_types_checked', None), None
+        try:
+            clone = copy.deepcopy(self)      # without the memo of checked graphs
+        finally:
+            self._types_checked = checked
+        clone._types_checked = checked       # same graphs, same verdict
         clone.theta = theta
         return clone

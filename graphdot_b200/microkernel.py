@@ -23,6 +23,7 @@ dotproduct.py:8-53; product.py:8-42).  Every kernel offers
 """
 import math
 from abc import ABC, abstractmethod
+import functools
 from collections import namedtuple
 
 import numpy as np
@@ -33,7 +34,13 @@ __all__ = ['MicroKernel', 'Product', 'Constant', 'KroneckerDelta',
 
 
 def _named(typename, fields):
-    fields = list(fields)
+    return _named_cached(typename, tuple(fields))
+
+
+@functools.lru_cache(maxsize=None)
+def _named_cached(typename, fields):
+    # one class per (name, fields): building a namedtuple costs 50 us, and
+    # every `.theta` / `.hyperparameters` access asks for one
     base = namedtuple(typename, fields)
 
     def __repr__(self):
