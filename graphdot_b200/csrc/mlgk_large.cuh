@@ -424,7 +424,8 @@ __device__ __forceinline__ int gdb_large_pcg(const gdb_params &P, const gdb_larg
         float s2[2] = {0.f, 0.f};
         // (two or four float4 per thread and vector in flight -- loads batched ahead of the
         // arithmetic -- were slower: the kernel sits at its 128-register cap, the batch spills
-        // into the gather loops; 44.0 k -> 36.2 k / 33.1 k pairs/s on 100 C4 graphs)
+        // into the gather loops; 44.0 k -> 36.2 k / 33.1 k pairs/s on 100 C4 graphs -- also
+        // with the sweep kept out of line, which by itself costs 10 %)
         for (size_t i = q_lo + threadIdx.x; i < q_hi; i += GDB_LBLOCK) {
             const float4 pv = p4[i], av = a4[i], dv = d4[i];
             float4 xv = x4[i], rv = r4[i];
