@@ -203,7 +203,24 @@ class DataFrame:
 
 class VolatileCookie(dict):
     """Per-graph cache for back ends; intentionally dropped by pickling and
-    deep copies (reference graphdot/util/cookie.py:5-12)."""
+    deep copies (reference graphdot/util/cookie.py:5-12).  ``epoch`` counts
+    the invalidations of ANY graph's cache (``Graph.permute(inplace=True)``,
+    ``Graph.unify_datatype``): callers that memoise work over a whole list of
+    graphs compare it instead of walking the list."""
+
+    epoch = 0
+
+    def clear(self):
+        VolatileCookie.epoch += 1
+        super().clear()
+
+    def pop(self, *args):
+        VolatileCookie.epoch += 1
+        return super().pop(*args)
+
+    def __delitem__(self, key):
+        VolatileCookie.epoch += 1
+        super().__delitem__(key)
 
     def __reduce__(self):
         return (VolatileCookie, ())

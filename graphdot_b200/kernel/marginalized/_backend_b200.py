@@ -21,7 +21,7 @@ import uuid
 import numpy as np
 
 from ... import native
-from ...graph import DataFrame
+from ...graph import DataFrame, Graph, VolatileCookie
 from ._backend import Backend
 
 _FROZEN = np.dtype([('_data', np.uint64), ('size', np.int32)], align=True)
@@ -317,7 +317,8 @@ class B200Backend(Backend):
         self.resend_graphs = False   # True: every call re-sends the packed
         #                              graphs host -> device (end-to-end timing)
         self._inflight = []      # host inputs of asynchronous solves
-        self._memo = None        # (ids of the graphs, the graphs, graph set)
+        self._memo = None        # (ids of the graphs, the graphs, graph set,
+        #                          cache-invalidation epoch or None)
         self.totals = {}         # running sums over all solves (bench)
         self.reset_totals()
         native.load()            # fail loudly if the library is missing
@@ -664,19 +665,25 @@ class B200Backend(Backend):
         ``gradient_dev=`` leave the results in caller-owned device memory."""
         timer.tic('transferring graphs to GPU')
         # the same graph OBJECTS as in the previous call (the diagonal and the
-        # main solve of one public call; every step of a training loop): skip
-        # the walk over the graphs' caches.  The memo keeps the list alive, so
-        # an id cannot be recycled while it is compared.
+        # main solve of one public call; every step of a training loop) and no
+        # graph cache invalidated since: skip the walk over the graphs' caches.
+        # The memo keeps the list alive, so an id cannot be recycled while it
+        # is compared.  Graphs of a foreign class (the reference's own Graph)
+        # have no invalidation counter: for them only the SAME list object,
+        # which the front end hands to the two solves of one call, is trusted.
         glist = graphs if type(graphs) is list else list(graphs)
         ids = tuple(map(id, glist))
         memo = self._memo
         if (memo is not None and memo[0] == ids
+                and (memo[3] == VolatileCookie.epoch if memo[3] is not None
+                     else memo[1] is graphs)
                 and glist[0].cookie.get(self.uuid) is memo[2].packed[0]
                 and glist[-1].cookie.get(self.uuid) is memo[2].packed[-1]):
             gs = memo[2]
         else:
             gs = self.graphset(glist)
-            self._memo = (ids, glist, gs)
+            own = all(isinstance(g, Graph) for g in glist)
+            self._memo = (ids, glist, gs, VolatileCookie.epoch if own else None)
         timer.toc('transferring graphs to GPU')
 
         timer.tic('code generation + JIT')

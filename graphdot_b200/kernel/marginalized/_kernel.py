@@ -24,7 +24,7 @@ from collections import namedtuple
 
 import numpy as np
 
-from ...graph import Graph
+from ...graph import Graph, VolatileCookie
 from ...util import Timer, flatten, fold_like, replace
 from ._backend import backend_factory
 from .starting_probability import Adhoc, StartingProbability, Uniform
@@ -162,11 +162,16 @@ class MarginalizedGraphKernel:
         graphs = list(X) if Y is None else list(it.chain(X, Y))
         # the type check walks every graph (2 ms for 2000): once per set of
         # graph objects, not once per call (training loops)
+        # -- and not again until a graph's cache is invalidated (in-place
+        # permutation, unify_datatype)
         ids = tuple(map(id, graphs))
         checked = getattr(self, '_types_checked', None)
-        if checked is None or checked[0] != ids:
+        if (checked is None or checked[0] != ids
+                or checked[2] != VolatileCookie.epoch):
             self._check_types(graphs)
-            self._types_checked = (ids, graphs)
+            own = all(isinstance(g, Graph) for g in graphs)
+            self._types_checked = ((ids, graphs, VolatileCookie.epoch)
+                                   if own else None)
         nx, ny = len(X), (len(X) if Y is None else len(Y))
 
         timer.tic('generating jobs')

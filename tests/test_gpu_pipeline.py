@@ -419,3 +419,21 @@ def test_backend_reorder_option_restores_the_tile_footprint():
         kernel(shuffled, nodal=True)
     with pytest.raises(ValueError):
         B200Backend(reorder='metis')
+
+
+def test_call_memo_is_invalidated_by_an_inplace_permutation():
+    """Repeated calls with the same graph objects skip the walk over the
+    graphs' caches; relabelling one graph in place (which clears its cache)
+    must be seen by the next call."""
+    G = make_config_graphs('C2', 6)
+    be = B200Backend()
+    kernel = make_config_kernel('C2', backend=be)
+    R0 = kernel(G, nodal=True)
+    assert np.array_equal(kernel(G, nodal=True), R0)       # memo hit
+    n = len(G[2].nodes)
+    G[2].permute(np.random.default_rng(0).permutation(n), inplace=True)
+    R1 = kernel(G, nodal=True)
+    R2 = make_config_kernel('C2', backend=B200Backend())(G, nodal=True)
+    assert np.array_equal(R1, R2)
+    assert not np.array_equal(R1, R0)
+    assert np.allclose(kernel(G), make_config_kernel('C2', backend=B200Backend())(G), rtol=1e-6)

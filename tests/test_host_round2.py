@@ -319,3 +319,22 @@ def test_backend_reorder_option_packs_the_permuted_graph():
     assert all(np.array_equal(x.blob, y.blob) for x, y in zip(a, b))
     with pytest.raises(ValueError):
         B200Backend(reorder='metis')
+
+
+def test_cookie_epoch_counts_cache_invalidations():
+    """The per-call memo of the front end / back end (same graph objects as
+    last time -> no walk over the list) is only valid while no graph cache was
+    invalidated: permute(inplace=True) and unify_datatype bump the epoch, a
+    plain copy or an out-of-place permutation does not."""
+    from graphdot_b200.graph import Graph, VolatileCookie
+    from graphdot_b200.synthetic import make_config_graphs
+    G = make_config_graphs('C2', 3)
+    e0 = VolatileCookie.epoch
+    G[0].cookie['k'] = 1
+    h = G[1].permute(np.arange(len(G[1].nodes))[::-1])
+    G[2].copy(deep=True)
+    assert VolatileCookie.epoch == e0 and h is not G[1]
+    G[0].permute(np.arange(len(G[0].nodes))[::-1], inplace=True)
+    assert VolatileCookie.epoch == e0 + 1 and 'k' not in G[0].cookie
+    Graph.unify_datatype(G, inplace=True)
+    assert VolatileCookie.epoch >= e0 + 2
