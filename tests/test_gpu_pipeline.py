@@ -437,3 +437,33 @@ def test_call_memo_is_invalidated_by_an_inplace_permutation():
     assert np.array_equal(R1, R2)
     assert not np.array_equal(R1, R0)
     assert np.allclose(kernel(G), make_config_kernel('C2', backend=B200Backend())(G), rtol=1e-6)
+
+
+@pytest.mark.parametrize('force_general', [False, True])
+def test_560_x_530_node_pair_vs_committed_oracle_answer(monkeypatch,
+                                                        force_general):
+    """560 x 530 nodes (N = 296 800), beyond BASELINE's C4 range: the cluster
+    kernel (18 columns per lane) and the general kernel with its global-memory
+    arena against the float64 oracle.  The oracle needs 80 s for this pair; its
+    answer is committed (tests/golden/large_pair_oracle.json, made by
+    make_large_pair_golden.py)."""
+    import json
+    import os
+    import sys
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    sys.path.insert(0, golden)
+    from make_large_pair_golden import graphs
+    want = json.load(open(os.path.join(golden, 'large_pair_oracle.json')))
+    g1, g2 = graphs()
+    assert [len(g1.nodes), len(g2.nodes)] == want['sizes']
+    if force_general:
+        monkeypatch.setenv('GDB_FORCE_GENERAL', '1')
+    be = B200Backend()
+    kernel = make_config_kernel('C4', backend=be)
+    K, dK = kernel([g1], [g2], eval_gradient=True)
+    assert be.last['kernel'] == ('mlgk_solve' if force_general
+                                 else 'mlgk_solve_large')
+    assert K[0, 0] == pytest.approx(want['gram'], rel=GRAM_RTOL)
+    go = np.array(want['gradient'])
+    assert np.allclose(dK[0, 0], go, rtol=GRAD_RTOL,
+                       atol=GRAD_RTOL * np.abs(go).max())
