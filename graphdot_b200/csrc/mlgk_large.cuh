@@ -283,6 +283,9 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
         const unsigned ell_sa = gdb_smem_u32(C.ell), ell_stride = n2p * (unsigned)sizeof(gdb_ell_t);
         const unsigned stage_sa = gdb_smem_u32(C.stage[b]);
         constexpr int NACC = MODE == 0 ? 1 : (GDB_NE > 0 ? GDB_NE : 1);
+        double dres[MODE == 0 ? 1 : NACC];  // MODE 1: partial sums of the step in double (see the epilogue)
+#pragma unroll
+        for (int a = 0; a < (MODE == 0 ? 1 : NACC); ++a) dres[a] = 0.0;
 #pragma unroll 1
         for (unsigned wi = warp; wi < rows_here * groups; wi += GDB_LBLOCK / 32) {
             const unsigned q = wi / rows_here;
@@ -369,7 +372,7 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
                             res[0] = fmaf(own_v, r, res[0]);
                         } else {
 #pragma unroll
-                            for (int a = 0; a < NACC; ++a) res[a] = fmaf(own_v, acc[a], res[a]);
+                            for (int a = 0; a < NACC; ++a) dres[a] += (double)(own_v * acc[a]);
                         }
                     }
                 }
@@ -385,6 +388,10 @@ template<int MODE> __device__ __forceinline__ void gdb_large_sweep(const gdb_par
             case 8: row_pass(gdb_int<8>{}); break;
             default: row_pass(gdb_int<0>{}); break;
             }
+        }
+        if constexpr (MODE == 1) {
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) res[a] += (float)dres[a];
         }
         __syncthreads();  // every warp is done with buffer b before it is refilled
         if (!C.dbl && t_end < C.t_hi) {
@@ -575,9 +582,12 @@ extern "C" __global__ void __cluster_dims__(GDB_CLUSTER, 1, 1) __launch_bounds__
 
         // ---- epilogue over this CTA's elements --------------------------------------------
         constexpr int NACC = 1 + (GDB_GRADIENT ? GDB_NP + 1 + GDB_NV : 0);
-        float acc[NACC];
+        // per-thread partial sums in double: a thread adds ~N / 512 terms of one sign and similar
+        // size; a float accumulator rounds them the same way for long stretches (label-free
+        // kernels at N = 9e5: K off by 1.2e-5 relative with float partial sums)
+        double dacc[NACC];
 #pragma unroll
-        for (int m = 0; m < NACC; ++m) acc[m] = 0.f;
+        for (int m = 0; m < NACC; ++m) dacc[m] = 0.0;
         for (size_t e = e_lo + threadIdx.x; e < e_hi; e += GDB_LBLOCK) {
             const unsigned i1 = (unsigned)(e / n2p), i2 = (unsigned)(e - (size_t)i1 * n2p);
             if (i2 >= (unsigned)n2) continue;
@@ -591,7 +601,7 @@ extern "C" __global__ void __cluster_dims__(GDB_CLUSTER, 1, 1) __launch_bounds__
 #if GDB_LMIN == 1
             xs -= v;
 #endif
-            acc[0] = fmaf(xs, p1 * p2, acc[0]);
+            dacc[0] += (double)(xs * (p1 * p2));
 #if GDB_GRADIENT
             const float yi = y[e];
 #if GDB_NP > 0
@@ -600,10 +610,10 @@ extern "C" __global__ void __cluster_dims__(GDB_CLUSTER, 1, 1) __launch_bounds__
                 P.p_start.jacobian(u1, d1);
                 P.p_start.jacobian(u2, d2);
 #pragma unroll
-                for (int m = 0; m < GDB_NP; ++m) acc[1 + m] = fmaf(fmaf(d1[m], p2, p1 * d2[m]), xs, acc[1 + m]);
+                for (int m = 0; m < GDB_NP; ++m) dacc[1 + m] += (double)(fmaf(d1[m], p2, p1 * d2[m]) * xs);
             }
 #endif
-            acc[1 + GDB_NP] += 2.f * Q * dx * yi * (1.f - __fdividef(xi, v));
+            dacc[1 + GDB_NP] += (double)(2.f * Q * dx * yi * (1.f - __fdividef(xi, v)));
 #if GDB_NV > 0
             {
                 float dv[GDB_NV];
@@ -615,12 +625,15 @@ extern "C" __global__ void __cluster_dims__(GDB_CLUSTER, 1, 1) __launch_bounds__
 #if GDB_LMIN == 1
                     t -= p1 * p2 * dv[m];
 #endif
-                    acc[2 + GDB_NP + m] += t;
+                    dacc[2 + GDB_NP + m] += (double)t;
                 }
             }
 #endif
 #endif
         }
+        float acc[NACC];
+#pragma unroll
+        for (int m = 0; m < NACC; ++m) acc[m] = (float)dacc[m];
 #if GDB_GRADIENT && GDB_NE > 0
         float eacc[GDB_NE];
 #pragma unroll

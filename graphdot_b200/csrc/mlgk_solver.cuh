@@ -559,16 +559,19 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
         }
 #else
         {
-            float sum = 0.f;
+            // per-thread partial sums in double: a thread adds N / GDB_BLOCK terms of one sign and
+            // similar size, and a float accumulator rounds them the same way for long stretches
+            // (label-free kernels, N = 1.65e6: K off by 6e-5 relative with float partial sums)
+            double dsum = 0.0;
             for (int i = threadIdx.x; i < (int)N; i += GDB_BLOCK) {
                 const int i1 = i / n2, i2 = i - i1 * n2;
                 float xi = x[i];
 #if GDB_LMIN == 1
                 xi -= P.node_kernel(g1.node[i1], g2.node[i2]);
 #endif
-                sum = fmaf(xi, P.p_start(g1.node[i1]) * P.p_start(g2.node[i2]), sum);
+                dsum += (double)(xi * (P.p_start(g1.node[i1]) * P.p_start(g2.node[i2])));
             }
-            sum = gdb_group_sum(sum, s_red, flip);
+            float sum = gdb_group_sum((float)dsum, s_red, flip);
 #if !GDB_DIAGONAL
             norm_rs = gdb_norm_scale(F, ja, jb);
             sum *= norm_rs;
@@ -593,9 +596,9 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
         // dK/dq    = sum y (2Q Dx) - y (2Q Dx / Vx) x
         // dK/dtv_m = sum y x Dx / Vx^2 dVx  [- p1 p2 dVx if lmin]
         // dK/dte_m = sum_{i,j} y_i x_j w1 w2 dEx_ij
-        float jac[GDB_NJ];
+        double jac[GDB_NJ];  // per-thread partial sums in double, see the Gram sum above
 #pragma unroll
-        for (int m = 0; m < GDB_NJ; ++m) jac[m] = 0.f;
+        for (int m = 0; m < GDB_NJ; ++m) jac[m] = 0.0;
         for (int i = threadIdx.x; i < (int)N; i += GDB_BLOCK) {
             const int i1 = i / n2, i2 = i - i1 * n2;
             const node_t &u1 = g1.node[i1];
@@ -614,10 +617,10 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
                 P.p_start.jacobian(u1, d1);
                 P.p_start.jacobian(u2, d2);
 #pragma unroll
-                for (int m = 0; m < GDB_NP; ++m) jac[m] = fmaf(fmaf(d1[m], p2, p1 * d2[m]), xs, jac[m]);
+                for (int m = 0; m < GDB_NP; ++m) jac[m] += (double)(fmaf(d1[m], p2, p1 * d2[m]) * xs);
             }
 #endif
-            jac[GDB_NP] += 2.f * Q * dx * yi * (1.f - __fdividef(xi, v));
+            jac[GDB_NP] += (double)(2.f * Q * dx * yi * (1.f - __fdividef(xi, v)));
 #if GDB_NV > 0
             {
                 float dv[GDB_NV];
@@ -629,7 +632,7 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
 #if GDB_LMIN == 1
                     t -= p1 * p2 * dv[m];
 #endif
-                    jac[GDB_NP + 1 + m] += t;
+                    jac[GDB_NP + 1 + m] += (double)t;
                 }
             }
 #endif
@@ -669,13 +672,13 @@ extern "C" __global__ void __launch_bounds__(GDB_BLOCK, GDB_MIN_BLOCKS)
                     }
                 }
 #pragma unroll
-                for (int m = 0; m < GDB_NE; ++m) jac[GDB_NP + 1 + GDB_NV + m] = fmaf(yi, acc[m], jac[GDB_NP + 1 + GDB_NV + m]);
+                for (int m = 0; m < GDB_NE; ++m) jac[GDB_NP + 1 + GDB_NV + m] += (double)(yi * acc[m]);
             }
 #endif
         }
 #pragma unroll
         for (int m = 0; m < GDB_NJ; ++m) {
-            float s = gdb_group_sum(jac[m], s_red, flip);
+            float s = gdb_group_sum((float)jac[m], s_red, flip);
 #if !GDB_DIAGONAL
             s = gdb_norm_grad(F, ja, jb, m, norm_rs, norm_k, s);
 #endif

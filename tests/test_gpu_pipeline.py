@@ -467,3 +467,27 @@ def test_560_x_530_node_pair_vs_committed_oracle_answer(monkeypatch,
     go = np.array(want['gradient'])
     assert np.allclose(dK[0, 0], go, rtol=GRAD_RTOL,
                        atol=GRAD_RTOL * np.abs(go).max())
+
+
+@pytest.mark.parametrize('sizes, which', [((1000, 900), 'mlgk_solve_large'),
+                                          ((1500, 1100), 'mlgk_solve')])
+def test_largest_pairs_against_the_closed_form(sizes, which):
+    """Sizes no oracle solves in seconds: for label-free (Constant) kernels
+    K = p^2 n1 n2 / (1 - (1-q)^2) whatever the graphs, so dK/dp = 2 K / p and
+    dK/dq = -2 (1-q) K / (1 - (1-q)^2).  1000 x 900 nodes is the top of the
+    cluster kernel's range (N = 9e5), 1500 x 1100 (N = 1.65e6) runs in the
+    general kernel's global-memory arena."""
+    from graphdot_b200.synthetic import newman_watts_strogatz
+    g1, g2 = (newman_watts_strogatz(np.random.default_rng(31 + k), n)
+              for k, n in enumerate(sizes))
+    be = B200Backend()
+    kernel = make_config_kernel('C1', backend=be)
+    K, dK = kernel([g1], [g2], eval_gradient=True)
+    assert be.last['kernel'] == which
+    q = kernel.q
+    want = sizes[0] * sizes[1] / (1 - (1 - q) ** 2)
+    assert K[0, 0] == pytest.approx(want, rel=GRAM_RTOL)
+    assert dK.shape == (1, 1, 2)
+    assert dK[0, 0, 0] == pytest.approx(2 * want, rel=GRAD_RTOL)
+    assert dK[0, 0, 1] == pytest.approx(
+        -2 * (1 - q) * want / (1 - (1 - q) ** 2), rel=GRAD_RTOL)
