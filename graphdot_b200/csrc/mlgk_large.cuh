@@ -572,6 +572,7 @@ extern "C" __global__ void __cluster_dims__(GDB_CLUSTER, 1, 1) __launch_bounds__
             const unsigned i1 = (unsigned)(e / n2p), i2 = (unsigned)(e - (size_t)i1 * n2p);
             r[e] = i2 < (unsigned)n2 ? P.p_start(C.g1.node[i1]) * P.p_start(C.g2.node[i2]) : 0.f;
         }
+        __syncthreads();  // the solve reads r four elements at a time: other threads' writes
         iters += gdb_large_pcg(P, C, diag, y, r, p, Ap, e_lo, e_hi, N, F.ftol, S, flip);
 #endif
         if (rank == 0 && threadIdx.x == 0) {

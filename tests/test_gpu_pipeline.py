@@ -491,3 +491,34 @@ def test_largest_pairs_against_the_closed_form(sizes, which):
     assert dK[0, 0, 0] == pytest.approx(2 * want, rel=GRAD_RTOL)
     assert dK[0, 0, 1] == pytest.approx(
         -2 * (1 - q) * want / (1 - (1 - q) ** 2), rel=GRAD_RTOL)
+
+
+@pytest.mark.parametrize('case', ['large', 'large-mid', 'general-mid'])
+def test_large_and_general_kernels_are_bit_reproducible(monkeypatch, case):
+    """Identical calls in fresh back ends return identical bits, Jacobian
+    included, and the same total number of CG iterations.  (The adjoint solve
+    of the cluster kernel once read its right-hand side four elements at a
+    time without a barrier after the loop that wrote it one element per
+    thread: Jacobians differed in the last bit between runs on mid-size
+    graphs.)"""
+    from graphdot_b200.synthetic import newman_watts_strogatz
+    if case == 'large':
+        G = make_config_graphs('C4', 4)
+    else:
+        G = [newman_watts_strogatz(np.random.default_rng(s), n)
+             for s, n in ((1, 41), (2, 56), (3, 64))]
+        if case == 'large-mid':
+            monkeypatch.setenv('GDB_SMEM_CAP', '40000')
+        else:
+            monkeypatch.setenv('GDB_FORCE_GENERAL', '1')
+    runs = []
+    for k in range(4):
+        be = B200Backend()
+        K, dK = make_config_kernel('C4', backend=be)(G, eval_gradient=True)
+        runs.append((K.copy(), dK.copy(), be.last.get('cg_iterations')))
+    assert be.last['kernel'] == ('mlgk_solve' if case == 'general-mid'
+                                 else 'mlgk_solve_large')
+    for K, dK, it in runs[1:]:
+        assert np.array_equal(K, runs[0][0])
+        assert np.array_equal(dK, runs[0][1])
+        assert it == runs[0][2]
