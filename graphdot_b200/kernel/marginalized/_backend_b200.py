@@ -54,7 +54,8 @@ class AttributeLayout:
             if isinstance(ct, np.dtype) and ct.kind != 'O':
                 fields.append((key, np.dtype(ct).newbyteorder('='), None))
             elif ct in (list, tuple, np.ndarray) or ct is None:
-                inner = {np.asarray(v).dtype for v in col}
+                inner = {v.dtype if type(v) is np.ndarray
+                         else np.asarray(v).dtype for v in col}
                 if len(inner) != 1:
                     raise TypeError(
                         f'Sequence attribute {key!r} has mixed element types '
@@ -94,8 +95,12 @@ class AttributeLayout:
             if inner is None:
                 rows[k] = np.asarray(col)[order]
                 continue
-            seqs = [np.ascontiguousarray(col[i], dtype=inner) for i in order]
-            sizes = np.array([len(s) for s in seqs], dtype=np.int64)
+            seqs = [col[i] for i in order]
+            if not all(type(v) is np.ndarray and v.dtype == inner
+                       and v.ndim == 1 for v in seqs):
+                seqs = [np.ascontiguousarray(v, dtype=inner).ravel()
+                        for v in seqs]
+            sizes = np.fromiter(map(len, seqs), np.int64, len(seqs))
             pad = (-pool_base) % 16
             if pad:
                 pool.append(b'\0' * pad)
